@@ -1,0 +1,526 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the product.
+
+A CPU (torch fp32 / numpy) restatement of PhoreGen's sampling hot path, written
+from the reference's *behaviour*; every function cites the reference file:line it
+follows (paths relative to the reference repo root).  Only `tests/`,
+`__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may
+import this module; nothing under `phoregen_b200/` does.
+
+It evaluates the reference FORMULATION (materialised kv inputs, per-triplet q, k, v MLPs,
+no algebraic factorisation), so that it is both the parity checker and an honest "port"
+CPU baseline for the reference's PyTorch path.
+
+Parity pinning: the reference ships no tests or golden vectors.  This oracle
+is pinned against the UNMODIFIED reference modules imported through `oracle/shims`
+(`tests/test_oracle_vs_reference.py`, run where /root/reference exists) and against the
+fixtures that import generated (`tests/golden/*.pt`, made by `oracle/make_golden.py`).
+The third-party kernels the reference calls (torch_cluster 1.6.0 knn, torch_scatter 2.0.9,
+torch_sparse 0.6.15; `phoregen_env.yml:314-317`) are absent from the reference tree; their
+published semantics are restated here (see `knn_graph`).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+SMEAR_OFFSETS = (0, 1, 1.25, 1.5, 1.75, 2, 2.25, 2.5, 2.75, 3, 3.5, 4, 4.5, 5, 5.5, 6, 7, 8, 9, 10)
+ANGLE_FREQS = (1.0, 2.0, 3.0, 1.0, 1.0 / 2.0, 1.0 / 3.0)
+N_HEADS = 16
+
+
+# --------------------------------------------------------------------------- small blocks
+def gaussian_smearing(dist):
+    """models/common.py:11-31 — fixed 20 offsets, coeff = -0.5/(1-0)^2."""
+    off = torch.tensor(SMEAR_OFFSETS, dtype=torch.float32, device=dist.device)
+    d = dist.reshape(-1, 1) - off.view(1, -1)
+    return torch.exp(-0.5 * d * d)
+
+
+def time_smearing(t, coeff, offset):
+    """models/common.py:34-55 (type_='linear'); t float [R]."""
+    t = t.clamp(min=0.0).clamp(max=float(offset[-1]))
+    d = t.view(-1, 1) - offset.view(1, -1)
+    return torch.exp(coeff * d * d)
+
+
+def angular_encoding(theta):
+    """models/common.py:67-87: [theta, sin(theta*f), cos(theta*f)], f = 1,2,3,1,1/2,1/3."""
+    f = torch.tensor(ANGLE_FREQS, dtype=torch.float32, device=theta.device)
+    x = theta.unsqueeze(-1)
+    return torch.cat([x, torch.sin(x * f), torch.cos(x * f)], -1)
+
+
+def mlp(sd, p, x):
+    """models/common.py:99-119: Linear -> LayerNorm(eps 1e-5) -> ReLU -> Linear."""
+    h = F.linear(x, sd[p + ".net.0.weight"], sd[p + ".net.0.bias"])
+    h = F.layer_norm(h, (h.shape[-1],), sd[p + ".net.1.weight"], sd[p + ".net.1.bias"], 1e-5)
+    h = F.relu(h)
+    return F.linear(h, sd[p + ".net.3.weight"], sd[p + ".net.3.bias"])
+
+
+def seg_softmax(src, index, n):
+    """torch_scatter.scatter_softmax over dim 0 (max-shift, exp, sum, divide)."""
+    idx = index.view(-1, 1).expand_as(src)
+    mx = torch.full((n, src.shape[1]), float("-inf"), dtype=src.dtype)
+    mx.scatter_reduce_(0, idx, src, reduce="amax", include_self=True)
+    ex = (src - mx[index]).exp()
+    sm = torch.zeros((n, src.shape[1]), dtype=src.dtype).index_add_(0, index, ex)
+    return ex / sm[index]
+
+
+def seg_sum(src, index, n):
+    out = torch.zeros((n,) + tuple(src.shape[1:]), dtype=src.dtype)
+    return out.index_add_(0, index, src)
+
+
+# --------------------------------------------------------------------------- graph construction (integer artefacts)
+def sq_dist_f32(a, b):
+    """fp32 squared distance, summed in the order ((dx^2 + dy^2) + dz^2), no FMA contraction."""
+    d = (a.astype(np.float32) - b.astype(np.float32)).astype(np.float32)
+    s = (d[..., 0] * d[..., 0]).astype(np.float32)
+    s = (s + (d[..., 1] * d[..., 1]).astype(np.float32)).astype(np.float32)
+    s = (s + (d[..., 2] * d[..., 2]).astype(np.float32)).astype(np.float32)
+    return s
+
+
+def knn_graph(x, k, batch):
+    """PyG knn_graph(x, k, batch, loop=False, flow='source_to_target') as called at
+    models/uni_denoiser.py:355 and models/common.py:301 (torch_cluster 1.6.0 semantics):
+    per query node (dst) take the k+1 nearest nodes of the same graph by
+    (squared fp32 distance, index) ascending, then drop the self edge.  Output is grouped by
+    dst ascending; within a dst, src by ascending distance (ties: lower index first).
+    x: [N,3] float tensor, batch: [N] sorted long.  Returns [2,E] long (src, dst)."""
+    xn = x.detach().cpu().numpy().astype(np.float32)
+    bn = batch.detach().cpu().numpy()
+    N = xn.shape[0]
+    src_all, dst_all = [], []
+    starts = np.flatnonzero(np.r_[True, bn[1:] != bn[:-1]])
+    ends = np.r_[starts[1:], N]
+    for s, e in zip(starts, ends):
+        pts = xn[s:e]
+        d = sq_dist_f32(pts[:, None, :], pts[None, :, :])          # [q, cand]
+        order = np.argsort(d, axis=1, kind="stable")[:, : k + 1]
+        q = np.repeat(np.arange(e - s)[:, None], order.shape[1], 1)
+        keep = order != q
+        src_all.append(order[keep] + s)
+        dst_all.append(q[keep] + s)
+    if not src_all:
+        return torch.zeros(2, 0, dtype=torch.long)
+    return torch.from_numpy(np.stack([np.concatenate(src_all), np.concatenate(dst_all)]).astype(np.int64))
+
+
+def make_edge_data(num_atoms):
+    """utils/sample_utils.py:40-54 — sampling edge order: per molecule the upper-triangular
+    pairs (a<b) row-major as (src=a,dst=b), followed by the flipped copies."""
+    ei, eb, start = [], [], 0
+    for g, n in enumerate(int(v) for v in num_atoms):
+        a, b = np.triu_indices(n, k=1)
+        half = np.stack([a, b])
+        full = np.concatenate([half, half[::-1]], 1) + start
+        ei.append(full)
+        eb.append(np.full(full.shape[1], g))
+        start += n
+    return (torch.from_numpy(np.concatenate(ei, 1).astype(np.int64)),
+            torch.from_numpy(np.concatenate(eb).astype(np.int64)))
+
+
+def full_edges_dst_major(num_atoms):
+    """datasets/transform.py:488-501 (FeaturizeLigandBond) — training edge order: dst-major,
+    src ascending, self excluded.  Returned as (src,dst) = (f_edge_index[0], f_edge_index[1])."""
+    ei, eb, start = [], [], 0
+    for g, n in enumerate(int(v) for v in num_atoms):
+        dst = np.repeat(np.arange(n), n)
+        src = np.tile(np.arange(n), n)
+        m = dst != src
+        ei.append(np.stack([src[m], dst[m]]) + start)
+        eb.append(np.full(int(m.sum()), g))
+        start += n
+    return (torch.from_numpy(np.concatenate(ei, 1).astype(np.int64)),
+            torch.from_numpy(np.concatenate(eb).astype(np.int64)))
+
+
+def fully_connect_phore(batch_phore):
+    """models/common.py:329-356 with both arguments = batch_phore: per graph all p*p ordered
+    pairs INCLUDING self loops; row0 = i repeated p times, row1 = j cycling."""
+    bn = batch_phore.cpu().numpy()
+    out = []
+    for g in np.unique(bn):
+        idx = np.flatnonzero(bn == g)
+        p = idx.size
+        out.append(np.stack([np.repeat(idx, p), np.tile(idx, p)]))
+    return torch.from_numpy(np.concatenate(out, 1).astype(np.int64))
+
+
+def compose_context(batch_phore, batch_ligand):
+    """models/common.py:166-208 — stable sort of cat(batch_phore, batch_ligand): per graph the
+    phore rows then the ligand rows.  Returns sort_idx, batch_ctx, mask_ligand, p_index_in_ctx,
+    l_index_in_ctx."""
+    bc = torch.cat([batch_phore, batch_ligand])
+    sort_idx = torch.sort(bc, stable=True).indices
+    P = batch_phore.numel()
+    mask_ligand = (sort_idx >= P)
+    inv = torch.empty_like(sort_idx)
+    inv[sort_idx] = torch.arange(sort_idx.numel())
+    return sort_idx, bc[sort_idx], mask_ligand, inv[:P], inv[P:]
+
+
+def triplets(bond_index, num_nodes):
+    """models/uni_denoiser.py:101-121 — for every edge e=(j->i) all edges (k->j), k != i, ordered
+    by e then k ascending.  Returns idx_i, idx_j, idx_k, idx_kj, idx_ji (all [E3] long)."""
+    row, col = bond_index[0].numpy(), bond_index[1].numpy()      # j -> i
+    E = row.size
+    # incoming edges of every node, sorted by source
+    order = np.lexsort((row, col))                               # by dst, then src
+    dst_sorted = col[order]
+    ptr = np.searchsorted(dst_sorted, np.arange(num_nodes + 1))
+    I, J, K, KJ, JI = [], [], [], [], []
+    for e in range(E):
+        j, i = row[e], col[e]
+        inc = order[ptr[j]:ptr[j + 1]]                           # edges k -> j, k ascending
+        ks = row[inc]
+        m = ks != i
+        cnt = int(m.sum())
+        I.append(np.full(cnt, i)); J.append(np.full(cnt, j)); K.append(ks[m])
+        KJ.append(inc[m]); JI.append(np.full(cnt, e))
+    cat = lambda L: torch.from_numpy(np.concatenate(L).astype(np.int64)) if L else torch.zeros(0, dtype=torch.long)
+    return cat(I), cat(J), cat(K), cat(KJ), cat(JI)
+
+
+def build_edge_type(edge_index, mask_ligand):
+    """models/uni_denoiser.py:363-379: (src lig, dst lig) -> 0 ; (lig, phore) -> 1 ; (phore, lig) -> 2 ; pp -> 3."""
+    s, d = mask_ligand[edge_index[0]], mask_ligand[edge_index[1]]
+    t = torch.full((edge_index.shape[1],), 3, dtype=torch.long)
+    t[s & d] = 0
+    t[s & ~d] = 1
+    t[~s & d] = 2
+    return t
+
+
+# --------------------------------------------------------------------------- denoiser layers
+def node_update_layer(sd, p, h, edge_feat, edge_index, e_w=None):
+    """models/uni_denoiser.py:40-72 (out_fc=False)."""
+    N = h.shape[0]
+    src, dst = edge_index
+    kv = torch.cat([edge_feat, h[dst], h[src]], -1)
+    k = mlp(sd, p + ".hk_func", kv).view(-1, N_HEADS, 8)
+    v = mlp(sd, p + ".hv_func", kv)
+    if e_w is not None:
+        v = v * e_w.view(-1, 1)
+    v = v.view(-1, N_HEADS, 8)
+    q = mlp(sd, p + ".hq_func", h).view(-1, N_HEADS, 8)
+    alpha = seg_softmax((q[dst] * k / np.sqrt(8)).sum(-1), dst, N)
+    return seg_sum(alpha.unsqueeze(-1) * v, dst, N).view(N, 128)
+
+
+def pos_update_layer(sd, p, h, rel_x, edge_feat, edge_index, e_w=None):
+    """models/uni_denoiser.py:187-209."""
+    N = h.shape[0]
+    src, dst = edge_index
+    kv = torch.cat([edge_feat, h[dst], h[src]], -1)
+    k = mlp(sd, p + ".xk_func", kv).view(-1, N_HEADS, 8)
+    v = mlp(sd, p + ".xv_func", kv)
+    if e_w is not None:
+        v = v * e_w.view(-1, 1)
+    v = v.unsqueeze(-1) * rel_x.unsqueeze(1)
+    q = mlp(sd, p + ".xq_func", h).view(-1, N_HEADS, 8)
+    alpha = seg_softmax((q[dst] * k / np.sqrt(8)).sum(-1), dst, N)
+    return seg_sum(alpha.unsqueeze(-1) * v, dst, N).mean(1)
+
+
+def bond_update_layer(sd, p, h, h_bond, pos, bond_index, trip=None, chunk=200000):
+    """models/uni_denoiser.py:123-165 (include_h_node=True).  Evaluated in triplet chunks to bound
+    host memory; chunk boundaries are aligned to whole segments so the result is unchanged."""
+    N, E = h.shape[0], h_bond.shape[0]
+    j, i = bond_index                                             # row=j (src), col=i (dst)
+    if trip is None:
+        trip = triplets(bond_index, N)
+    idx_i, idx_j, idx_k, idx_kj, idx_ji = trip
+    dist = (pos[i] - pos[j]).pow(2).sum(-1).sqrt()
+    r_feat = gaussian_smearing(dist)
+    out = torch.zeros(E, 128)
+    E3 = idx_ji.numel()
+    s = 0
+    while s < E3:
+        e = min(E3, s + chunk)
+        if e < E3:                                                # align to segment boundary
+            last = idx_ji[e - 1]
+            while e < E3 and idx_ji[e] == last:
+                e += 1
+        sl = slice(s, e)
+        ti, tj, tk, tkj, tji = idx_i[sl], idx_j[sl], idx_k[sl], idx_kj[sl], idx_ji[sl]
+        pos_i = pos[ti]
+        pji, pki = pos[tj] - pos_i, pos[tk] - pos_i
+        a = (pji * pki).sum(-1)
+        b = torch.linalg.cross(pji, pki).norm(dim=-1)
+        a_feat = angular_encoding(torch.atan2(b, a))
+        kv = torch.cat([h_bond[tkj], r_feat[tkj], r_feat[tji], a_feat, h[tk], h[tj]], -1)
+        qi = torch.cat([h_bond[tji], h[ti]], -1)
+        k = mlp(sd, p + ".hk_func", kv).view(-1, N_HEADS, 8)
+        v = mlp(sd, p + ".hv_func", kv).view(-1, N_HEADS, 8)
+        q = mlp(sd, p + ".hq_func", qi).view(-1, N_HEADS, 8)
+        alpha = seg_softmax((q * k / np.sqrt(8)).sum(-1), tji, E)
+        out += seg_sum(alpha.unsqueeze(-1) * v, tji, E).view(E, 128)
+        s = e
+    return out
+
+
+def neib_norm(l_x, l_batch):
+    """models/common.py:300-304: mean of the 3 nearest ligand atoms minus the atom itself."""
+    ei = knn_graph(l_x, 3, l_batch)
+    n_src, n_dst = ei
+    sm = seg_sum(l_x[n_src], n_dst, l_x.shape[0])
+    cnt = seg_sum(torch.ones(n_src.numel(), 1), n_dst, l_x.shape[0]).clamp(min=1)
+    return sm / cnt - l_x
+
+
+def direction_feat(x, phore_norm, edge_index, mask_ligand, batch):
+    """models/common.py:307-326."""
+    comb = torch.zeros_like(x)
+    comb[~mask_ligand] = phore_norm
+    comb[mask_ligand] = neib_norm(x[mask_ligand], batch[mask_ligand])
+    src, dst = edge_index
+    v1, v2, v3 = comb[src], comb[dst], x[src] - x[dst]
+    return torch.stack([(v1 * v2).sum(-1), (v1 * v3).sum(-1), (v2 * v3).sum(-1)], -1)
+
+
+def attention_layer(sd, p, h, x, edge_type_onehot, edge_index, h_bond, bond_index, mask_ligand, e_w,
+                    phore_norm, batch, trip=None, stages=None):
+    """models/uni_denoiser.py:260-298."""
+    src, dst = edge_index
+    rel_x = x[dst] - x[src]
+    dist = torch.norm(rel_x, p=2, dim=-1, keepdim=True)
+    smear = gaussian_smearing(dist)                                # [E,20]
+    dist_feat = (edge_type_onehot.unsqueeze(-1) * smear.unsqueeze(1)).reshape(smear.shape[0], -1)   # common.py:156-163
+    edge_feat = torch.cat([dist_feat, edge_type_onehot], -1)
+    dire = direction_feat(x, phore_norm, edge_index, mask_ligand, batch)
+    dire = F.linear(dire, sd[p + ".dire_embedding.weight"], sd[p + ".dire_embedding.bias"])
+    edge_feat = torch.cat([edge_feat, dire], -1)
+    nh_e = node_update_layer(sd, p + ".node_layer_with_edge", h, edge_feat, edge_index, e_w)
+    nh_b = node_update_layer(sd, p + ".node_layer_with_bond", h, h_bond, bond_index)
+    new_h_bond = h_bond + bond_update_layer(sd, p + ".bond_layer", h, h_bond, x, bond_index, trip)
+    new_h = h + F.linear(nh_e + nh_b, sd[p + ".lin_node.weight"], sd[p + ".lin_node.bias"])
+    dx_e = pos_update_layer(sd, p + ".pos_layer_with_edge", new_h, rel_x, edge_feat, edge_index, e_w)
+    bs, bd = bond_index
+    dx_b = pos_update_layer(sd, p + ".pos_layer_with_bond", new_h, x[bd] - x[bs], new_h_bond, bond_index)
+    new_x = x + (dx_e + dx_b) * mask_ligand[:, None]
+    if stages is not None:
+        stages.append(dict(nh_e=nh_e, nh_b=nh_b, h=new_h, h_bond=new_h_bond, x=new_x, dx_e=dx_e, dx_b=dx_b))
+    return new_h, new_h_bond, new_x
+
+
+def denoiser_forward(sd, h, x, bond_index, h_bond, mask_ligand, batch, phore_norm, p="denoiser", k=32,
+                     num_layers=6, stages=None):
+    """models/uni_denoiser.py:396-430 (num_blocks=1, cutoff_mode='knn', use_global_ew)."""
+    edge_index = knn_graph(x, k, batch)
+    etype = build_edge_type(edge_index, mask_ligand)
+    et1h = F.one_hot(etype, 4).float()
+    src, dst = edge_index
+    dist = torch.norm(x[dst] - x[src], p=2, dim=-1, keepdim=True)
+    e_w = torch.sigmoid(mlp(sd, p + ".edge_pred_layer", gaussian_smearing(dist)))
+    trip = triplets(bond_index, h.shape[0])
+    if stages is not None:
+        stages.append(dict(knn_edge_index=edge_index, edge_type=etype, e_w=e_w))
+    for l in range(num_layers):
+        h, h_bond, x = attention_layer(sd, f"{p}.base_block.{l}", h, x, et1h, edge_index, h_bond, bond_index,
+                                       mask_ligand, e_w, phore_norm, batch, trip, stages)
+    return dict(x=x, h=h, h_bond=h_bond)
+
+
+def shifted_softplus_head(sd, p, x):
+    """models/diffusion.py:55-59,71-75; models/common.py:58-64."""
+    h = F.linear(x, sd[p + ".0.weight"], sd[p + ".0.bias"])
+    h = F.softplus(h) - math.log(2.0)
+    return F.linear(h, sd[p + ".2.weight"], sd[p + ".2.bias"])
+
+
+def phore_encode(sd, h_phore, pos_phore, batch_phore):
+    """models/diffusion.py:186-191."""
+    h = F.linear(h_phore, sd["phore_embedding.weight"], sd["phore_embedding.bias"])
+    ei = fully_connect_phore(batch_phore)
+    src, dst = ei
+    d = torch.norm(pos_phore[dst] - pos_phore[src], p=2, dim=-1, keepdim=True)
+    return node_update_layer(sd, "phore_encoder", h, d, ei)
+
+
+def predict_atom_count(sd, h_p, batch_p, raw_h_p, n_graphs):
+    """models/diffusion.py:148-163 (count_pred_type='boundary', data_name zinc_300/pdbbind)."""
+    def head(p, x):
+        y = F.relu(F.linear(x, sd[p + ".0.weight"], sd[p + ".0.bias"]))
+        return torch.sigmoid(F.linear(y, sd[p + ".2.weight"], sd[p + ".2.bias"]))
+
+    def gmean(v, b):
+        s = seg_sum(v, b, n_graphs)
+        c = seg_sum(torch.ones_like(v), b, n_graphs).clamp(min=1)
+        return s / c
+    c = gmean(head("atom_mlp", h_p), batch_p)
+    m = raw_h_p[:, 12] != 1
+    cl = gmean(head("atom_mlp_1", h_p[m]), batch_p[m])
+    return cl, cl + F.relu(c - cl)
+
+
+def phorediff_forward(sd, h_node_pert, pos_pert, batch_node, h_edge_pert, edge_index, batch_edge, time_step,
+                      h_phore, pos_phore, phore_norm, batch_phore, stages=None):
+    """models/diffusion.py:175-246 (bond_diffusion, bond_net_type='lin', hp_emb_with_pos)."""
+    coeff, offset = sd["time_emb.0.coeff"], sd["time_emb.0.offset"]
+    te_n = time_smearing(time_step[batch_node].float(), coeff, offset)
+    h_node = torch.cat([F.linear(h_node_pert, sd["node_embedder.weight"]), te_n], -1)
+    te_e = time_smearing(time_step[batch_edge].float(), coeff, offset)
+    h_ph = phore_encode(sd, h_phore, pos_phore, batch_phore)
+    sort_idx, batch_all, mask_ligand, p_idx, l_idx = compose_context(batch_phore, batch_node)
+    h_all = torch.cat([h_ph, h_node], 0)[sort_idx]
+    pos_all = torch.cat([pos_phore, pos_pert], 0)[sort_idx]
+    bond_all = l_idx[edge_index]
+    h_edge = torch.cat([F.linear(h_edge_pert, sd["edge_embedder.weight"]), te_e], -1)
+    if stages is not None:
+        stages.append(dict(h_phore_emb=h_ph, h_all=h_all, pos_all=pos_all, batch_all=batch_all,
+                           mask_ligand=mask_ligand, bond_index_in_all=bond_all, h_edge=h_edge))
+    out = denoiser_forward(sd, h_all, pos_all, bond_all, h_edge, mask_ligand, batch_all, phore_norm, stages=stages)
+    v = shifted_softplus_head(sd, "v_inference", out["h"][mask_ligand])
+    b = shifted_softplus_head(sd, "bond_inference", out["h_bond"])
+    n_graphs = int(time_step.numel())
+    cnt = predict_atom_count(sd, h_ph, batch_phore, h_phore, n_graphs)
+    return v, out["x"][mask_ligand], b, cnt
+
+
+# --------------------------------------------------------------------------- transitions
+def q_v_posterior(q_mats, tq_onestep, log_v0, log_vt, t, batch):
+    """models/transition.py:285-315 (v0_prob=True)."""
+    tb = t[batch]
+    tm1 = (tb - 1).clamp(min=0)
+    f1 = torch.einsum("bj,bjk->bk", log_vt.exp(), tq_onestep[tb])
+    f2 = torch.einsum("bj,bjk->bk", log_v0.exp(), q_mats[tm1])
+    out = torch.log(f1 + 1e-30).clamp_min(-32.0) + torch.log(f2 + 1e-30).clamp_min(-32.0)
+    out = out - torch.logsumexp(out, -1, keepdim=True)
+    return torch.where((tb == 0).unsqueeze(-1), log_v0, out)
+
+
+def log_sample_categorical(logits, uniform):
+    """models/common.py:425-431 with the uniform draw supplied."""
+    g = -torch.log(-torch.log(uniform + 1e-30) + 1e-30)
+    return (g + logits).argmax(-1)
+
+
+def pos_prev_from_recon(sd, x_t, x_recon, t, batch, noise, energy_grad=0.0):
+    """models/transition.py:44-63 with the normal draw supplied."""
+    tb = t[batch]
+    c0 = sd["pos_transition.coef_x0"][tb].unsqueeze(-1)
+    ct = sd["pos_transition.coef_xt"][tb].unsqueeze(-1)
+    sg = sd["pos_transition.std"][tb].unsqueeze(-1)
+    mu = c0 * x_recon + ct * x_t - energy_grad
+    return torch.where((tb == 0).unsqueeze(-1), mu, mu + sg * noise)
+
+
+def guidance_grad(pos, batch_node, edge_cls, edge_index, batch_edge, opts, phore_center, n_graphs):
+    """Closed-form gradient of the energies of utils/sample_utils.py:135-165 as combined at
+    models/diffusion.py:476-502 (gradient summed over drifts, applied unscaled).
+    edge_cls: [E_b] long class of the freshly sampled h_edge_prev (argmax of its one-hot)."""
+    g = torch.zeros_like(pos)
+    for drift in opts or []:
+        if drift["type"] == "atom_prox":
+            src, dst = edge_index
+            m = edge_cls > 0
+            if not bool(m.any()):
+                continue
+            d = pos[src] - pos[dst]
+            ln = d.norm(dim=-1)
+            sgn = (ln > drift["max_d"]).float() - (ln < drift["min_d"]).float()
+            cnt = seg_sum(m.float(), batch_edge, n_graphs)
+            w = torch.where(m, sgn / cnt[batch_edge].clamp(min=1), torch.zeros_like(sgn)) / n_graphs
+            unit = d / ln.clamp(min=1e-30).unsqueeze(-1)
+            gg = w.unsqueeze(-1) * unit
+            g = g.index_add(0, src, gg).index_add(0, dst, -gg)
+        elif drift["type"] == "center_prox":
+            n = seg_sum(torch.ones(pos.shape[0]), batch_node, n_graphs)
+            c = seg_sum(pos, batch_node, n_graphs) / n.unsqueeze(-1)
+            diff = c - phore_center.view(1, 3)
+            nr = diff.norm(dim=-1, keepdim=True)
+            u = diff / nr.clamp(min=1e-30)
+            g = g + (u / n.unsqueeze(-1) / n_graphs)[batch_node]
+    return g
+
+
+def init_log_prob(kind, K):
+    """models/transition.py:183-196,331-335."""
+    if kind == "absorb":
+        p = 0.01 * np.ones(K); p[0] = 1.0
+    elif kind == "tomask":
+        p = 0.001 * np.ones(K); p[-1] = 1.0
+    else:
+        p = np.ones(K)
+    p = p / p.sum()
+    return torch.log(torch.from_numpy(p) + 1e-30).clamp_min(-32.0)
+
+
+def reverse_step(sd, state, t_scalar, topo, phore, draws, guidance=None):
+    """One iteration of the loop body of models/diffusion.py:432-517 with the random draws supplied.
+    state: dict(h_node [Nl,12] one-hot, pos [Nl,3], h_edge [E,6] one-hot, log_node, log_edge)
+    topo : dict(batch_node, edge_index, batch_edge, n_graphs)
+    draws: dict(u_node [Nl,12], u_edge [E,6], z_pos [Nl,3])"""
+    G = topo["n_graphs"]
+    t = torch.full((G,), int(t_scalar), dtype=torch.long)
+    pn, pp, pe, _ = phorediff_forward(sd, state["h_node"], state["pos"], topo["batch_node"], state["h_edge"],
+                                      topo["edge_index"], topo["batch_edge"], t, phore["x"], phore["pos"],
+                                      phore["norm"], phore["batch"])
+    log_node = q_v_posterior(sd["node_transition.q_mats"], sd["node_transition.transpopse_q_onestep_mats"],
+                             F.log_softmax(pn, -1), state["log_node"], t, topo["batch_node"])
+    node_cls = log_sample_categorical(log_node, draws["u_node"])
+    log_edge = q_v_posterior(sd["edge_transition.q_mats"], sd["edge_transition.transpopse_q_onestep_mats"],
+                             F.log_softmax(pe, -1), state["log_edge"], t, topo["batch_edge"])
+    edge_cls = log_sample_categorical(log_edge, draws["u_edge"])
+    eg = 0.0
+    if guidance:
+        eg = guidance_grad(state["pos"], topo["batch_node"], edge_cls, topo["edge_index"], topo["batch_edge"],
+                           guidance["opts"], guidance["phore_center"], G)
+    pos_prev = pos_prev_from_recon(sd, state["pos"], pp, t, topo["batch_node"], draws["z_pos"], eg)
+    new_state = dict(h_node=F.one_hot(node_cls, 12).float(), pos=pos_prev,
+                     h_edge=F.one_hot(edge_cls, 6).float(), log_node=log_node, log_edge=log_edge)
+    return new_state, dict(pred_node=pn, pred_pos=pp, pred_edge=pe, node_cls=node_cls, edge_cls=edge_cls)
+
+
+# --------------------------------------------------------------------------- synthetic workloads
+def synthetic_phore(rng, p, n_ex=0):
+    """18-dim pharmacophore features as datasets/get_phore_data.py:55-70 builds them:
+    13-way type one-hot, alpha, has_norm one-hot(2), EX one-hot(2).  Non-EX types drawn from the 12
+    non-EX classes; n_ex extra exclusion spheres (type 12) appended."""
+    P = p + n_ex
+    types = np.r_[rng.integers(0, 12, size=p), np.full(n_ex, 12)]
+    x = np.zeros((P, 18), dtype=np.float32)
+    x[np.arange(P), types] = 1.0
+    x[:, 13] = np.r_[rng.uniform(0.5, 1.5, size=p), np.full(n_ex, 0.837)]
+    has_norm = np.r_[rng.integers(0, 2, size=p), np.zeros(n_ex, dtype=np.int64)]
+    x[np.arange(P), 14 + has_norm] = 1.0
+    is_ex = (types == 12).astype(np.int64)
+    x[np.arange(P), 16 + is_ex] = 1.0
+    pos = rng.normal(0.0, 4.0, size=(P, 3)).astype(np.float32)
+    pos -= pos.mean(0, keepdims=True)
+    nrm = rng.normal(size=(P, 3)).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm *= has_norm[:, None].astype(np.float32)
+    return x, pos, nrm.astype(np.float32)
+
+
+def synthetic_batch(seed, n_graphs, n_atoms=30, p_choices=(6, 7, 8), n_ex=0, edge_order="sampling"):
+    """Seeded synthetic ligand+pharmacophore batch in the reference's tensor layout (config[1] shapes).
+    n_atoms: int or (lo, hi) inclusive range."""
+    rng = np.random.default_rng(seed)
+    if isinstance(n_atoms, int):
+        na = np.full(n_graphs, n_atoms)
+    else:
+        na = rng.integers(n_atoms[0], n_atoms[1] + 1, size=n_graphs)
+    xs, ps, ns, bs = [], [], [], []
+    for g in range(n_graphs):
+        p = int(rng.choice(p_choices))
+        x, pos, nrm = synthetic_phore(rng, p, n_ex)
+        xs.append(x); ps.append(pos); ns.append(nrm); bs.append(np.full(x.shape[0], g))
+    phore = dict(x=torch.from_numpy(np.concatenate(xs)), pos=torch.from_numpy(np.concatenate(ps)),
+                 norm=torch.from_numpy(np.concatenate(ns)), batch=torch.from_numpy(np.concatenate(bs).astype(np.int64)))
+    Nl = int(na.sum())
+    batch_node = torch.from_numpy(np.repeat(np.arange(n_graphs), na).astype(np.int64))
+    ei, eb = make_edge_data(na) if edge_order == "sampling" else full_edges_dst_major(na)
+    node_cls = torch.from_numpy(rng.integers(0, 12, size=Nl).astype(np.int64))
+    edge_cls = torch.from_numpy(rng.integers(0, 6, size=ei.shape[1]).astype(np.int64))
+    pos = torch.from_numpy(rng.normal(0.0, 1.0, size=(Nl, 3)).astype(np.float32))
+    return dict(num_atoms=torch.from_numpy(na.astype(np.int64)), batch_node=batch_node, edge_index=ei,
+                batch_edge=eb, h_node=F.one_hot(node_cls, 12).float(), h_edge=F.one_hot(edge_cls, 6).float(),
+                pos=pos, phore=phore, n_graphs=n_graphs)

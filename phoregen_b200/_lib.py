@@ -1,0 +1,77 @@
+"""ctypes binding of libphoregen_b200.so (C ABI declared in include/phoregen_b200.h).
+
+There is no CPU fallback: if the library is missing the import raises, loudly.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_uint64, c_void_p, POINTER
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libphoregen_b200.so")
+
+
+class PhoreGenLibraryError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise PhoreGenLibraryError(
+            f"{LIB_PATH} is missing: build it with `python -m phoregen_b200.build` "
+            "(there is no CPU / PyTorch fallback for the hot path)")
+    return ctypes.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+_P = c_void_p
+_SIGS = {
+    "pg_version": (c_int, []),
+    "pg_last_error": (c_char_p, []),
+    "pg_weight_slot_count": (c_int, []),
+    "pg_weight_slot_name": (c_char_p, [c_int]),
+    "pg_weight_slot_numel": (c_int64, [c_int]),
+    "pg_model_create": (c_int, [POINTER(_P), _P, POINTER(c_int64), c_int]),
+    "pg_model_destroy": (None, [_P]),
+    "pg_plan_workspace_bytes": (c_int64, [c_int, POINTER(c_int32), POINTER(c_int32)]),
+    "pg_plan_create": (c_int, [POINTER(_P), c_int, POINTER(c_int32), POINTER(c_int32), c_int, _P, _P, c_int64, _P]),
+    "pg_plan_destroy": (None, [_P]),
+    "pg_plan_num_ligand_atoms": (c_int64, [_P]),
+    "pg_plan_num_phore_nodes": (c_int64, [_P]),
+    "pg_plan_num_bond_edges": (c_int64, [_P]),
+    "pg_plan_num_knn_edges": (c_int64, [_P]),
+    "pg_plan_num_triplets": (c_int64, [_P]),
+    "pg_plan_export_bond_edges": (c_int, [_P, _P, _P, _P]),
+    "pg_plan_export_triplets": (c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "pg_knn_graph": (c_int, [_P, _P, c_int, _P, _P]),
+    "pg_denoiser_forward": (c_int, [_P] * 10),
+    "pg_phore_encode": (c_int, [_P] * 6),
+    "pg_phorediff_forward": (c_int, [_P] * 13),
+    "pg_categorical_step": (c_int, [c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_uint64, c_uint32, _P, _P, _P, _P, _P]),
+    "pg_position_step": (c_int, [c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_uint64, c_uint32, _P, _P, _P, _P, _P]),
+    "pg_guidance_grad": (c_int, [_P, _P, _P, c_int, c_float, c_float, _P, _P, _P]),
+    "pg_plan_ligand_graph": (_P, [_P]),
+    "pg_plan_edge_graph": (_P, [_P]),
+    "pg_plan_kernel_launches": (c_int64, [_P]),
+}
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(lib, _name)          # AttributeError here = header/library drift; never silently ignored
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+
+def last_error():
+    msg = lib.pg_last_error()
+    return msg.decode() if msg else ""
+
+
+def check(rc, what):
+    if rc != 0:
+        raise PhoreGenLibraryError(f"{what} failed (code {rc}): {last_error()}")
+
+
+def slot_table():
+    n = lib.pg_weight_slot_count()
+    return [(lib.pg_weight_slot_name(i).decode(), int(lib.pg_weight_slot_numel(i))) for i in range(n)]

@@ -1,0 +1,57 @@
+#pragma once
+#include "pg_common.cuh"
+
+// Weights of one attention sub-layer (pointers into the packed blob).
+struct AttnW {
+    const float *tab_k, *tab_v;                   // kNN: [4][24][128]; phore encoder: [128] distance column
+    const float *lnk_g, *lnk_b, *lnv_g, *lnv_b;   // LayerNorm of the key / value MLPs
+    const float *w2k, *b2k;                       // key MLP second Linear   [128 out][128 in], [128]
+    const float *w2v, *b2v;                       // value MLP second Linear [128|16 out][128 in], [128|16]
+};
+
+struct NodeCols {            // column offsets inside the node-GEMM output (row stride lda)
+    const float* A; long long lda;
+    int dst_k, src_k, dst_v, src_v;
+};
+
+struct KnnAttnArgs {
+    PlanDev d;
+    const float* x;          // [N,3] context coordinates (FEAT 0) / pharmacophore positions [P,3] (FEAT 1)
+    const float* comb;       // [N,3] direction vectors (FEAT 0)
+    const int* knn_src;      // [Ek]
+    const float* ew;         // [Ek]
+    NodeCols nc;
+    const float* q;          // [rows,128]
+    AttnW w;
+    float* out;              // node mode [rows,128]; pos mode [rows,3]
+    int maxr;
+};
+
+struct BondAttnArgs {
+    PlanDev d;
+    const float* x;          // [N,3]
+    NodeCols nc;
+    const float* B; long long ldb; int b_k, b_v;   // per-edge partial pre-activations (edge GEMM output)
+    const float* q;          // [N,128]
+    AttnW w;
+    float* out;              // node mode [N,128]; pos mode [N,3]
+    int maxr;
+};
+
+struct TripArgs {
+    PlanDev d;
+    const float* x;
+    const float* T; long long ldt; int t_k, t_v;   // h_bond @ Wb (edge GEMM output)
+    const float* H; long long ldh; int hk_k, hj_k, hk_v, hj_v;   // node GEMM output (h @ Whk, h @ Whj + b1)
+    const float* q;          // [Eb,128] per-edge query
+    const float *wrkj, *wrji, *wa;   // [20][256], [20][256], [13][256]  (k | v along the 256 axis)
+    AttnW w;
+    float* hb;               // [Eb,128] updated in place: hb += attention output
+    int maxr, maxn;
+};
+
+int pg_launch_knn_attn(const KnnAttnArgs& a, int feat, int pos, cudaStream_t s);
+int pg_launch_bond_attn(const BondAttnArgs& a, int pos, cudaStream_t s);
+int pg_launch_trip(const TripArgs& a, cudaStream_t s);
+int pg_launch_edge_weight(const PlanDev& d, const float* x, const int* knn_src, const float* w1t, const float* b1,
+                          const float* g, const float* b, const float* w2, const float* b2, float* ew, cudaStream_t s);

@@ -1,0 +1,20 @@
+#pragma once
+#include "pg_common.cuh"
+
+enum { PRO_PLAIN = 0, PRO_SUM2 = 1, PRO_LNRELU = 2 };
+
+struct GemmArgs {
+    long long M;
+    const float* A; long long lda;       // input rows (first 128 columns starting at A)
+    const float* A2; long long lda2;     // SUM2: second input; LNRELU: optional gather-add rows A2[gidx[m]]
+    const int* gidx;                     // optional row gather for A2
+    const float* ln_g; const float* ln_b;
+    const float* Wt; long long ldw;      // [128][ldw] (k-major); column block nt starts at nt*128
+    const float* bias;                   // [ntiles*128] or null
+    float* C; long long ldc;
+    int ntiles;
+    const float* resid; long long ldr;   // optional residual added in the epilogue (may alias C)
+    int relu;
+};
+
+int pg_launch_gemm(const GemmArgs& a, int pro, cudaStream_t stream);

@@ -1,0 +1,421 @@
+// Packed-weight slot table, embedding / head kernels and the forward orchestration
+// (call stack §3.2).
+#include <string.h>
+#include <string>
+#include "pg_attn.h"
+#include "pg_gemm.h"
+#include "pg_plan.h"
+
+int pg_launch_knn(PgPlan* p, const float* x, const float* phore_norm, int mode, int* knn_src, float* comb,
+                  int64_t* ei, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------ slots
+namespace {
+const char* kSub[5] = {"nk", "nb", "tr", "pk", "pb"};   // node-kNN, node-bond, triplet, pos-kNN, pos-bond
+
+std::vector<PgSlotDesc> build_slots() {
+    std::vector<PgSlotDesc> v;
+    auto add = [&](const std::string& n, long long numel) {
+        PgSlotDesc s;
+        memset(&s, 0, sizeof(s));
+        strncpy(s.name, n.c_str(), sizeof(s.name) - 1);
+        s.numel = numel;
+        v.push_back(s);
+    };
+    add("G.node_emb_t", 12 * 118); add("G.edge_emb_t", 6 * 118);
+    add("G.time_coeff", 10); add("G.time_offset", 10);
+    add("G.ph_emb_wt", 18 * 128); add("G.ph_emb_b", 128);
+    add("PE.wcat_t", 128 * 640); add("PE.bcat", 640);
+    add("PE.wd_k", 128); add("PE.wd_v", 128);
+    add("PE.lnk_g", 128); add("PE.lnk_b", 128); add("PE.lnv_g", 128); add("PE.lnv_b", 128);
+    add("PE.lnq_g", 128); add("PE.lnq_b", 128); add("PE.w2q_t", 128 * 128); add("PE.b2q", 128);
+    add("PE.w2k", 128 * 128); add("PE.b2k", 128); add("PE.w2v", 128 * 128); add("PE.b2v", 128);
+    add("G.ew.w1t", 20 * 128); add("G.ew.b1", 128); add("G.ew.ln_g", 128); add("G.ew.ln_b", 128);
+    add("G.ew.w2", 128); add("G.ew.b2", 4);
+    add("G.vinf.w1t", 128 * 128); add("G.vinf.b1", 128); add("G.vinf.w2", 12 * 128); add("G.vinf.b2", 12);
+    add("G.binf.w1t", 128 * 128); add("G.binf.b1", 128); add("G.binf.w2", 6 * 128); add("G.binf.b2", 8);
+    for (int l = 0; l < PG_NUM_LAYERS; l++) {
+        std::string L = "L" + std::to_string(l) + ".";
+        add(L + "n1.wt", 128 * 1920); add(L + "n1.b", 1920);
+        add(L + "e1.wt", 128 * 640); add(L + "e1.b", 640);
+        add(L + "n2.wt", 128 * 1280); add(L + "n2.b", 1280);
+        add(L + "e2.wt", 128 * 256); add(L + "e2.b", 256);
+        add(L + "lin.wt", 128 * 128); add(L + "lin.b", 128);
+        for (int s = 0; s < 5; s++) {
+            std::string S = L + kSub[s] + ".";
+            add(S + "lnq_g", 128); add(S + "lnq_b", 128); add(S + "w2q_t", 128 * 128); add(S + "b2q", 128);
+            add(S + "lnk_g", 128); add(S + "lnk_b", 128); add(S + "lnv_g", 128); add(S + "lnv_b", 128);
+            add(S + "w2k", 128 * 128); add(S + "b2k", 128);
+            const bool pos = s >= 3;
+            add(S + "w2v", (pos ? 16 : 128) * 128); add(S + "b2v", pos ? 16 : 128);
+            if (s == 0 || s == 3) { add(S + "tab_k", 4 * 24 * 128); add(S + "tab_v", 4 * 24 * 128); }
+            if (s == 2) { add(S + "wrkj", 20 * 256); add(S + "wrji", 20 * 256); add(S + "wa", 13 * 256); }
+        }
+    }
+    return v;
+}
+}  // namespace
+
+const std::vector<PgSlotDesc>& pg_slot_table() {
+    static std::vector<PgSlotDesc> t = build_slots();
+    return t;
+}
+int pg_slot_index(const char* name) {
+    const auto& t = pg_slot_table();
+    for (size_t i = 0; i < t.size(); i++)
+        if (!strcmp(t[i].name, name)) return (int)i;
+    return -1;
+}
+extern "C" int pg_weight_slot_count(void) { return (int)pg_slot_table().size(); }
+extern "C" const char* pg_weight_slot_name(int s) {
+    const auto& t = pg_slot_table();
+    return (s < 0 || s >= (int)t.size()) ? nullptr : t[s].name;
+}
+extern "C" int64_t pg_weight_slot_numel(int s) {
+    const auto& t = pg_slot_table();
+    return (s < 0 || s >= (int)t.size()) ? -1 : t[s].numel;
+}
+extern "C" int pg_model_create(PgModel** out, const float* d_blob, const int64_t* h_offsets, int n_slots) {
+    if (!out || !d_blob || !h_offsets || n_slots != pg_weight_slot_count()) { pg_set_error("pg_model_create: expected %d slots", pg_weight_slot_count()); return PG_EINVAL; }
+    for (int i = 0; i < n_slots; i++)
+        if (h_offsets[i] < 0 || (h_offsets[i] & 3)) { pg_set_error("slot %d offset must be a non-negative multiple of 4 floats", i); return PG_EINVAL; }
+    if (((uintptr_t)d_blob & 15) != 0) { pg_set_error("weight blob must be 16-byte aligned"); return PG_EINVAL; }
+    PgModel* m = new PgModel();
+    m->blob = d_blob;
+    m->off.assign(h_offsets, h_offsets + n_slots);
+    *out = m;
+    return PG_OK;
+}
+extern "C" void pg_model_destroy(PgModel* m) { delete m; }
+
+namespace {
+struct W {   // named slot lookup, cached per model instance lifetime is unnecessary: lookups are cheap string compares
+    const PgModel* m;
+    const float* operator()(const std::string& name) const {
+        int i = pg_slot_index(name.c_str());
+        return i < 0 ? nullptr : m->w(i);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ small kernels
+// time embedding (common.py:34-55, type_='linear'): exp(coeff_g * (clamp(t) - offset_g)^2)
+__device__ __forceinline__ float time_feat(float t, const float* coeff, const float* offset, int gq) {
+    t = fminf(fmaxf(t, 0.f), offset[9]);
+    const float dlt = t - offset[gq];
+    return expf(coeff[gq] * dlt * dlt);
+}
+
+// context rows (diffusion.py:180-181,193-200): ligand row = [node_embedder(h_node) (118) | time (10)], phore row = encoder output
+__global__ void __launch_bounds__(256) embed_nodes_kernel(PlanDev d, const float* __restrict__ h_node, const float* __restrict__ pos,
+                                                          const int64_t* __restrict__ tstep, const float* __restrict__ h_ph,
+                                                          const float* __restrict__ pos_ph, const float* __restrict__ wn_t,
+                                                          const float* __restrict__ tcoef, const float* __restrict__ toff,
+                                                          float* __restrict__ h, float* __restrict__ x) {
+    const int lane = threadIdx.x & 31;
+    const int v = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (v >= d.N) return;
+    const int g = d.node_graph[v];
+    const int loc = v - d.ctx_off[g], p = d.g_p[g];
+    if (loc < p) {
+        const int pi = d.ph_off[g] + loc;
+        st4(h + (size_t)v * 128 + lane * 4, ldg4(h_ph + (size_t)pi * 128 + lane * 4));
+        if (lane < 3) x[(size_t)v * 3 + lane] = pos_ph[(size_t)pi * 3 + lane];
+    } else {
+        const int ai = d.lig_off[g] + loc - p;
+        const float t = (float)tstep[g];
+        float hv[12];
+#pragma unroll
+        for (int c = 0; c < 12; c++) hv[c] = h_node[(size_t)ai * 12 + c];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int o = lane * 4 + i;
+            float acc;
+            if (o < 118) {
+                acc = 0.f;
+#pragma unroll
+                for (int c = 0; c < 12; c++) acc = fmaf(hv[c], __ldg(wn_t + c * 118 + o), acc);
+            } else {
+                acc = time_feat(t, tcoef, toff, o - 118);
+            }
+            h[(size_t)v * 128 + o] = acc;
+        }
+        if (lane < 3) x[(size_t)v * 3 + lane] = pos[(size_t)ai * 3 + lane];
+    }
+}
+
+// bond rows (diffusion.py:183,205): [edge_embedder(h_edge) (118) | time (10)], scattered to the internal edge order
+__global__ void __launch_bounds__(256) embed_edges_kernel(PlanDev d, const float* __restrict__ h_edge, const int64_t* __restrict__ tstep,
+                                                          const float* __restrict__ we_t, const float* __restrict__ tcoef,
+                                                          const float* __restrict__ toff, float* __restrict__ hb) {
+    const int lane = threadIdx.x & 31;
+    const long long e = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);   // reference-order edge
+    if (e >= d.Eb) return;
+    const float t = (float)tstep[d.edge_graph[e]];
+    const long long slot = d.perm[e];
+    float hv[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) hv[c] = h_edge[(size_t)e * 6 + c];
+    float4 o4;
+    float* op = &o4.x;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int o = lane * 4 + i;
+        float acc;
+        if (o < 118) {
+            acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 6; c++) acc = fmaf(hv[c], __ldg(we_t + c * 118 + o), acc);
+        } else {
+            acc = time_feat(t, tcoef, toff, o - 118);
+        }
+        op[i] = acc;
+    }
+    st4(hb + (size_t)slot * 128 + lane * 4, o4);
+}
+
+// phore_embedding Linear(18 -> 128) (diffusion.py:186)
+__global__ void __launch_bounds__(256) phore_embed_kernel(int P, const float* __restrict__ xph, const float* __restrict__ wt,
+                                                          const float* __restrict__ b, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int v = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (v >= P) return;
+    float4 acc = ldg4(b + lane * 4);
+#pragma unroll
+    for (int c = 0; c < PG_PHORE_FEAT; c++) acc = f4fma(xph[(size_t)v * PG_PHORE_FEAT + c], ldg4(wt + c * 128 + lane * 4), acc);
+    st4(out + (size_t)v * 128 + lane * 4, acc);
+}
+
+// rows of a [*,128] matrix permuted between reference and internal edge order
+__global__ void __launch_bounds__(256) permute_rows_kernel(long long rows, const int* __restrict__ perm, const float* __restrict__ src,
+                                                           float* __restrict__ dst, int scatter) {
+    const int lane = threadIdx.x & 31;
+    const long long e = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (e >= rows) return;
+    const long long s = perm[e];
+    if (scatter) st4(dst + (size_t)s * 128 + lane * 4, ld4(src + (size_t)e * 128 + lane * 4));   // dst[perm[e]] = src[e]
+    else st4(dst + (size_t)e * 128 + lane * 4, ld4(src + (size_t)s * 128 + lane * 4));           // dst[e] = src[perm[e]]
+}
+
+// x += (dx1 + dx2) * mask_ligand  (uni_denoiser.py:295-296)
+__global__ void pos_update_kernel(PlanDev d, float* __restrict__ x, const float* __restrict__ dx1, const float* __restrict__ dx2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.N * 3) return;
+    const int v = i / 3;
+    const int g = d.node_graph[v];
+    if (v - d.ctx_off[g] >= d.g_p[g]) x[i] += dx1[i] + dx2[i];
+}
+
+// second half of the output heads (diffusion.py:55-59,71-75): out = W2 . (softplus(hid) - ln 2) + b2 ; warp per row.
+// ROWSEL 0: ligand atoms (row a -> context node), also emits the atom's final position; 1: reference-order edges.
+template <int K, int ROWSEL>
+__global__ void __launch_bounds__(256) head_out_kernel(PlanDev d, const float* __restrict__ hid, const float* __restrict__ w2,
+                                                       const float* __restrict__ b2, float* __restrict__ out,
+                                                       const float* __restrict__ x, float* __restrict__ x_out) {
+    const int lane = threadIdx.x & 31;
+    const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const long long rows = ROWSEL == 0 ? d.Nl : d.Eb;
+    if (r >= rows) return;
+    long long srow;
+    if (ROWSEL == 0) {
+        const int g = d.lig_graph[r];
+        srow = d.ctx_off[g] + d.g_p[g] + (r - d.lig_off[g]);
+        if (x_out && lane < 3) x_out[r * 3 + lane] = x[srow * 3 + lane];
+    } else {
+        srow = d.perm[r];
+    }
+    float4 v = ld4(hid + (size_t)srow * 128 + lane * 4);
+    auto ssp = [](float t) { return (t > 20.f ? t : log1pf(expf(t))) - 0.69314718055994531f; };
+    v = make_float4(ssp(v.x), ssp(v.y), ssp(v.z), ssp(v.w));
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const float s = warp_sum(f4dot(v, ldg4(w2 + k * 128 + lane * 4)));
+        if (lane == 0) out[r * K + k] = s + __ldg(b2 + k);
+    }
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ orchestration
+namespace {
+#define PG_TRY(expr)              \
+    do {                          \
+        int _r = (expr);          \
+        if (_r != PG_OK) return _r; \
+    } while (0)
+
+inline int round4(int v) { return (v + 3) & ~3; }
+
+int gemm(PgPlan* p, cudaStream_t s, int pro, long long M, const float* A, long long lda, const float* Wt, long long ldw,
+         const float* bias, float* C, long long ldc, int ntiles, const float* A2 = nullptr, long long lda2 = 0,
+         const int* gidx = nullptr, const float* lng = nullptr, const float* lnb = nullptr, const float* resid = nullptr,
+         long long ldr = 0) {
+    GemmArgs a;
+    a.M = M; a.A = A; a.lda = lda; a.A2 = A2; a.lda2 = lda2; a.gidx = gidx; a.ln_g = lng; a.ln_b = lnb;
+    a.Wt = Wt; a.ldw = ldw; a.bias = bias; a.C = C; a.ldc = ldc; a.ntiles = ntiles; a.resid = resid; a.ldr = ldr; a.relu = 0;
+    p->launches++;
+    return pg_launch_gemm(a, pro, s);
+}
+
+AttnW attn_w(const W& w, const std::string& S, bool tabs) {
+    AttnW a;
+    a.tab_k = tabs ? w(S + "tab_k") : nullptr; a.tab_v = tabs ? w(S + "tab_v") : nullptr;
+    a.lnk_g = w(S + "lnk_g"); a.lnk_b = w(S + "lnk_b"); a.lnv_g = w(S + "lnv_g"); a.lnv_b = w(S + "lnv_b");
+    a.w2k = w(S + "w2k"); a.b2k = w(S + "b2k"); a.w2v = w(S + "w2v"); a.b2v = w(S + "b2v");
+    return a;
+}
+
+// column blocks of the packed node GEMMs (must match phoregen_b200/weights.py)
+enum { N1_NK_DK = 0, N1_NK_SK = 128, N1_NK_DV = 256, N1_NK_SV = 384, N1_NK_Q = 512, N1_NB_DK = 640, N1_NB_SK = 768,
+       N1_NB_DV = 896, N1_NB_SV = 1024, N1_NB_Q = 1152, N1_TR_HK_K = 1280, N1_TR_HJ_K = 1408, N1_TR_HK_V = 1536,
+       N1_TR_HJ_V = 1664, N1_TR_Q = 1792, N1_COLS = 1920 };
+enum { E1_NB_K = 0, E1_NB_V = 128, E1_TR_K = 256, E1_TR_V = 384, E1_TR_Q = 512, E1_COLS = 640 };
+enum { N2_PK_DK = 0, N2_PK_SK = 128, N2_PK_DV = 256, N2_PK_SV = 384, N2_PK_Q = 512, N2_PB_DK = 640, N2_PB_SK = 768,
+       N2_PB_DV = 896, N2_PB_SV = 1024, N2_PB_Q = 1152, N2_COLS = 1280 };
+
+// the 6-layer denoiser on the plan's internal buffers h / x / hb (uni_denoiser.py:396-430)
+int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStream_t s) {
+    const PlanDev& d = p->d;
+    const W w{m};
+    const long long N = d.N, Eb = d.Eb;
+    PG_CUDA_CHECK(cudaMemsetAsync(p->o2, 0, (size_t)N * 128 * sizeof(float), s));
+    PG_CUDA_CHECK(cudaMemsetAsync(p->dx2, 0, (size_t)N * 3 * sizeof(float), s));
+    PG_TRY(pg_launch_knn(p, p->x, nullptr, 0, p->knn_src, nullptr, nullptr, s));
+    PG_TRY(pg_launch_edge_weight(d, p->x, p->knn_src, w("G.ew.w1t"), w("G.ew.b1"), w("G.ew.ln_g"), w("G.ew.ln_b"),
+                                 w("G.ew.w2"), w("G.ew.b2"), p->ew, s));
+    p->launches++;
+    const int maxr_knn = round4(std::min(PG_KNN, d.max_ng - 1));
+    const int maxr_bond = round4(d.max_n - 1);
+    const int maxr_trip = round4(std::max(d.max_n - 2, 1));
+    for (int l = 0; l < PG_NUM_LAYERS; l++) {
+        const std::string L = "L" + std::to_string(l) + ".";
+        // direction vectors (k=3 ligand kNN) of this layer's coordinates
+        PG_TRY(pg_launch_knn(p, p->x, phore_norm, 1, nullptr, p->comb, nullptr, s));
+        // first Linear of every MLP, node and bond parts
+        PG_TRY(gemm(p, s, PRO_PLAIN, N, p->h, 128, w(L + "n1.wt"), N1_COLS, w(L + "n1.b"), p->nbuf, N1_COLS, N1_COLS / 128));
+        PG_TRY(gemm(p, s, PRO_PLAIN, Eb, p->hb, 128, w(L + "e1.wt"), E1_COLS, w(L + "e1.b"), p->ebuf, E1_COLS, E1_COLS / 128));
+        // queries: LN -> ReLU -> second Linear
+        PG_TRY(gemm(p, s, PRO_LNRELU, N, p->nbuf + N1_NK_Q, N1_COLS, w(L + "nk.w2q_t"), 128, w(L + "nk.b2q"), p->qn1, 128, 1,
+                    nullptr, 0, nullptr, w(L + "nk.lnq_g"), w(L + "nk.lnq_b")));
+        PG_TRY(gemm(p, s, PRO_LNRELU, N, p->nbuf + N1_NB_Q, N1_COLS, w(L + "nb.w2q_t"), 128, w(L + "nb.b2q"), p->qn2, 128, 1,
+                    nullptr, 0, nullptr, w(L + "nb.lnq_g"), w(L + "nb.lnq_b")));
+        PG_TRY(gemm(p, s, PRO_LNRELU, Eb, p->ebuf + E1_TR_Q, E1_COLS, w(L + "tr.w2q_t"), 128, w(L + "tr.b2q"), p->qt, 128, 1,
+                    p->nbuf + N1_TR_Q, N1_COLS, d.edst_node, w(L + "tr.lnq_g"), w(L + "tr.lnq_b")));
+        {   // node update over the kNN graph
+            KnnAttnArgs a;
+            a.d = d; a.x = p->x; a.comb = p->comb; a.knn_src = p->knn_src; a.ew = p->ew;
+            a.nc = NodeCols{p->nbuf, N1_COLS, N1_NK_DK, N1_NK_SK, N1_NK_DV, N1_NK_SV};
+            a.q = p->qn1; a.w = attn_w(w, L + "nk.", true); a.out = p->o1; a.maxr = maxr_knn;
+            PG_TRY(pg_launch_knn_attn(a, 0, 0, s)); p->launches++;
+        }
+        {   // node update over the bond graph
+            BondAttnArgs a;
+            a.d = d; a.x = p->x;
+            a.nc = NodeCols{p->nbuf, N1_COLS, N1_NB_DK, N1_NB_SK, N1_NB_DV, N1_NB_SV};
+            a.B = p->ebuf; a.ldb = E1_COLS; a.b_k = E1_NB_K; a.b_v = E1_NB_V;
+            a.q = p->qn2; a.w = attn_w(w, L + "nb.", false); a.out = p->o2; a.maxr = maxr_bond;
+            PG_TRY(pg_launch_bond_attn(a, 0, s)); p->launches++;
+        }
+        {   // bond update over triplets (uses the old h, x); h_bond updated in place
+            TripArgs a;
+            a.d = d; a.x = p->x; a.T = p->ebuf; a.ldt = E1_COLS; a.t_k = E1_TR_K; a.t_v = E1_TR_V;
+            a.H = p->nbuf; a.ldh = N1_COLS; a.hk_k = N1_TR_HK_K; a.hj_k = N1_TR_HJ_K; a.hk_v = N1_TR_HK_V; a.hj_v = N1_TR_HJ_V;
+            a.q = p->qt; a.wrkj = w(L + "tr.wrkj"); a.wrji = w(L + "tr.wrji"); a.wa = w(L + "tr.wa");
+            a.w = attn_w(w, L + "tr.", false); a.hb = p->hb; a.maxr = maxr_trip; a.maxn = d.max_n;
+            PG_TRY(pg_launch_trip(a, s)); p->launches++;
+        }
+        // h <- h + lin_node(o1 + o2)
+        PG_TRY(gemm(p, s, PRO_SUM2, N, p->o1, 128, w(L + "lin.wt"), 128, w(L + "lin.b"), p->h, 128, 1, p->o2, 128, nullptr,
+                    nullptr, nullptr, p->h, 128));
+        // position update with the new h / h_bond and the old coordinates
+        PG_TRY(gemm(p, s, PRO_PLAIN, N, p->h, 128, w(L + "n2.wt"), N2_COLS, w(L + "n2.b"), p->nbuf, N2_COLS, N2_COLS / 128));
+        PG_TRY(gemm(p, s, PRO_PLAIN, Eb, p->hb, 128, w(L + "e2.wt"), 256, w(L + "e2.b"), p->ebuf, 256, 2));
+        PG_TRY(gemm(p, s, PRO_LNRELU, N, p->nbuf + N2_PK_Q, N2_COLS, w(L + "pk.w2q_t"), 128, w(L + "pk.b2q"), p->qn1, 128, 1,
+                    nullptr, 0, nullptr, w(L + "pk.lnq_g"), w(L + "pk.lnq_b")));
+        PG_TRY(gemm(p, s, PRO_LNRELU, N, p->nbuf + N2_PB_Q, N2_COLS, w(L + "pb.w2q_t"), 128, w(L + "pb.b2q"), p->qn2, 128, 1,
+                    nullptr, 0, nullptr, w(L + "pb.lnq_g"), w(L + "pb.lnq_b")));
+        {
+            KnnAttnArgs a;
+            a.d = d; a.x = p->x; a.comb = p->comb; a.knn_src = p->knn_src; a.ew = p->ew;
+            a.nc = NodeCols{p->nbuf, N2_COLS, N2_PK_DK, N2_PK_SK, N2_PK_DV, N2_PK_SV};
+            a.q = p->qn1; a.w = attn_w(w, L + "pk.", true); a.out = p->dx1; a.maxr = maxr_knn;
+            PG_TRY(pg_launch_knn_attn(a, 0, 1, s)); p->launches++;
+        }
+        {
+            BondAttnArgs a;
+            a.d = d; a.x = p->x;
+            a.nc = NodeCols{p->nbuf, N2_COLS, N2_PB_DK, N2_PB_SK, N2_PB_DV, N2_PB_SV};
+            a.B = p->ebuf; a.ldb = 256; a.b_k = 0; a.b_v = 128;
+            a.q = p->qn2; a.w = attn_w(w, L + "pb.", false); a.out = p->dx2; a.maxr = maxr_bond;
+            PG_TRY(pg_launch_bond_attn(a, 1, s)); p->launches++;
+        }
+        pos_update_kernel<<<(unsigned)((N * 3 + 255) / 256), 256, 0, s>>>(d, p->x, p->dx1, p->dx2);
+        PG_LAUNCH_CHECK(); p->launches++;
+    }
+    return PG_OK;
+}
+}  // namespace
+
+extern "C" int pg_phore_encode(const PgModel* m, PgPlan* p, const float* d_h_phore, const float* d_pos_phore, float* d_out,
+                               void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const PlanDev& d = p->d;
+    const W w{m};
+    if (d.max_p > 256) { pg_set_error("phore encoder: more than 256 pharmacophore nodes per graph"); return PG_ELIMIT; }
+    phore_embed_kernel<<<(unsigned)((d.P + 7) / 8), 256, 0, s>>>(d.P, d_h_phore, w("G.ph_emb_wt"), w("G.ph_emb_b"), p->pemb);
+    PG_LAUNCH_CHECK(); p->launches++;
+    PG_TRY(gemm(p, s, PRO_PLAIN, d.P, p->pemb, 128, w("PE.wcat_t"), 640, w("PE.bcat"), p->pbuf, 640, 5));
+    PG_TRY(gemm(p, s, PRO_LNRELU, d.P, p->pbuf + 512, 640, w("PE.w2q_t"), 128, w("PE.b2q"), p->pq, 128, 1, nullptr, 0, nullptr,
+                w("PE.lnq_g"), w("PE.lnq_b")));
+    KnnAttnArgs a;
+    a.d = d; a.x = d_pos_phore; a.comb = nullptr; a.knn_src = nullptr; a.ew = nullptr;
+    a.nc = NodeCols{p->pbuf, 640, 0, 128, 256, 384};
+    a.q = p->pq;
+    a.w.tab_k = w("PE.wd_k"); a.w.tab_v = w("PE.wd_v");
+    a.w.lnk_g = w("PE.lnk_g"); a.w.lnk_b = w("PE.lnk_b"); a.w.lnv_g = w("PE.lnv_g"); a.w.lnv_b = w("PE.lnv_b");
+    a.w.w2k = w("PE.w2k"); a.w.b2k = w("PE.b2k"); a.w.w2v = w("PE.w2v"); a.w.b2v = w("PE.b2v");
+    a.out = d_out; a.maxr = round4(d.max_p);
+    PG_TRY(pg_launch_knn_attn(a, 1, 0, s)); p->launches++;
+    return PG_OK;
+}
+
+extern "C" int pg_denoiser_forward(const PgModel* m, PgPlan* p, const float* d_h, const float* d_x, const float* d_h_bond,
+                                   const float* d_phore_norm, float* d_h_out, float* d_x_out, float* d_h_bond_out,
+                                   void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const PlanDev& d = p->d;
+    PG_CUDA_CHECK(cudaMemcpyAsync(p->h, d_h, (size_t)d.N * 128 * 4, cudaMemcpyDeviceToDevice, s));
+    PG_CUDA_CHECK(cudaMemcpyAsync(p->x, d_x, (size_t)d.N * 3 * 4, cudaMemcpyDeviceToDevice, s));
+    permute_rows_kernel<<<(unsigned)((d.Eb + 7) / 8), 256, 0, s>>>(d.Eb, d.perm, d_h_bond, p->hb, 1);
+    PG_LAUNCH_CHECK(); p->launches++;
+    PG_TRY(run_denoiser(m, p, d_phore_norm, s));
+    PG_CUDA_CHECK(cudaMemcpyAsync(d_h_out, p->h, (size_t)d.N * 128 * 4, cudaMemcpyDeviceToDevice, s));
+    PG_CUDA_CHECK(cudaMemcpyAsync(d_x_out, p->x, (size_t)d.N * 3 * 4, cudaMemcpyDeviceToDevice, s));
+    permute_rows_kernel<<<(unsigned)((d.Eb + 7) / 8), 256, 0, s>>>(d.Eb, d.perm, p->hb, d_h_bond_out, 0);
+    PG_LAUNCH_CHECK(); p->launches++;
+    return PG_OK;
+}
+
+extern "C" int pg_phorediff_forward(const PgModel* m, PgPlan* p, const float* d_h_node, const float* d_pos,
+                                    const float* d_h_edge, const int64_t* d_time_step, const float* d_h_phore_emb,
+                                    const float* d_pos_phore, const float* d_phore_norm, float* d_logits_node,
+                                    float* d_pos_out, float* d_logits_edge, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const PlanDev& d = p->d;
+    const W w{m};
+    embed_nodes_kernel<<<(unsigned)((d.N + 7) / 8), 256, 0, s>>>(d, d_h_node, d_pos, d_time_step, d_h_phore_emb, d_pos_phore,
+                                                                  w("G.node_emb_t"), w("G.time_coeff"), w("G.time_offset"), p->h, p->x);
+    PG_LAUNCH_CHECK(); p->launches++;
+    embed_edges_kernel<<<(unsigned)((d.Eb + 7) / 8), 256, 0, s>>>(d, d_h_edge, d_time_step, w("G.edge_emb_t"), w("G.time_coeff"),
+                                                                   w("G.time_offset"), p->hb);
+    PG_LAUNCH_CHECK(); p->launches++;
+    PG_TRY(run_denoiser(m, p, d_phore_norm, s));
+    // output heads
+    PG_TRY(gemm(p, s, PRO_PLAIN, d.N, p->h, 128, w("G.vinf.w1t"), 128, w("G.vinf.b1"), p->qn1, 128, 1));
+    head_out_kernel<PG_NODE_CLASSES, 0><<<(unsigned)((d.Nl + 7) / 8), 256, 0, s>>>(d, p->qn1, w("G.vinf.w2"), w("G.vinf.b2"),
+                                                                                   d_logits_node, p->x, d_pos_out);
+    PG_LAUNCH_CHECK(); p->launches++;
+    PG_TRY(gemm(p, s, PRO_PLAIN, d.Eb, p->hb, 128, w("G.binf.w1t"), 128, w("G.binf.b1"), p->qt, 128, 1));
+    head_out_kernel<PG_EDGE_CLASSES, 1><<<(unsigned)((d.Eb + 7) / 8), 256, 0, s>>>(d, p->qt, w("G.binf.w2"), w("G.binf.b2"),
+                                                                                   d_logits_edge, nullptr, nullptr);
+    PG_LAUNCH_CHECK(); p->launches++;
+    return PG_OK;
+}

@@ -1,0 +1,348 @@
+"""Drop-in for reference models/diffusion.py `PhoreDiff` (inference tier): same constructor, attribute names,
+641-key state_dict, `forward` and `sample` signatures and return layouts; the arithmetic runs in the CUDA library.
+
+    from phoregen_b200.diffusion import PhoreDiff        # instead of `from models.diffusion import PhoreDiff`
+
+Reference call sites served: sample_all.py:57-60,91-94 (construct, load_state_dict, sample) and
+models/diffusion.py:175-246 (forward).  `compute_loss` (training tier, diffusion.py:249-352) is not part of round 1.
+"""
+import math
+
+import numpy as np
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import _lib, schedules
+from .engine import BatchPlan, PackedModel
+from .modules import get_denoiser_net, get_phore_encoder
+
+
+class _Cfg(dict):
+    """Minimal attribute-dict so plain YAML dicts work where the reference expects an EasyDict."""
+
+    def __init__(self, d):
+        super().__init__()
+        for k, v in dict(d).items():
+            self[k] = _Cfg(v) if isinstance(v, dict) else ([_Cfg(i) if isinstance(i, dict) else i for i in v]
+                                                         if isinstance(v, list) else v)
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+
+def _frozen(arr):
+    return nn.Parameter(torch.from_numpy(np.asarray(arr)).float(), requires_grad=False)
+
+
+class ContigousTransition(nn.Module):
+    """Frozen tables of transition.py:9-26 (state_dict keys pos_transition.*)."""
+
+    def __init__(self, betas):
+        super().__init__()
+        for k, v in schedules.gaussian_tables(betas).items():
+            setattr(self, k, _frozen(v))
+
+
+class GeneralCategoricalTransition(nn.Module):
+    """Frozen tables of transition.py:178-215 (state_dict keys {node,edge}_transition.*)."""
+
+    def __init__(self, betas, num_classes, init_prob=None):
+        super().__init__()
+        self.num_classes = num_classes
+        tabs, prior = schedules.categorical_tables(betas, num_classes, init_prob)
+        self.init_prob = prior
+        self.q_mats = _frozen(tabs["q_mats"])
+        self.transpopse_q_onestep_mats = _frozen(tabs["transpopse_q_onestep_mats"])
+
+    def init_log_prob(self):
+        return torch.log(torch.from_numpy(self.init_prob) + 1e-30).clamp_min(-32.0).float()
+
+
+class TimeGaussianSmearing(nn.Module):
+    """Buffers of common.py:34-49 (type_='linear')."""
+
+    def __init__(self, stop, num_gaussians):
+        super().__init__()
+        offset = torch.linspace(0.0, float(stop), num_gaussians)
+        diff = torch.diff(offset)
+        diff = torch.cat([diff[:1], diff])
+        self.register_buffer("coeff", -0.5 / (diff ** 2))
+        self.register_buffer("offset", offset)
+
+
+class _Head(nn.Sequential):
+    pass
+
+
+class PhoreDiff(nn.Module):
+    def __init__(self, config, data_name="zinc_300", **kwargs):
+        super().__init__()
+        config = config if hasattr(config, "denoiser") and not isinstance(config, dict) else _Cfg(config)
+        self.config, self.data_name = config, data_name
+        self.num_node_types, self.num_edge_types = config.num_atom_classes, config.num_bond_classes
+        self.bond_len_loss, self.bond_diffusion = config.bond_len_loss, config.bond_diffusion
+        self.bond_net_type, self.count_pred_type = config.bond_net_type, config.count_pred_type
+        self.max_atom, self.min_atom = 78, 4
+        self.loss_weight = getattr(config, "loss_weight", [1, 100, 100])
+        self.count_factor = getattr(config, "count_factor", 1)
+        self.hp_emb_with_pos = getattr(config, "hp_emb_with_pos", False)
+        d = config.diff
+        if (self.num_node_types, self.num_edge_types, config.hidden_dim, d.time_dim) != (12, 6, 128, 10) or \
+                not self.bond_diffusion or self.bond_net_type != "lin" or not self.hp_emb_with_pos or \
+                d.categorical_space != "discrete" or self.count_pred_type != "boundary":
+            raise NotImplementedError("phoregen_b200 kernels are compiled for the train_lig-phore.yml model section")
+        self.num_timesteps, self.categorical_space = d.num_timesteps, d.categorical_space
+        sched = lambda c: schedules.beta_schedule(c.beta_schedule, self.num_timesteps,
+                                                  **{k: v for k, v in dict(c).items() if k not in ("beta_schedule", "init_prob")})
+        self.pos_transition = ContigousTransition(sched(d.diff_pos))
+        self.node_transition = GeneralCategoricalTransition(sched(d.diff_atom), 12, d.diff_atom.init_prob)
+        self.edge_transition = GeneralCategoricalTransition(sched(d.diff_bond), 6, d.diff_bond.init_prob)
+        self.node_embedder = nn.Linear(12, config.hidden_dim - d.time_dim, bias=False)
+        self.edge_embedder = nn.Linear(6, config.hidden_dim - d.time_dim, bias=False)
+        self.time_emb = nn.Sequential(TimeGaussianSmearing(self.num_timesteps, d.time_dim))
+        self.phore_embedding = nn.Linear(config.phore_feat_dim, config.hidden_dim)
+        if config.phore_feat_dim != 18:
+            raise NotImplementedError("phore_feat_dim must be 18 at run time (16 in the YAML + 2: sample_all.py:41-43)")
+        self.phore_encoder = get_phore_encoder(config.denoiser)
+        self.denoiser = get_denoiser_net(config.denoiser)
+        H = config.hidden_dim
+        self.v_inference = _Head(nn.Linear(H, H), nn.Identity(), nn.Linear(H, 12))          # index 1 = ShiftedSoftplus (no params)
+        from .modules import GaussianSmearing
+        self.distance_expansion = GaussianSmearing(0.0, 5.0, num_gaussians=config.denoiser.num_r_gaussian, fix_offset=False)
+        self.bond_inference = _Head(nn.Linear(H, H), nn.Identity(), nn.Linear(H, 6))
+        self.atom_mlp = nn.Sequential(nn.Linear(H, 2 * H), nn.ReLU(), nn.Linear(2 * H, 1), nn.Sigmoid())
+        self.atom_mlp_1 = nn.Sequential(nn.Linear(H, 2 * H), nn.ReLU(), nn.Linear(2 * H, 1), nn.Sigmoid())
+        self._packed, self._packed_key = None, None
+        self._plan, self._plan_key = None, None
+
+    # ------------------------------------------------------------------ packing / plans
+    def packed(self, device=None):
+        device = torch.device(device) if device is not None else self.node_embedder.weight.device
+        params = list(self.parameters())
+        key = (str(device), tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
+        if self._packed is None or self._packed_key != key:
+            self._packed = PackedModel(self.state_dict(), device)
+            self._packed_key = key
+        return self._packed
+
+    def _plan_for(self, batch_node, batch_phore, edge_index, n_graphs, device):
+        key = (int(batch_node.numel()), int(batch_phore.numel()), int(edge_index.shape[1]), edge_index.data_ptr(),
+               batch_node.data_ptr(), batch_phore.data_ptr())
+        if self._plan is None or self._plan_key != key or not torch.equal(self._plan_edges, edge_index):
+            na = torch.bincount(batch_node, minlength=n_graphs).cpu().numpy()
+            npn = torch.bincount(batch_phore, minlength=n_graphs).cpu().numpy()
+            if bool((batch_node[1:] < batch_node[:-1]).any()) or bool((batch_phore[1:] < batch_phore[:-1]).any()):
+                raise ValueError("batch vectors must be sorted by graph")
+            self._plan = BatchPlan(na, npn, device, ref_edge_index=edge_index)
+            self._plan_key, self._plan_edges = key, edge_index.clone()
+        return self._plan
+
+    # ------------------------------------------------------------------ O2 (tiny, off the sampling loop)
+    def predict_atom_count(self, h_p, batch_p, _h_p, n_graphs=None):
+        """diffusion.py:148-163.  [P,128] x two 2-layer heads; not on the per-step path of sample() (its result is
+        discarded there, diffusion.py:436) so it stays a handful of cuBLAS calls on the module's own parameters."""
+        n_graphs = int(batch_p.max().item()) + 1 if n_graphs is None else n_graphs
+
+        def gmean(v, b):
+            s = torch.zeros(n_graphs, 1, device=v.device).index_add_(0, b, v)
+            c = torch.zeros(n_graphs, 1, device=v.device).index_add_(0, b, torch.ones_like(v)).clamp(min=1)
+            return s / c
+        cnt = gmean(self.atom_mlp(h_p), batch_p)
+        col = 12 if self.data_name in ("zinc_300", "pdbbind") else 10
+        m = _h_p[:, col] != 1
+        cl = gmean(self.atom_mlp_1(h_p[m]), batch_p[m])
+        return cl, cl + F.relu(cnt - cl)
+
+    # ------------------------------------------------------------------ forward (diffusion.py:175-246)
+    @torch.no_grad()
+    def forward(self, h_node_pert, pos_pert, batch_node, h_edge_pert, edge_index, batch_edge, time_step,
+                h_phore, pos_phore, phore_norm, batch_phore, plan=None, h_phore_emb=None):
+        dev = pos_pert.device
+        n_graphs = int(time_step.numel())
+        plan = plan or self._plan_for(batch_node, batch_phore, edge_index, n_graphs, dev)
+        pm = self.packed(dev)
+        if h_phore_emb is None:
+            h_phore_emb = plan.phore_encode(pm, h_phore, pos_phore)
+        v, pos, b = plan.phorediff_forward(pm, h_node_pert, pos_pert, h_edge_pert, time_step.to(torch.int64).contiguous(),
+                                           h_phore_emb, pos_phore, phore_norm)
+        cnt = self.predict_atom_count(h_phore_emb, batch_phore, h_phore, n_graphs)
+        return v, pos, b, cnt
+
+    def compute_loss(self, data):
+        raise NotImplementedError("training tier (diffusion.py:249-352) is scheduled after the sampling path; see DESIGN.md")
+
+    # ------------------------------------------------------------------ D2 (diffusion.py:356-387)
+    @torch.no_grad()
+    def sample_nodes(self, data, batch_size, device, sample_mode="uniform", normal_scale=4.0):
+        ph = data["phore"]
+        x, pos = ph.x.to(device).float(), ph.pos.to(device).float()
+        plan = BatchPlan([2], [x.shape[0]], device, edge_order=1)          # single-graph plan for the encoder
+        h_p = plan.phore_encode(self.packed(device), x, pos)
+        cnt = self.atom_mlp(h_p).mean(0, keepdim=True)
+        col = 12 if self.data_name in ("zinc_300", "pdbbind") else 10
+        m = x[:, col] != 1
+        cl = self.atom_mlp_1(h_p[m]).mean(0, keepdim=True)
+        cu = cl + F.relu(cnt - cl)
+        scale = self.max_atom - self.min_atom
+        lo = int((cl * scale + self.min_atom).round().int().item())
+        hi = int((cu * scale + self.min_atom).round().int().item())
+        if sample_mode == "uniform":                                        # utils/sample_utils.py:28-37 (CPU RNG)
+            n = torch.randint(lo, hi + 1, (batch_size,))
+        elif sample_mode == "normal":
+            n = torch.normal((lo + hi) / 2, (hi - lo) / normal_scale, (batch_size,)).clamp(lo, hi).round().int()
+        else:
+            raise NotImplementedError(f"The sample nodes mode {sample_mode} is not implemented.")
+        return n.to(device)
+
+    # ------------------------------------------------------------------ D1 (diffusion.py:390-525)
+    @torch.no_grad()
+    def sample(self, data, n_graphs, device, pos_guidance_opt=None, sample_mode="uniform", normal_scale=4.0,
+               ligand_num_atoms=None, save_traj=True, seed=None, use_cuda_graph=True, num_steps=None, **kwargs):
+        """Reverse diffusion for `n_graphs` copies of one pharmacophore.  Returns the reference's dict
+        {'pred': [logits_node, pos+center, logits_edge], 'traj': [node, pos, edge], 'lig_info': [...]}.
+        Extensions (keyword-only in spirit): `ligand_num_atoms` bypasses the atom-count head, `save_traj=False`
+        keeps only the final state (time dim 1), `seed` fixes the Philox stream, `num_steps` truncates the loop
+        (benchmarks / tests)."""
+        device = torch.device(device)
+        sampler = TrajectorySampler(self, data, n_graphs, device, ligand_num_atoms=ligand_num_atoms,
+                                    sample_mode=sample_mode, normal_scale=normal_scale, guidance=pos_guidance_opt,
+                                    save_traj=save_traj, seed=seed, use_cuda_graph=use_cuda_graph)
+        sampler.run(num_steps)
+        return sampler.results()
+
+
+class TrajectorySampler:
+    """State + one captured CUDA graph of a reverse step (forward + categorical/Gaussian posterior update).
+
+    All shapes are static across the trajectory (bond/triplet topology is fixed and the kNN edge count is
+    N*min(32,N-1) per graph whatever the coordinates), the time step and the RNG counter live in device scalars,
+    so the whole step is captured once and replayed `num_timesteps` times."""
+
+    def __init__(self, model, data, n_graphs, device, ligand_num_atoms=None, sample_mode="uniform", normal_scale=4.0,
+                 guidance=None, save_traj=True, seed=None, use_cuda_graph=True):
+        self.m, self.device, self.G = model, device, n_graphs
+        self.T = model.num_timesteps
+        pm = self.pm = model.packed(device)
+        ph = data["phore"]
+        px, ppos, pnorm = ph.x.to(device).float(), ph.pos.to(device).float(), ph.norm.to(device).float()
+        if ligand_num_atoms is None:
+            ligand_num_atoms = model.sample_nodes(data, n_graphs, device, sample_mode, normal_scale)
+        self.num_atoms = torch.as_tensor(ligand_num_atoms).to(device)
+        na = self.num_atoms.cpu().numpy().astype(np.int32)
+        center = getattr(data, "center", None)
+        self.center = (torch.zeros(3, device=device) if center is None else torch.as_tensor(center).to(device).float()).contiguous()
+        p = px.shape[0]
+        plan = self.plan = BatchPlan(na, np.full(n_graphs, p, dtype=np.int32), device, edge_order=0)
+        # Batch.from_data_list([data.clone()] * n_graphs)  (diffusion.py:399)
+        self.px, self.ppos, self.pnorm = px.repeat(n_graphs, 1), ppos.repeat(n_graphs, 1).contiguous(), pnorm.repeat(n_graphs, 1).contiguous()
+        self.h_phore_emb = plan.phore_encode(pm, self.px, self.ppos)      # step-invariant (SURVEY.md §8(d) reduction 4)
+        self.batch_node = torch.repeat_interleave(torch.arange(n_graphs, device=device), self.num_atoms.long())
+        self.edge_index, self.edge_batch = plan.bond_edges()                # G1 on device
+        Nl, Eb = plan.Nl, plan.Eb
+        self.seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if seed is None else int(seed)
+        gen = torch.Generator(device=device)
+        gen.manual_seed(self.seed)
+        # initial state (diffusion.py:406-408; transition.py:65-69,331-339)
+        self.pos = (torch.randn(Nl, 3, device=device, generator=gen) - self.center).contiguous()
+        self.log_node = torch.empty(Nl, 12, device=device)
+        self.log_edge = torch.empty(Eb, 6, device=device)
+        self.h_node, self.node_cls = self._init_categorical(model.node_transition, Nl, self.log_node, gen)
+        self.h_edge, self.edge_cls = self._init_categorical(model.edge_transition, Eb, self.log_edge, gen)
+        self.pred = (torch.empty(Nl, 12, device=device), torch.empty(Nl, 3, device=device), torch.empty(Eb, 6, device=device))
+        self.time_step = torch.full((n_graphs,), self.T - 1, dtype=torch.int64, device=device)
+        self.step_counter = torch.zeros(1, dtype=torch.int64, device=device)
+        self.guidance = guidance
+        self.grad = torch.zeros(Nl, 3, device=device) if guidance else None
+        self.phore_center = None
+        if guidance:
+            col = 12 if model.data_name in ("zinc_300", "pdbbind") else 10
+            self.phore_center = ppos[px[:, col] != 1].mean(0).contiguous()   # diffusion.py:493-497
+        self.save_traj = save_traj
+        if save_traj:
+            try:
+                self.traj_node = torch.zeros(self.T + 1, Nl, dtype=torch.uint8, device=device)
+                self.traj_edge = torch.zeros(self.T + 1, Eb, dtype=torch.uint8, device=device)
+                self.traj_pos = torch.zeros(self.T + 1, Nl, 3, device=device)
+            except torch.OutOfMemoryError as e:
+                raise RuntimeError(f"CUDA out of memory allocating trajectory buffers: {e}") from e
+            self.traj_node[0], self.traj_edge[0], self.traj_pos[0] = self.node_cls.to(torch.uint8), self.edge_cls.to(torch.uint8), self.pos
+        else:
+            self.traj_node = self.traj_edge = self.traj_pos = None
+        self.use_cuda_graph = use_cuda_graph
+        self.graph = None
+        self.steps_done = 0
+
+    def _init_categorical(self, trans, rows, log_out, gen):
+        K = trans.num_classes
+        logits = trans.init_log_prob().to(self.device).unsqueeze(0).expand(rows, K)
+        u = torch.rand(rows, K, device=self.device, generator=gen)
+        cls = (-torch.log(-torch.log(u + 1e-30) + 1e-30) + logits).argmax(-1)
+        onehot = F.one_hot(cls, K).float().contiguous()
+        log_out.copy_(torch.log(onehot.clamp(min=1e-30)))                    # index_to_log_onehot (common.py:398-402)
+        return onehot, cls.to(torch.int32).contiguous()
+
+    def _step(self):
+        """Loop body of diffusion.py:432-517."""
+        plan, pm = self.plan, self.pm
+        plan.phorediff_forward(pm, self.h_node, self.pos, self.h_edge, self.time_step, self.h_phore_emb, self.ppos,
+                               self.pnorm, out=self.pred)
+        plan.categorical_step(pm, "node", self.pred[0], self.log_node, self.time_step, seed=self.seed,
+                              step_counter=self.step_counter, onehot=self.h_node, cls=self.node_cls, traj=self.traj_node)
+        plan.categorical_step(pm, "edge", self.pred[2], self.log_edge, self.time_step, seed=self.seed,
+                              step_counter=self.step_counter, onehot=self.h_edge, cls=self.edge_cls, traj=self.traj_edge)
+        if self.guidance:
+            plan.guidance_grad(self.pos, self.edge_cls, self.guidance, self.phore_center, out=self.grad)
+        plan.position_step(pm, self.pos, self.pred[1], self.time_step, energy_grad=self.grad, seed=self.seed,
+                           step_counter=self.step_counter, out=self.pos, traj=self.traj_pos, center=self.center)
+        self.time_step.sub_(1)
+        self.step_counter.add_(1)
+
+    def run(self, num_steps=None):
+        n = self.T - self.steps_done if num_steps is None else min(num_steps, self.T - self.steps_done)
+        if n <= 0:
+            return
+        if not self.use_cuda_graph:
+            for _ in range(n):
+                self._step()
+        else:
+            if self.graph is None:
+                # warm-up outside capture (lazy module loading, cudaFuncSetAttribute), then roll the counters back
+                self._snapshot = [t.clone() for t in self._state_tensors()]
+                s = torch.cuda.Stream(device=self.device)
+                s.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(s):
+                    self._step()
+                torch.cuda.current_stream(self.device).wait_stream(s)
+                for t, c in zip(self._state_tensors(), self._snapshot):
+                    t.copy_(c)
+                self._snapshot = None
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._step()
+            for _ in range(n):
+                self.graph.replay()
+        self.steps_done += n
+
+    def _state_tensors(self):
+        ts = [self.h_node, self.pos, self.h_edge, self.log_node, self.log_edge, self.node_cls, self.edge_cls,
+              self.time_step, self.step_counter]
+        if self.save_traj:
+            ts += [self.traj_node[1], self.traj_edge[1], self.traj_pos[1]]
+        return ts
+
+    def results(self):
+        pred_pos = self.pred[1] + self.center                                  # reference quirk 3 (diffusion.py:519)
+        if self.save_traj:
+            # reference layout: one-hot f32 with time as dim 0 (diffusion.py:418-426)
+            node_traj = F.one_hot(self.traj_node.long(), 12).float()
+            edge_traj = F.one_hot(self.traj_edge.long(), 6).float()
+            pos_traj = self.traj_pos                                           # slot 0 is the un-centred init (diffusion.py:425)
+        else:
+            node_traj, pos_traj, edge_traj = self.h_node[None], (self.pos + self.center)[None], self.h_edge[None]
+        return {"pred": [self.pred[0], pred_pos, self.pred[2]],
+                "traj": [node_traj, pos_traj, edge_traj],
+                "lig_info": [self.num_atoms, self.batch_node, self.edge_index, self.edge_batch]}

@@ -1,0 +1,207 @@
+"""Host-side handles over the C ABI: packed model, batch plan, and the per-call wrappers.
+
+PyTorch is used here for device memory, streams and (elsewhere) torch.distributed only; every kernel on the
+hot path lives in libphoregen_b200.so.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib
+from .weights import blob_to_device
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "device-resident contiguous tensor required"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t):
+    return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+
+
+def _alloc(shape, dtype, device):
+    try:
+        return torch.empty(shape, dtype=dtype, device=device)
+    except torch.OutOfMemoryError as e:  # callers pattern-match this phrase (sample_all.py:96, run/run.py:145)
+        raise RuntimeError(f"CUDA out of memory while allocating phoregen_b200 work space: {e}") from e
+
+
+class PackedModel:
+    """Weights of a PhoreDiff state_dict packed for the CUDA kernels."""
+
+    def __init__(self, state_dict, device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.PhoreGenLibraryError("phoregen_b200 runs on CUDA devices only (no CPU fallback)")
+        self.blob, offsets = blob_to_device(state_dict, self.device)
+        self._offsets = offsets
+        h = ctypes.c_void_p()
+        check(lib.pg_model_create(ctypes.byref(h), _ptr(self.blob),
+                                  offsets.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), len(offsets)), "pg_model_create")
+        self.handle = h
+        g = lambda k: state_dict[k].detach().to(self.device, torch.float32).contiguous()
+        self.tables = {k: g(k) for k in (
+            "pos_transition.coef_x0", "pos_transition.coef_xt", "pos_transition.std",
+            "node_transition.q_mats", "node_transition.transpopse_q_onestep_mats",
+            "edge_transition.q_mats", "edge_transition.transpopse_q_onestep_mats") if k in state_dict}
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            lib.pg_model_destroy(h)
+            self.handle = None
+
+
+class BatchPlan:
+    """Static topology + work space of one batch (see pg_plan_create in include/phoregen_b200.h)."""
+
+    def __init__(self, num_atoms, num_phore, device, edge_order=0, ref_edge_index=None):
+        self.device = torch.device(device)
+        na = np.ascontiguousarray(np.asarray(num_atoms, dtype=np.int32))
+        npn = np.ascontiguousarray(np.asarray(num_phore, dtype=np.int32))
+        assert na.shape == npn.shape and na.ndim == 1
+        self.num_atoms, self.num_phore, self.G = na, npn, int(na.size)
+        pa = na.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+        pp = npn.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+        nbytes = int(lib.pg_plan_workspace_bytes(self.G, pa, pp))
+        if nbytes < 0:
+            check(nbytes, "pg_plan_workspace_bytes")
+        self.workspace = _alloc((nbytes + 256,), torch.uint8, self.device)
+        base = self.workspace.data_ptr()
+        aligned = (base + 255) & ~255
+        self.workspace_bytes = nbytes
+        if ref_edge_index is not None:
+            ref_edge_index = ref_edge_index.to(self.device, torch.int64).contiguous()
+            edge_order = 2
+        self.edge_order = edge_order
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.pg_plan_create(ctypes.byref(h), self.G, pa, pp, edge_order, _ptr(ref_edge_index),
+                                     ctypes.c_void_p(aligned), nbytes, _stream()), "pg_plan_create")
+        self.handle = h
+        self.Nl = int(lib.pg_plan_num_ligand_atoms(h))
+        self.P = int(lib.pg_plan_num_phore_nodes(h))
+        self.N = self.Nl + self.P
+        self.Eb = int(lib.pg_plan_num_bond_edges(h))
+        self.Ek = int(lib.pg_plan_num_knn_edges(h))
+        self.E3 = int(lib.pg_plan_num_triplets(h))
+        self._lig_graph_ptr = lib.pg_plan_ligand_graph(h)
+        self._edge_graph_ptr = lib.pg_plan_edge_graph(h)
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            lib.pg_plan_destroy(h)
+            self.handle = None
+
+    @property
+    def launches(self):
+        return int(lib.pg_plan_kernel_launches(self.handle))
+
+    # ---- graph artefacts (G1, B1, K1) ------------------------------------------------------
+    def bond_edges(self):
+        ei = _alloc((2, self.Eb), torch.int64, self.device)
+        eb = _alloc((self.Eb,), torch.int64, self.device)
+        check(lib.pg_plan_export_bond_edges(self.handle, _ptr(ei), _ptr(eb), _stream()), "pg_plan_export_bond_edges")
+        return ei, eb
+
+    def triplets(self):
+        outs = [_alloc((self.E3,), torch.int64, self.device) for _ in range(5)]
+        check(lib.pg_plan_export_triplets(self.handle, *[_ptr(o) for o in outs], _stream()), "pg_plan_export_triplets")
+        return outs
+
+    def knn_graph(self, x, mode=0):
+        """mode 0: k=32 joint graph in context numbering; mode 1: k=3 ligand-only graph in ligand numbering."""
+        x = _f32(x)
+        assert x.shape == (self.N, 3)
+        if mode == 0:
+            E = self.Ek
+        else:
+            E = int(sum(int(n) * min(3, int(n) - 1) for n in self.num_atoms))
+        ei = _alloc((2, E), torch.int64, self.device)
+        check(lib.pg_knn_graph(self.handle, _ptr(x), mode, _ptr(ei), _stream()), "pg_knn_graph")
+        return ei
+
+    # ---- forward passes ---------------------------------------------------------------------
+    def phore_encode(self, model, h_phore, pos_phore):
+        h_phore, pos_phore = _f32(h_phore), _f32(pos_phore)
+        assert h_phore.shape == (self.P, 18) and pos_phore.shape == (self.P, 3)
+        out = _alloc((self.P, 128), torch.float32, self.device)
+        check(lib.pg_phore_encode(model.handle, self.handle, _ptr(h_phore), _ptr(pos_phore), _ptr(out), _stream()),
+              "pg_phore_encode")
+        return out
+
+    def denoiser_forward(self, model, h, x, h_bond, phore_norm):
+        h, x, h_bond, phore_norm = _f32(h), _f32(x), _f32(h_bond), _f32(phore_norm)
+        assert h.shape == (self.N, 128) and x.shape == (self.N, 3) and h_bond.shape == (self.Eb, 128)
+        assert phore_norm.shape == (self.P, 3)
+        ho, xo, bo = torch.empty_like(h), torch.empty_like(x), torch.empty_like(h_bond)
+        check(lib.pg_denoiser_forward(model.handle, self.handle, _ptr(h), _ptr(x), _ptr(h_bond), _ptr(phore_norm),
+                                      _ptr(ho), _ptr(xo), _ptr(bo), _stream()), "pg_denoiser_forward")
+        return ho, xo, bo
+
+    def phorediff_forward(self, model, h_node, pos, h_edge, time_step, h_phore_emb, pos_phore, phore_norm, out=None):
+        h_node, pos, h_edge = _f32(h_node), _f32(pos), _f32(h_edge)
+        assert h_node.shape == (self.Nl, 12) and pos.shape == (self.Nl, 3) and h_edge.shape == (self.Eb, 6)
+        assert time_step.dtype == torch.int64 and time_step.shape == (self.G,) and time_step.is_contiguous()
+        assert h_phore_emb.shape == (self.P, 128)
+        if out is None:
+            out = (_alloc((self.Nl, 12), torch.float32, self.device), _alloc((self.Nl, 3), torch.float32, self.device),
+                   _alloc((self.Eb, 6), torch.float32, self.device))
+        check(lib.pg_phorediff_forward(model.handle, self.handle, _ptr(h_node), _ptr(pos), _ptr(h_edge), _ptr(time_step),
+                                       _ptr(_f32(h_phore_emb)), _ptr(_f32(pos_phore)), _ptr(_f32(phore_norm)),
+                                       _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _stream()), "pg_phorediff_forward")
+        return out
+
+    # ---- transitions -----------------------------------------------------------------------
+    def categorical_step(self, model, kind, pred, log_vt, time_step, uniform=None, seed=0, step_counter=None,
+                         onehot=None, cls=None, traj=None):
+        K = 12 if kind == "node" else 6
+        rows = self.Nl if kind == "node" else self.Eb
+        assert pred.shape == (rows, K) and log_vt.shape == (rows, K) and pred.is_contiguous() and log_vt.is_contiguous()
+        qm = model.tables[f"{kind}_transition.q_mats"]
+        tq = model.tables[f"{kind}_transition.transpopse_q_onestep_mats"]
+        rg = self._lig_graph_ptr if kind == "node" else self._edge_graph_ptr
+        if onehot is None:
+            onehot = _alloc((rows, K), torch.float32, self.device)
+        if cls is None:
+            cls = _alloc((rows,), torch.int32, self.device)
+        check(lib.pg_categorical_step(rows, K, _ptr(pred), _ptr(log_vt), _ptr(qm), _ptr(tq), _ptr(time_step),
+                                      ctypes.c_void_p(rg), _ptr(uniform), seed, 1 if kind == "node" else 2,
+                                      _ptr(step_counter), _ptr(onehot), _ptr(cls), _ptr(traj), _stream()), "pg_categorical_step")
+        return onehot, cls
+
+    def position_step(self, model, x_t, x_recon, time_step, normal=None, energy_grad=None, seed=0, step_counter=None,
+                      out=None, traj=None, center=None):
+        assert x_t.shape == (self.Nl, 3) and x_recon.shape == (self.Nl, 3)
+        if out is None:
+            out = torch.empty_like(x_t)
+        t = model.tables
+        check(lib.pg_position_step(self.Nl, _ptr(x_t), _ptr(x_recon), _ptr(energy_grad), _ptr(t["pos_transition.coef_x0"]),
+                                   _ptr(t["pos_transition.coef_xt"]), _ptr(t["pos_transition.std"]), _ptr(time_step),
+                                   ctypes.c_void_p(self._lig_graph_ptr), _ptr(normal), seed, 3, _ptr(step_counter),
+                                   _ptr(out), _ptr(traj), _ptr(center), _stream()), "pg_position_step")
+        return out
+
+    def guidance_grad(self, pos, edge_cls, opts, phore_center, out=None):
+        flags, min_d, max_d = 0, 0.0, 0.0
+        for o in opts or []:
+            if o["type"] == "atom_prox":
+                flags |= 1
+                min_d, max_d = float(o["min_d"]), float(o["max_d"])
+            elif o["type"] == "center_prox":
+                flags |= 2
+        if out is None:
+            out = torch.empty_like(pos)
+        check(lib.pg_guidance_grad(self.handle, _ptr(pos), _ptr(edge_cls), flags, min_d, max_d,
+                                   _ptr(phore_center), _ptr(out), _stream()), "pg_guidance_grad")
+        return out

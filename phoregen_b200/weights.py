@@ -1,0 +1,151 @@
+"""Pack a reference-layout state_dict (641 keys, SURVEY.md §8(b) "Checkpoint") into the fp32 blob the CUDA
+library reads.  Pure re-layout plus the exact algebraic folds described in DESIGN.md ("Factorisation"):
+the first Linear of each MLP is split along its concatenated input (reference uni_denoiser.py:43-46,141-147,
+190-193), the one-hot edge type (x) smearing product (common.py:156-163, uni_denoiser.py:270-271) becomes four
+20x128 weight slices, and `dire_embedding` (uni_denoiser.py:257-258,279) is folded into the first Linear.
+Folds are done in float64 and rounded once to fp32.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+SUBS = {"nk": "node_layer_with_edge", "nb": "node_layer_with_bond", "tr": "bond_layer",
+        "pk": "pos_layer_with_edge", "pb": "pos_layer_with_bond"}
+_FN = {"nk": ("hk_func", "hv_func", "hq_func"), "nb": ("hk_func", "hv_func", "hq_func"),
+       "tr": ("hk_func", "hv_func", "hq_func"), "pk": ("xk_func", "xv_func", "xq_func"),
+       "pb": ("xk_func", "xv_func", "xq_func")}
+
+
+def _mlp(sd, prefix):
+    g = lambda k: sd[prefix + k].detach().double().cpu().numpy()
+    return dict(W1=g(".net.0.weight"), b1=g(".net.0.bias"), g=g(".net.1.weight"), b=g(".net.1.bias"),
+                W2=g(".net.3.weight"), b2=g(".net.3.bias"))
+
+
+def _knn_tables(W1, Wde):
+    """[4][24][128]: rows 0-19 smear slice of the edge type, 20 the type column, 21-23 dire (folded)."""
+    tab = np.zeros((4, 24, 128))
+    dire = W1[:, 84:93] @ Wde                       # [128,3]
+    for t in range(4):
+        tab[t, :20] = W1[:, t * 20:(t + 1) * 20].T
+        tab[t, 20] = W1[:, 80 + t]
+        tab[t, 21:24] = dire.T
+    return tab
+
+
+def pack_state_dict(sd):
+    """-> dict slot name -> float64 ndarray (flattened later)."""
+    out = {}
+    f = lambda k: sd[k].detach().double().cpu().numpy()
+    out["G.node_emb_t"] = f("node_embedder.weight").T
+    out["G.edge_emb_t"] = f("edge_embedder.weight").T
+    out["G.time_coeff"] = f("time_emb.0.coeff")
+    out["G.time_offset"] = f("time_emb.0.offset")
+    out["G.ph_emb_wt"] = f("phore_embedding.weight").T
+    out["G.ph_emb_b"] = f("phore_embedding.bias")
+    # pharmacophore encoder: kv input = [dist(1) | h_dst(128) | h_src(128)]  (models/__init__.py:29-35)
+    k, v, q = (_mlp(sd, "phore_encoder." + n) for n in ("hk_func", "hv_func", "hq_func"))
+    z = np.zeros(128)
+    out["PE.wcat_t"] = np.concatenate([k["W1"][:, 1:129].T, k["W1"][:, 129:257].T, v["W1"][:, 1:129].T,
+                                       v["W1"][:, 129:257].T, q["W1"].T], 1)
+    out["PE.bcat"] = np.concatenate([k["b1"], z, v["b1"], z, q["b1"]])
+    out["PE.wd_k"], out["PE.wd_v"] = k["W1"][:, 0], v["W1"][:, 0]
+    for tag, m in (("k", k), ("v", v), ("q", q)):
+        out[f"PE.ln{tag}_g"], out[f"PE.ln{tag}_b"] = m["g"], m["b"]
+    out["PE.w2q_t"], out["PE.b2q"] = q["W2"].T, q["b2"]
+    out["PE.w2k"], out["PE.b2k"], out["PE.w2v"], out["PE.b2v"] = k["W2"], k["b2"], v["W2"], v["b2"]
+    # global edge weight MLP (uni_denoiser.py:326,410-415)
+    e = _mlp(sd, "denoiser.edge_pred_layer")
+    out["G.ew.w1t"], out["G.ew.b1"], out["G.ew.ln_g"], out["G.ew.ln_b"] = e["W1"].T, e["b1"], e["g"], e["b"]
+    out["G.ew.w2"] = e["W2"][0]
+    out["G.ew.b2"] = np.concatenate([e["b2"], np.zeros(3)])
+    out["G.vinf.w1t"], out["G.vinf.b1"] = f("v_inference.0.weight").T, f("v_inference.0.bias")
+    out["G.vinf.w2"], out["G.vinf.b2"] = f("v_inference.2.weight"), f("v_inference.2.bias")
+    out["G.binf.w1t"], out["G.binf.b1"] = f("bond_inference.0.weight").T, f("bond_inference.0.bias")
+    out["G.binf.w2"] = f("bond_inference.2.weight")
+    out["G.binf.b2"] = np.concatenate([f("bond_inference.2.bias"), np.zeros(2)])
+
+    n_layers = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("denoiser.base_block."))
+    for l in range(n_layers):
+        P = f"denoiser.base_block.{l}."
+        L = f"L{l}."
+        m = {s: tuple(_mlp(sd, P + SUBS[s] + "." + fn) for fn in _FN[s]) for s in SUBS}
+        Wde, bde = f(P + "dire_embedding.weight"), f(P + "dire_embedding.bias")      # [9,3], [9]
+
+        def knn_cols(s):       # kv input = [edge_feat(93) | h_dst(128) | h_src(128)]
+            k, v, q = m[s]
+            cols, bias = [], []
+            for mm in (k, v):
+                cols += [mm["W1"][:, 93:221].T, mm["W1"][:, 221:349].T]
+                bias += [mm["b1"] + mm["W1"][:, 84:93] @ bde, z]
+            return cols + [q["W1"].T], bias + [q["b1"]]
+
+        def bond_cols(s):      # kv input = [h_bond(128) | h_dst(128) | h_src(128)]
+            k, v, q = m[s]
+            cols, bias = [], []
+            for mm in (k, v):
+                cols += [mm["W1"][:, 128:256].T, mm["W1"][:, 256:384].T]
+                bias += [mm["b1"], z]
+            return cols + [q["W1"].T], bias + [q["b1"]]
+
+        tk, tv, tq = m["tr"]   # kv = [h_bond_kj(128) | r_kj(20) | r_ji(20) | a(13) | h_k(128) | h_j(128)], q = [h_bond_ji | h_i]
+        c1, b1 = knn_cols("nk")
+        c2, b2 = bond_cols("nb")
+        c3 = [tk["W1"][:, 181:309].T, tk["W1"][:, 309:437].T, tv["W1"][:, 181:309].T, tv["W1"][:, 309:437].T,
+              tq["W1"][:, 128:256].T]
+        b3 = [z, tk["b1"], z, tv["b1"], tq["b1"]]
+        out[L + "n1.wt"] = np.concatenate(c1 + c2 + c3, 1)
+        out[L + "n1.b"] = np.concatenate(b1 + b2 + b3)
+        out[L + "e1.wt"] = np.concatenate([m["nb"][0]["W1"][:, :128].T, m["nb"][1]["W1"][:, :128].T,
+                                           tk["W1"][:, :128].T, tv["W1"][:, :128].T, tq["W1"][:, :128].T], 1)
+        out[L + "e1.b"] = np.zeros(640)
+        c4, b4 = knn_cols("pk")
+        c5, b5 = bond_cols("pb")
+        out[L + "n2.wt"] = np.concatenate(c4 + c5, 1)
+        out[L + "n2.b"] = np.concatenate(b4 + b5)
+        out[L + "e2.wt"] = np.concatenate([m["pb"][0]["W1"][:, :128].T, m["pb"][1]["W1"][:, :128].T], 1)
+        out[L + "e2.b"] = np.zeros(256)
+        out[L + "lin.wt"], out[L + "lin.b"] = f(P + "lin_node.weight").T, f(P + "lin_node.bias")
+        for s in SUBS:
+            k, v, q = m[s]
+            S = L + s + "."
+            out[S + "lnq_g"], out[S + "lnq_b"], out[S + "w2q_t"], out[S + "b2q"] = q["g"], q["b"], q["W2"].T, q["b2"]
+            out[S + "lnk_g"], out[S + "lnk_b"], out[S + "lnv_g"], out[S + "lnv_b"] = k["g"], k["b"], v["g"], v["b"]
+            out[S + "w2k"], out[S + "b2k"], out[S + "w2v"], out[S + "b2v"] = k["W2"], k["b2"], v["W2"], v["b2"]
+            if s in ("nk", "pk"):
+                out[S + "tab_k"], out[S + "tab_v"] = _knn_tables(k["W1"], Wde), _knn_tables(v["W1"], Wde)
+            if s == "tr":
+                out[S + "wrkj"] = np.concatenate([k["W1"][:, 128:148].T, v["W1"][:, 128:148].T], 1)
+                out[S + "wrji"] = np.concatenate([k["W1"][:, 148:168].T, v["W1"][:, 148:168].T], 1)
+                out[S + "wa"] = np.concatenate([k["W1"][:, 168:181].T, v["W1"][:, 168:181].T], 1)
+    return out
+
+
+def build_blob(sd):
+    """-> (fp32 numpy blob, int64 offsets in floats) following the library's own slot table."""
+    packed = pack_state_dict(sd)
+    table = _lib.slot_table()
+    offsets = np.zeros(len(table), dtype=np.int64)
+    chunks, cur = [], 0
+    for i, (name, numel) in enumerate(table):
+        if name not in packed:
+            raise KeyError(f"weight packer does not produce slot {name!r}")
+        arr = np.ascontiguousarray(packed[name], dtype=np.float64).reshape(-1)
+        if arr.size != numel:
+            raise ValueError(f"slot {name}: expected {numel} values, packed {arr.size}")
+        pad = (-arr.size) % 4
+        offsets[i] = cur
+        chunks.append(arr.astype(np.float32))
+        if pad:
+            chunks.append(np.zeros(pad, dtype=np.float32))
+        cur += arr.size + pad
+    extra = set(packed) - {n for n, _ in table}
+    if extra:
+        raise KeyError(f"packer produced unknown slots: {sorted(extra)[:5]}")
+    return np.concatenate(chunks), offsets
+
+
+def blob_to_device(sd, device):
+    blob, offsets = build_blob(sd)
+    return torch.from_numpy(blob).to(device), offsets
