@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the PhoreGen sampling hot path (BASELINE.json metric: molecules/sec for a full 1000-step reverse
+trajectory; denoiser step ms).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one reverse-diffusion step (PhoreDiff.forward + categorical/Gaussian posterior update, the loop body of
+reference models/diffusion.py:432-517) over one batch of synthetic molecules.  Workload at N=1 is BASELINE.json
+configs[1]: 1024 molecules x 30 heavy atoms, 6-8 pharmacophore features each, random-init weights, seed 2032.
+Every step of a trajectory has identical shapes and executes identical work, so
+    molecules/sec = molecules / (1000 * seconds_per_step)
+and K timed steps measure it without running all 1000 (``--full-trajectory`` runs them all).
+For N>1 (torchrun) each rank runs its own 1024 molecules (weak scaling, no collective inside the loop) and the
+sampled molecules are gathered to rank 0 once, inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TRAJ_STEPS = 1000
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def f_ref_flops(n, p):
+    """Algorithmic FLOPs of one molecule-step in the reference formulation (SURVEY.md §8(d) `F_ref`), and the
+    triplet-layer share per layer (term C)."""
+    N, Eb, E3 = n + p, n * (n - 1), n * (n - 1) * (n - 2)
+    Ek = N * min(32, N - 1)
+    A = Ek * 2 * (349 * 128 + 128 * 128) + N * 2 * 128 * 128
+    B = Eb * 2 * (384 * 128 + 128 * 128) + N * 2 * 128 * 128
+    C = E3 * (2 * (437 * 128 + 128 * 128) + (256 * 128 + 128 * 128))
+    D = Ek * ((349 * 128 + 128 * 128) + (349 * 128 + 128 * 16)) + N * 2 * 128 * 128
+    F_ = Eb * ((384 * 128 + 128 * 128) + (384 * 128 + 128 * 16)) + N * 2 * 128 * 128
+    Gm = N * 128 * 128
+    once = p * p * 2 * (257 * 128 + 128 * 128) + Ek * (20 * 128 + 128) + n * (128 * 128 + 128 * 12) + Eb * (128 * 128 + 128 * 6)
+    macs = 6 * (A + B + C + D + F_ + Gm) + once
+    return 2.0 * macs, 2.0 * C
+
+
+def f_exec_trip_flops(n):
+    """FLOPs the factorised triplet kernel actually issues per molecule-layer (DESIGN.md 'Factorisation')."""
+    Eb, E3 = n * (n - 1), n * (n - 1) * (n - 2)
+    per_row = 2 * (13 * 128 + 2 * 128) + 2 * 6 * 128 + 16 * 128 + 16 * 128          # angle part, LN x2, logits, aggregate
+    per_seg = 2 * 20 * 128 + 128 * 128 + 128 * 128                                  # r_ji part, query fold, value second Linear
+    per_unit_row = 2 * (20 * 128 + 3 * 128)                                         # staging of P rows
+    return 2.0 * (E3 * per_row + Eb * per_seg + Eb * per_unit_row)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"bf16_tflops_sustained": d.get("bf16_tflops_sustained", 1400.0), "bf16_tflops": d.get("bf16_tflops", 1590.0),
+                "hbm_gbs": d.get("hbm_gbs", 6650.0), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops_sustained": 1400.0, "bf16_tflops": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def workload(seed, n_graphs, n_atoms):
+    from phoregen_b200.synthetic import synthetic_batch
+    return synthetic_batch(seed, n_graphs, n_atoms=n_atoms)
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
+def cpu_reference_step_time(n_mol, n_atoms, steps, warmup, seed=2032):
+    """Times the reference formulation's reverse step on the host cores: the oracle port of
+    models/diffusion.py:432-517 (torch fp32, all host threads)."""
+    from oracle import phoregen_oracle as O
+    from phoregen_b200.diffusion import PhoreDiff
+    from phoregen_b200.testing import MODEL_CONFIG, random_state_dict
+    torch.set_num_threads(os.cpu_count())
+    sd = random_state_dict(PhoreDiff(MODEL_CONFIG, "zinc_300"), 0)
+    b = O.synthetic_batch(seed, n_mol, n_atoms=n_atoms)
+    g = torch.Generator().manual_seed(seed)
+    Nl, Eb = b["h_node"].shape[0], b["h_edge"].shape[0]
+    st = dict(h_node=b["h_node"], pos=b["pos"], h_edge=b["h_edge"], log_node=torch.log(b["h_node"].clamp(min=1e-30)),
+              log_edge=torch.log(b["h_edge"].clamp(min=1e-30)))
+    topo = dict(batch_node=b["batch_node"], edge_index=b["edge_index"], batch_edge=b["batch_edge"], n_graphs=n_mol)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            d = dict(u_node=torch.rand(Nl, 12, generator=g), u_edge=torch.rand(Eb, 6, generator=g), z_pos=torch.randn(Nl, 3, generator=g))
+            t0 = time.perf_counter()
+            st, _ = O.reverse_step(sd, st, 999 - i, topo, b["phore"], d)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return float(np.mean(times)), torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_mol = args.cpu_molecules
+    sec, cores = cpu_reference_step_time(n_mol, args.atoms, args.steps, args.warmup)
+    val = n_mol / (sec * TRAJ_STEPS)
+    sample = f"{n_mol} molecules x {args.atoms} atoms per step, {args.steps} timed steps of the 1000-step trajectory"
+    line = {
+        "impl": "reference", "metric": "molecules/sec (full 1000-step reverse trajectory)", "value": val, "unit": "molecules/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"configs[1]: {args.atoms}-atom molecules, 6-8 pharmacophore features, random-init weights, seed 2032",
+                   "trajectory_steps": TRAJ_STEPS, "note": "reference formulation (oracle port of models/diffusion.py loop body) on host cores"},
+        "cpu_baseline": {"value": val, "unit": "molecules/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch.distributed as dist
+    from phoregen_b200.diffusion import PhoreDiff, TrajectorySampler
+    from phoregen_b200.distributed import gather_results, pack_results
+    from phoregen_b200.testing import MODEL_CONFIG, random_state_dict
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    G = args.molecules
+    model = PhoreDiff(MODEL_CONFIG, "zinc_300")
+    model.load_state_dict(random_state_dict(model, 0), strict=True)
+    model = model.to(dev).eval()
+    b = workload(2032 + rank, G, args.atoms)
+    ph = b["phore"]
+    smp = TrajectorySampler(model, None, G, dev, ligand_num_atoms=b["num_atoms"], save_traj=False, seed=2032 + rank,
+                            use_cuda_graph=True, phore_batch=ph)
+    plan = smp.plan
+    p_mean = plan.P / G
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- warm-up (also captures the CUDA graph of the step)
+    smp.run(max(W, 3))
+    launches_per_step = None
+    barrier()
+    # ---- timed region: device-resident state, CUDA-graph replay of the whole step
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    l0 = plan.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    smp.run(K)
+    gathered = None
+    if world > 1:
+        local = pack_results(smp.pos + smp.center, smp.node_cls, smp.edge_cls, smp.num_atoms)
+        gathered = gather_results(local, dst=0)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / K
+    value = world * G / (ms_per_step * 1e-3 * TRAJ_STEPS)
+
+    # ---- kernels per step: counted from an eager (non-captured) step through the library's own launch counter
+    eager = TrajectorySampler(model, None, G, dev, ligand_num_atoms=b["num_atoms"], save_traj=False, seed=1, use_cuda_graph=False,
+                              phore_batch=ph)
+    eager.run(2)
+    c0 = eager.plan.launches
+    eager.plan.timing(True)
+    n_prof = 3
+    eager.run(n_prof)
+    torch.cuda.synchronize(dev)
+    timing = eager.plan.read_timing()
+    eager.plan.timing(False)
+    launches_per_step = (eager.plan.launches - c0) // n_prof + 3          # + node/edge categorical + position kernels
+    trip_ms, trip_n = timing["trip"]
+    class_ms = {k: v[0] / n_prof for k, v in timing.items()}
+
+    # ---- end to end through the public forward() with HOST buffers: pinned H2D of the step's inputs, D2H of its result
+    pin = lambda t: t.contiguous().pin_memory()
+    host_in = dict(h_node=pin(b["h_node"]), pos=pin(b["pos"]), h_edge=pin(b["h_edge"]), px=pin(ph["x"]), ppos=pin(ph["pos"]), pnorm=pin(ph["norm"]))
+    h2d = sum(t.numel() * t.element_size() for t in host_in.values())
+    host_out = dict(node_cls=torch.empty(plan.Nl, dtype=torch.int32).pin_memory(), edge_cls=torch.empty(plan.Eb, dtype=torch.int32).pin_memory(),
+                    pos=torch.empty(plan.Nl, 3).pin_memory())
+    d2h = sum(t.numel() * t.element_size() for t in host_out.values())
+    bn, be, bp = b["batch_node"].to(dev), b["batch_edge"].to(dev), ph["batch"].to(dev)
+    ei = b["edge_index"].to(dev)
+    tstep = torch.full((G,), 500, dtype=torch.int64, device=dev)
+    log_node, log_edge = smp.log_node.clone(), smp.log_edge.clone()
+    ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+    pm = model.packed(dev)
+
+    def e2e_step():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host_in.items()}
+        v, pos, e, _ = model(d["h_node"], d["pos"], bn, d["h_edge"], ei, be, tstep, d["px"], d["ppos"], d["pnorm"], bp, plan=plan)
+        _, nc = plan.categorical_step(pm, "node", v, log_node, tstep, seed=1, step_counter=ctr)
+        _, ec = plan.categorical_step(pm, "edge", e, log_edge, tstep, seed=1, step_counter=ctr)
+        xp = plan.position_step(pm, d["pos"], pos, tstep, seed=1, step_counter=ctr)
+        host_out["node_cls"].copy_(nc, non_blocking=True)
+        host_out["edge_cls"].copy_(ec, non_blocking=True)
+        host_out["pos"].copy_(xp, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_e2e = max(3, min(K, 10))
+    e0.record()
+    for _ in range(n_e2e):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / n_e2e
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * G / (e2e_ms * 1e-3 * TRAJ_STEPS)
+
+    if rank == 0:
+        peaks = load_peaks()
+        n = args.atoms
+        f_ref, f_trip_layer = f_ref_flops(n, p_mean)
+        trip_launch_ms = trip_ms / max(trip_n, 1)
+        achieved = f_trip_layer * G / (trip_launch_ms * 1e-3) / 1e12
+        exec_tf = f_exec_trip_flops(n) * G / (trip_launch_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "trip_kernel (BondUpdateLayer, uni_denoiser.py:123-165)",
+                "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
+                "traffic": None, "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                "launch_ms": trip_launch_ms, "launches_timed": trip_n,
+                "algorithmic_flops_per_launch": f_trip_layer * G, "executed_flops_per_launch": f_exec_trip_flops(n) * G,
+                "achieved_executed": exec_tf,
+                "note": "achieved counts the reference formulation's FLOPs (SURVEY.md §8(d) term C); the kernel executes the exactly "
+                        "factorised form in fp32 on the FFMA pipe (round-1 kernel; tcgen05 version is the next step), so the "
+                        "executed-FLOP rate is `achieved_executed`",
+                "step_share": trip_ms / n_prof / max(sum(class_ms.values()), 1e-9), "ms_per_step_by_kernel_class": class_ms,
+                "whole_step_f_ref_tflops": f_ref * G / (ms_per_step * 1e-3) / 1e12}
+        line = {
+            "metric": "molecules/sec (full 1000-step reverse trajectory)", "value": value, "unit": "molecules/s", "n_gpus": world,
+            "steps": K, "warmup": max(W, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"configs[1]: {G} molecules/GPU x {n} heavy atoms, 6-8 pharmacophore features (mean {p_mean:.2f}), "
+                                   "random-init weights, seed 2032", "molecules_per_gpu": G, "atoms": n, "trajectory_steps": TRAJ_STEPS,
+                       "step": "PhoreDiff.forward + categorical/Gaussian posterior update (diffusion.py:432-517), whole step replayed as one CUDA graph",
+                       "value_formula": "n_gpus * molecules_per_gpu / (1000 * seconds_per_step)",
+                       "l2": f"per-step working set {plan.workspace_bytes / 2**30:.1f} GiB >> 126 MB L2 (inputs larger than L2; no flush needed)",
+                       "parallelism": f"molecule-sharded x{world}, final gather only"},
+            "roofline": roof,
+            "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                    "call": "PhoreDiff.forward(host tensors) + pg_categorical_step/pg_position_step, pinned H2D and D2H inside the timed region"},
+            "gpu_launches": int(launches_per_step * K),
+            "gpu_launches_per_step": int(launches_per_step),
+            "clocks": clk,
+            "denoiser_step_ms": ms_per_step,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            sec, cores = cpu_reference_step_time(args.cpu_molecules, n, 2, 1)
+            line["cpu_baseline"] = {"value": args.cpu_molecules / (sec * TRAJ_STEPS), "unit": "molecules/s", "cores": cores, "kind": "port",
+                                    "sample": f"{args.cpu_molecules} molecules x {n} atoms, 1 warm-up + 2 timed reverse steps ({sec:.2f} s/step), extrapolated x1000"}
+        if gathered is not None:
+            line["config"]["gathered_molecules"] = int(gathered["num_atoms"].numel())
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--molecules", type=int, default=1024, help="molecules per GPU")
+    ap.add_argument("--atoms", type=int, default=30)
+    ap.add_argument("--cpu-molecules", type=int, default=4, help="bounded CPU sample size")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-trajectory", action="store_true", help="time all 1000 steps")
+    args = ap.parse_args()
+    if args.full_trajectory:
+        args.steps = TRAJ_STEPS - max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -138,6 +138,10 @@ int pg_guidance_grad(const PgPlan* p, const float* d_pos, const int32_t* d_edge_
 const int32_t* pg_plan_ligand_graph(const PgPlan* p);   /* device [Nl]  atom -> graph */
 const int32_t* pg_plan_edge_graph(const PgPlan* p);     /* device [E_b] reference-order edge -> graph */
 int64_t pg_plan_kernel_launches(const PgPlan* p);       /* kernels launched through this plan so far */
+/* Per-kernel-class device timing with CUDA events on the launching stream (eager launches only, not under
+ * stream capture).  Classes: 0 dense GEMM, 1 kNN attention, 2 bond attention, 3 triplet, 4 kNN graph build, 5 other. */
+int pg_plan_timing_enable(PgPlan* p, int on);
+int pg_plan_timing_read(PgPlan* p, int kernel_class, double* ms_total, int64_t* launches);   /* synchronous */
 
 #ifdef __cplusplus
 }

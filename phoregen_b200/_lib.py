@@ -53,6 +53,8 @@ _SIGS = {
     "pg_plan_ligand_graph": (_P, [_P]),
     "pg_plan_edge_graph": (_P, [_P]),
     "pg_plan_kernel_launches": (c_int64, [_P]),
+    "pg_plan_timing_enable": (c_int, [_P, c_int]),
+    "pg_plan_timing_read": (c_int, [_P, c_int, POINTER(ctypes.c_double), POINTER(c_int64)]),
 }
 for _name, (_res, _args) in _SIGS.items():
     _fn = getattr(lib, _name)          # AttributeError here = header/library drift; never silently ignored

@@ -135,6 +135,7 @@ extern "C" int pg_plan_create(PgPlan** out, int G, const int32_t* na, const int3
     PgPlan* pl = new PgPlan();
     pl->edge_order = edge_order;
     pl->launches = 0;
+    pl->timing = 0;
     Carver c(d_workspace);
     carve(c, s, G, pl);
     PlanDev& d = pl->d;
@@ -231,6 +232,21 @@ extern "C" int64_t pg_plan_num_triplets(const PgPlan* p) { return p->d.E3; }
 extern "C" const int32_t* pg_plan_ligand_graph(const PgPlan* p) { return p->d.lig_graph; }
 extern "C" const int32_t* pg_plan_edge_graph(const PgPlan* p) { return p->d.edge_graph; }
 extern "C" int64_t pg_plan_kernel_launches(const PgPlan* p) { return p->launches; }
+extern "C" int pg_plan_timing_enable(PgPlan* p, int on) {
+    for (int c = 0; c < KC_COUNT; c++) { for (auto e : p->tev[c]) cudaEventDestroy(e); p->tev[c].clear(); }
+    p->timing = on;
+    return PG_OK;
+}
+extern "C" int pg_plan_timing_read(PgPlan* p, int kclass, double* ms_total, int64_t* launches) {
+    if (kclass < 0 || kclass >= KC_COUNT || !ms_total || !launches) { pg_set_error("pg_plan_timing_read: bad argument"); return PG_EINVAL; }
+    double tot = 0; auto& v = p->tev[kclass];
+    for (size_t i = 0; i + 1 < v.size(); i += 2) {
+        PG_CUDA_CHECK(cudaEventSynchronize(v[i + 1]));
+        float ms = 0; PG_CUDA_CHECK(cudaEventElapsedTime(&ms, v[i], v[i + 1])); tot += ms;
+    }
+    *ms_total = tot; *launches = (int64_t)(v.size() / 2);
+    return PG_OK;
+}
 
 // ---------------------------------------------------------------- G1 export
 __global__ void export_edges_kernel(PlanDev d, const int* __restrict__ inv_perm, int64_t* ei, int64_t* eb) {
@@ -362,6 +378,7 @@ int pg_launch_knn(PgPlan* p, const float* x, const float* phore_norm, int mode, 
     const int wpb = 4;
     size_t smem = (size_t)wpb * (d.max_ng + 8) * sizeof(float);
     unsigned grid = (unsigned)((d.N + wpb - 1) / wpb);
+    PgTimed timed(p, KC_GRAPH, stream);
     if (mode == 0) {
         knn_kernel<0><<<grid, wpb * 32, smem, stream>>>(d, x, phore_norm, knn_src, comb, ei, d.Ek);
     } else {

@@ -252,6 +252,7 @@ int gemm(PgPlan* p, cudaStream_t s, int pro, long long M, const float* A, long l
     a.M = M; a.A = A; a.lda = lda; a.A2 = A2; a.lda2 = lda2; a.gidx = gidx; a.ln_g = lng; a.ln_b = lnb;
     a.Wt = Wt; a.ldw = ldw; a.bias = bias; a.C = C; a.ldc = ldc; a.ntiles = ntiles; a.resid = resid; a.ldr = ldr; a.relu = 0;
     p->launches++;
+    PgTimed timed(p, KC_GEMM, s);
     return pg_launch_gemm(a, pro, s);
 }
 
@@ -304,7 +305,7 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
             a.d = d; a.x = p->x; a.comb = p->comb; a.knn_src = p->knn_src; a.ew = p->ew;
             a.nc = NodeCols{p->nbuf, N1_COLS, N1_NK_DK, N1_NK_SK, N1_NK_DV, N1_NK_SV};
             a.q = p->qn1; a.w = attn_w(w, L + "nk.", true); a.out = p->o1; a.maxr = maxr_knn;
-            PG_TRY(pg_launch_knn_attn(a, 0, 0, s)); p->launches++;
+            { PgTimed timed(p, KC_KNN_ATTN, s); PG_TRY(pg_launch_knn_attn(a, 0, 0, s)); } p->launches++;
         }
         {   // node update over the bond graph
             BondAttnArgs a;
@@ -312,7 +313,7 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
             a.nc = NodeCols{p->nbuf, N1_COLS, N1_NB_DK, N1_NB_SK, N1_NB_DV, N1_NB_SV};
             a.B = p->ebuf; a.ldb = E1_COLS; a.b_k = E1_NB_K; a.b_v = E1_NB_V;
             a.q = p->qn2; a.w = attn_w(w, L + "nb.", false); a.out = p->o2; a.maxr = maxr_bond;
-            PG_TRY(pg_launch_bond_attn(a, 0, s)); p->launches++;
+            { PgTimed timed(p, KC_BOND_ATTN, s); PG_TRY(pg_launch_bond_attn(a, 0, s)); } p->launches++;
         }
         {   // bond update over triplets (uses the old h, x); h_bond updated in place
             TripArgs a;
@@ -320,7 +321,7 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
             a.H = p->nbuf; a.ldh = N1_COLS; a.hk_k = N1_TR_HK_K; a.hj_k = N1_TR_HJ_K; a.hk_v = N1_TR_HK_V; a.hj_v = N1_TR_HJ_V;
             a.q = p->qt; a.wrkj = w(L + "tr.wrkj"); a.wrji = w(L + "tr.wrji"); a.wa = w(L + "tr.wa");
             a.w = attn_w(w, L + "tr.", false); a.hb = p->hb; a.maxr = maxr_trip; a.maxn = d.max_n;
-            PG_TRY(pg_launch_trip(a, s)); p->launches++;
+            { PgTimed timed(p, KC_TRIP, s); PG_TRY(pg_launch_trip(a, s)); } p->launches++;
         }
         // h <- h + lin_node(o1 + o2)
         PG_TRY(gemm(p, s, PRO_SUM2, N, p->o1, 128, w(L + "lin.wt"), 128, w(L + "lin.b"), p->h, 128, 1, p->o2, 128, nullptr,
@@ -337,7 +338,7 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
             a.d = d; a.x = p->x; a.comb = p->comb; a.knn_src = p->knn_src; a.ew = p->ew;
             a.nc = NodeCols{p->nbuf, N2_COLS, N2_PK_DK, N2_PK_SK, N2_PK_DV, N2_PK_SV};
             a.q = p->qn1; a.w = attn_w(w, L + "pk.", true); a.out = p->dx1; a.maxr = maxr_knn;
-            PG_TRY(pg_launch_knn_attn(a, 0, 1, s)); p->launches++;
+            { PgTimed timed(p, KC_KNN_ATTN, s); PG_TRY(pg_launch_knn_attn(a, 0, 1, s)); } p->launches++;
         }
         {
             BondAttnArgs a;
@@ -345,7 +346,7 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
             a.nc = NodeCols{p->nbuf, N2_COLS, N2_PB_DK, N2_PB_SK, N2_PB_DV, N2_PB_SV};
             a.B = p->ebuf; a.ldb = 256; a.b_k = 0; a.b_v = 128;
             a.q = p->qn2; a.w = attn_w(w, L + "pb.", false); a.out = p->dx2; a.maxr = maxr_bond;
-            PG_TRY(pg_launch_bond_attn(a, 1, s)); p->launches++;
+            { PgTimed timed(p, KC_BOND_ATTN, s); PG_TRY(pg_launch_bond_attn(a, 1, s)); } p->launches++;
         }
         pos_update_kernel<<<(unsigned)((N * 3 + 255) / 256), 256, 0, s>>>(d, p->x, p->dx1, p->dx2);
         PG_LAUNCH_CHECK(); p->launches++;

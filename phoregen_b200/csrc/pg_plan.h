@@ -23,6 +23,21 @@ struct PgPlan {
     float* gcnt;                  // [G] scratch (guidance)
     int* flag;                    // device error flag
     long long launches;
+    // optional per-kernel-class device timing (eager mode only; bench.py's roofline leg)
+    int timing;
+    std::vector<cudaEvent_t> tev[8];   // pairs (start, stop) per class
+};
+
+enum PgKernelClass { KC_GEMM = 0, KC_KNN_ATTN, KC_BOND_ATTN, KC_TRIP, KC_GRAPH, KC_OTHER, KC_COUNT };
+
+struct PgTimed {   // RAII: CUDA events around one launch on the launching stream
+    PgPlan* p; int c; cudaStream_t s;
+    PgTimed(PgPlan* p_, int c_, cudaStream_t s_) : p(p_), c(c_), s(s_) {
+        if (p->timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); p->tev[c].push_back(e); }
+    }
+    ~PgTimed() {
+        if (p->timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); p->tev[c].push_back(e); }
+    }
 };
 
 // weight slots -------------------------------------------------------------------------------------

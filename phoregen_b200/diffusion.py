@@ -223,22 +223,36 @@ class TrajectorySampler:
     so the whole step is captured once and replayed `num_timesteps` times."""
 
     def __init__(self, model, data, n_graphs, device, ligand_num_atoms=None, sample_mode="uniform", normal_scale=4.0,
-                 guidance=None, save_traj=True, seed=None, use_cuda_graph=True):
+                 guidance=None, save_traj=True, seed=None, use_cuda_graph=True, phore_batch=None):
+        """`data` is one pharmacophore replicated `n_graphs` times (the reference's sample()); alternatively
+        `phore_batch` = dict(x [P,18], pos [P,3], norm [P,3], batch [P]) supplies a different pharmacophore per
+        molecule (something the reference's sample() cannot do: sample_all.py:69-94 handles one at a time)."""
         self.m, self.device, self.G = model, device, n_graphs
         self.T = model.num_timesteps
         pm = self.pm = model.packed(device)
-        ph = data["phore"]
-        px, ppos, pnorm = ph.x.to(device).float(), ph.pos.to(device).float(), ph.norm.to(device).float()
-        if ligand_num_atoms is None:
-            ligand_num_atoms = model.sample_nodes(data, n_graphs, device, sample_mode, normal_scale)
+        if phore_batch is None:
+            ph = data["phore"]
+            px, ppos, pnorm = ph.x.to(device).float(), ph.pos.to(device).float(), ph.norm.to(device).float()
+            if ligand_num_atoms is None:
+                ligand_num_atoms = model.sample_nodes(data, n_graphs, device, sample_mode, normal_scale)
+            num_phore = np.full(n_graphs, px.shape[0], dtype=np.int32)
+            center = getattr(data, "center", None)
+            # Batch.from_data_list([data.clone()] * n_graphs)  (diffusion.py:399)
+            self.px, self.ppos, self.pnorm = px.repeat(n_graphs, 1), ppos.repeat(n_graphs, 1).contiguous(), pnorm.repeat(n_graphs, 1).contiguous()
+            single_x, single_pos = px, ppos
+        else:
+            if ligand_num_atoms is None:
+                raise ValueError("phore_batch needs explicit ligand_num_atoms")
+            self.px = phore_batch["x"].to(device).float().contiguous()
+            self.ppos = phore_batch["pos"].to(device).float().contiguous()
+            self.pnorm = phore_batch["norm"].to(device).float().contiguous()
+            num_phore = torch.bincount(phore_batch["batch"], minlength=n_graphs).cpu().numpy().astype(np.int32)
+            center = None
+            single_x = single_pos = None
         self.num_atoms = torch.as_tensor(ligand_num_atoms).to(device)
         na = self.num_atoms.cpu().numpy().astype(np.int32)
-        center = getattr(data, "center", None)
         self.center = (torch.zeros(3, device=device) if center is None else torch.as_tensor(center).to(device).float()).contiguous()
-        p = px.shape[0]
-        plan = self.plan = BatchPlan(na, np.full(n_graphs, p, dtype=np.int32), device, edge_order=0)
-        # Batch.from_data_list([data.clone()] * n_graphs)  (diffusion.py:399)
-        self.px, self.ppos, self.pnorm = px.repeat(n_graphs, 1), ppos.repeat(n_graphs, 1).contiguous(), pnorm.repeat(n_graphs, 1).contiguous()
+        plan = self.plan = BatchPlan(na, num_phore, device, edge_order=0)
         self.h_phore_emb = plan.phore_encode(pm, self.px, self.ppos)      # step-invariant (SURVEY.md §8(d) reduction 4)
         self.batch_node = torch.repeat_interleave(torch.arange(n_graphs, device=device), self.num_atoms.long())
         self.edge_index, self.edge_batch = plan.bond_edges()                # G1 on device
@@ -259,8 +273,10 @@ class TrajectorySampler:
         self.grad = torch.zeros(Nl, 3, device=device) if guidance else None
         self.phore_center = None
         if guidance:
+            if single_x is None:
+                raise NotImplementedError("guidance needs the single-pharmacophore form (its energy uses one phore centre)")
             col = 12 if model.data_name in ("zinc_300", "pdbbind") else 10
-            self.phore_center = ppos[px[:, col] != 1].mean(0).contiguous()   # diffusion.py:493-497
+            self.phore_center = single_pos[single_x[:, col] != 1].mean(0).contiguous()   # diffusion.py:493-497
         self.save_traj = save_traj
         if save_traj:
             try:

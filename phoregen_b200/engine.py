@@ -107,6 +107,20 @@ class BatchPlan:
     def launches(self):
         return int(lib.pg_plan_kernel_launches(self.handle))
 
+    KERNEL_CLASSES = ("gemm", "knn_attn", "bond_attn", "trip", "knn_graph", "other")
+
+    def timing(self, on):
+        check(lib.pg_plan_timing_enable(self.handle, int(bool(on))), "pg_plan_timing_enable")
+
+    def read_timing(self):
+        """-> {class: (total_ms, launches)} measured with CUDA events on the launching stream."""
+        out = {}
+        for i, name in enumerate(self.KERNEL_CLASSES):
+            ms, n = ctypes.c_double(), ctypes.c_int64()
+            check(lib.pg_plan_timing_read(self.handle, i, ctypes.byref(ms), ctypes.byref(n)), "pg_plan_timing_read")
+            out[name] = (ms.value, n.value)
+        return out
+
     # ---- graph artefacts (G1, B1, K1) ------------------------------------------------------
     def bond_edges(self):
         ei = _alloc((2, self.Eb), torch.int64, self.device)

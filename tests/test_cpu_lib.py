@@ -1,0 +1,87 @@
+"""CPU tests of the boundary: the C-ABI library loads without a GPU and exports every symbol the header declares;
+the weight packer and the library agree on the slot table; host-side helpers."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import ROOT, build_model
+
+
+def test_library_exports_every_declared_symbol():
+    from phoregen_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "phoregen_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(pg_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(_lib.lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    assert _lib.lib.pg_version() >= 100
+
+
+def test_weight_packer_fills_every_slot():
+    from phoregen_b200 import _lib
+    from phoregen_b200.weights import build_blob, pack_state_dict
+    _, sd = build_model()
+    table = _lib.slot_table()
+    assert len(table) == len({n for n, _ in table})
+    blob, off = build_blob(sd)
+    assert blob.dtype == np.float32 and np.all(off % 4 == 0) and np.isfinite(blob).all()
+    packed = pack_state_dict(sd)
+    # the fold of dire_embedding and the type-selected smearing slices reproduce the reference's first Linear exactly
+    rng = np.random.default_rng(0)
+    W1 = sd["denoiser.base_block.2.node_layer_with_edge.hk_func.net.0.weight"].double().numpy()
+    b1 = sd["denoiser.base_block.2.node_layer_with_edge.hk_func.net.0.bias"].double().numpy()
+    Wde = sd["denoiser.base_block.2.dire_embedding.weight"].double().numpy()
+    bde = sd["denoiser.base_block.2.dire_embedding.bias"].double().numpy()
+    smear, dots, hd, hs = rng.random(20), rng.normal(size=3), rng.normal(size=128), rng.normal(size=128)
+    for t in range(4):
+        onehot = np.eye(4)[t]
+        edge_feat = np.concatenate([np.outer(onehot, smear).reshape(-1), onehot, Wde @ dots + bde])
+        want = W1 @ np.concatenate([edge_feat, hd, hs]) + b1
+        tab = packed["L2.nk.tab_k"][t]
+        n1, nb = packed["L2.n1.wt"], packed["L2.n1.b"]
+        got = (smear @ tab[:20] + tab[20] + dots @ tab[21:24] + hd @ n1[:, 0:128] + nb[0:128] + hs @ n1[:, 128:256] + nb[128:256])
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    from phoregen_b200 import _lib
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.PhoreGenLibraryError, match="no CPU / PyTorch fallback"):
+        _lib._load()
+
+
+def test_cpu_device_is_refused():
+    from phoregen_b200 import _lib
+    from phoregen_b200.engine import PackedModel
+    _, sd = build_model()
+    with pytest.raises(_lib.PhoreGenLibraryError, match="CUDA devices only"):
+        PackedModel(sd, "cpu")
+
+
+def test_topology_from_context():
+    from oracle import phoregen_oracle as O
+    from phoregen_b200.modules import topology_from_context
+    bp = torch.tensor([0, 0, 0, 1, 1, 2])
+    bl = torch.tensor([0, 0, 1, 1, 1, 1, 2, 2])
+    _, batch, mask, _, _ = O.compose_context(bp, bl)
+    p, n = topology_from_context(batch, mask)
+    assert p.tolist() == [3, 2, 1] and n.tolist() == [2, 4, 2]
+    with pytest.raises(ValueError):
+        topology_from_context(batch, ~mask)
+
+
+def test_schedules_shapes_and_invariants():
+    from phoregen_b200 import schedules
+    b = schedules.beta_schedule("segment", 1000, time_segment=[600, 400],
+                                segment_diff=[dict(scale_start=0.9999, scale_end=0.001, width=3), dict(scale_start=0.001, scale_end=0.0001, width=2)])
+    assert b.shape == (1000,) and (b >= 0).all() and (b <= 1).all()
+    tabs, prior = schedules.categorical_tables(b, 6, "absorb")
+    np.testing.assert_allclose(tabs["q_mats"].sum(-1), 1.0, atol=1e-9)       # rows of a transition matrix
+    np.testing.assert_allclose(prior.sum(), 1.0)
+    g = schedules.gaussian_tables(schedules.beta_schedule("advance", 1000, scale_start=0.9999, scale_end=0.0001, width=3))
+    assert g["std"][0] == 0.0 and np.all(np.diff(g["alphas_bar"]) <= 0)

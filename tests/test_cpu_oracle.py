@@ -1,0 +1,113 @@
+"""CPU tests: the oracle restatement against the golden fixtures produced by the unmodified reference
+(and against the reference itself where /root/reference is mounted)."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import assert_close, build_model, load_golden
+from oracle import phoregen_oracle as O
+
+HAVE_REF = os.path.isdir("/root/reference/models")
+
+
+@pytest.fixture(scope="module")
+def sd():
+    from phoregen_b200.testing import state_dict_digest
+    _, sd = build_model()
+    assert load_golden("meta.pt")["state_dict_digest"] == state_dict_digest(sd)
+    return sd
+
+
+def test_state_dict_layout_matches_reference_checkpoint_contract(sd):
+    meta = load_golden("meta.pt")
+    assert len(sd) == 641
+    assert sorted((k, tuple(v.shape)) for k, v in sd.items()) == meta["keys"]
+
+
+def test_oracle_graph_artefacts_match_reference_golden():
+    g = load_golden("graph.pt")
+    ei, eb = O.make_edge_data(g["num_atoms"])
+    assert torch.equal(ei, g["edge_index"]) and torch.equal(eb, g["edge_batch"])
+    assert torch.equal(O.knn_graph(g["x"], 32, g["batch"]), g["knn32"])
+    m = g["mask_ligand"]
+    assert torch.equal(O.knn_graph(g["x"][m], 3, g["batch"][m]), g["knn3"])
+    for got, want in zip(O.triplets(g["bond_ctx"], g["x"].shape[0]), g["triplets"]):
+        assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("name", ["forward_small.pt", "forward_ex.pt"])
+def test_oracle_forward_matches_reference_golden(sd, name):
+    f = load_golden(name)
+    b = O.synthetic_batch(f["seed"], f["n_graphs"], n_atoms=f["n_atoms"], n_ex=f["n_ex"])
+    ph = b["phore"]
+    stages = []
+    v, pos, e, cnt = O.phorediff_forward(sd, b["h_node"], b["pos"], b["batch_node"], b["h_edge"], b["edge_index"],
+                                         b["batch_edge"], torch.tensor(f["times"]), ph["x"], ph["pos"], ph["norm"], ph["batch"],
+                                         stages=stages)
+    tight = dict(rtol=1e-5, atol=2e-5)
+    assert_close(v, f["pred_node"], "logits_node", **tight)
+    assert_close(pos, f["pred_pos"], "pos", **tight)
+    assert_close(e, f["pred_edge"], "logits_edge", **tight)
+    assert_close(cnt[0], f["count_l"], "count_l", **tight)
+    if "layer0" in f:
+        assert_close(stages[0]["h_phore_emb"], f["h_phore_emb"], "h_phore_emb", **tight)
+        for got, want, what in zip((stages[2]["h"], stages[2]["h_bond"], stages[2]["x"]), f["layer0"], ("h", "h_bond", "x")):
+            assert_close(got, want, "layer0 " + what, **tight)
+
+
+def test_oracle_transitions_match_reference_golden(sd):
+    f = load_golden("transition.pt")
+    for kind in ("node", "edge"):
+        d = f[kind]
+        post = O.q_v_posterior(sd[f"{kind}_transition.q_mats"], sd[f"{kind}_transition.transpopse_q_onestep_mats"],
+                               F.log_softmax(d["pred"], -1), d["log_vt"], f["t"], d["batch"])
+        assert torch.equal(post, d["post"])
+        assert torch.equal(O.log_sample_categorical(post, d["uniform"]), d["cls"])
+    p = f["pos"]
+    assert torch.equal(O.pos_prev_from_recon(sd, p["x_t"], p["x_recon"], f["t"], p["batch"], p["normal"], p["grad"]), p["x_prev"])
+
+
+def test_oracle_reverse_steps_match_reference_golden(sd):
+    f = load_golden("reverse_steps.pt")
+    b = O.synthetic_batch(f["seed"], 3, n_atoms=(8, 11))
+    topo = dict(batch_node=b["batch_node"], edge_index=b["edge_index"], batch_edge=b["batch_edge"], n_graphs=3)
+    st = f["init"]
+    for step, d, want in zip(f["steps"], f["draws"], f["outs"]):
+        st, out = O.reverse_step(sd, st, step, topo, b["phore"], d)
+        assert torch.equal(out["node_cls"], want["node_cls"]) and torch.equal(out["edge_cls"], want["edge_cls"])
+        assert_close(st["pos"], want["pos"], "pos", rtol=1e-5, atol=1e-5)
+        assert_close(st["log_edge"], want["log_edge"], "log_edge", rtol=1e-5, atol=1e-5)
+
+
+def test_synthetic_batch_is_reproducible():
+    a, b = O.synthetic_batch(2032, 3, n_atoms=30), O.synthetic_batch(2032, 3, n_atoms=30)
+    assert torch.equal(a["pos"], b["pos"]) and torch.equal(a["phore"]["x"], b["phore"]["x"])
+    assert a["edge_index"].shape == (2, 3 * 870) and a["phore"]["x"].shape[1] == 18
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference not mounted")
+def test_oracle_matches_unmodified_reference_live(sd):
+    import yaml
+    from oracle.shims.install import EasyDict, install
+    install()
+    from models.diffusion import PhoreDiff
+    cfg = EasyDict(yaml.safe_load(open("/root/reference/configs/train_lig-phore.yml")))
+    cfg.model.phore_feat_dim += 2
+    ref = PhoreDiff(cfg.model, "zinc_300").eval()
+    # the mirror's schedule tables are bit-identical to the reference's own constructor output
+    own = ref.state_dict()
+    for k in own:
+        if "transition" in k or k.endswith(("offset", "coeff", "freq_bands")):
+            assert torch.equal(own[k], sd[k]), k
+    ref.load_state_dict(sd, strict=True)
+    b = O.synthetic_batch(55, 2, n_atoms=(5, 8), n_ex=10)
+    ph = b["phore"]
+    t = torch.tensor([321, 0])
+    with torch.no_grad():
+        want = ref(b["h_node"], b["pos"], b["batch_node"], b["h_edge"], b["edge_index"], b["batch_edge"], t, ph["x"], ph["pos"], ph["norm"], ph["batch"])
+    got = O.phorediff_forward(sd, b["h_node"], b["pos"], b["batch_node"], b["h_edge"], b["edge_index"], b["batch_edge"], t, ph["x"], ph["pos"], ph["norm"], ph["batch"])
+    for g_, w_ in zip(got[:3], want[:3]):
+        assert_close(g_, w_, "forward", rtol=1e-5, atol=2e-5)
