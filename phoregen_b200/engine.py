@@ -168,11 +168,12 @@ class BatchPlan:
         assert h_node.shape == (self.Nl, 12) and pos.shape == (self.Nl, 3) and h_edge.shape == (self.Eb, 6)
         assert time_step.dtype == torch.int64 and time_step.shape == (self.G,) and time_step.is_contiguous()
         assert h_phore_emb.shape == (self.P, 128)
+        h_phore_emb, pos_phore, phore_norm = _f32(h_phore_emb), _f32(pos_phore), _f32(phore_norm)   # keep converted copies alive
         if out is None:
             out = (_alloc((self.Nl, 12), torch.float32, self.device), _alloc((self.Nl, 3), torch.float32, self.device),
                    _alloc((self.Eb, 6), torch.float32, self.device))
         check(lib.pg_phorediff_forward(model.handle, self.handle, _ptr(h_node), _ptr(pos), _ptr(h_edge), _ptr(time_step),
-                                       _ptr(_f32(h_phore_emb)), _ptr(_f32(pos_phore)), _ptr(_f32(phore_norm)),
+                                       _ptr(h_phore_emb), _ptr(pos_phore), _ptr(phore_norm),
                                        _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _stream()), "pg_phorediff_forward")
         return out
 

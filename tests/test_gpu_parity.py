@@ -189,8 +189,9 @@ def test_transition_matches_reference_golden(model, dev):
     rg = e["batch"].to(dev).int().contiguous()
     oh = torch.empty(rows, 6, device=dev); cl = torch.empty(rows, dtype=torch.int32, device=dev)
     P = lambda x: ctypes.c_void_p(x.data_ptr())
-    check(lib.pg_categorical_step(rows, 6, P(e["pred"].to(dev)), P(log_vt), P(pm.tables["edge_transition.q_mats"]),
-                                  P(pm.tables["edge_transition.transpopse_q_onestep_mats"]), P(t), P(rg), P(e["uniform"].to(dev)),
+    pred_d, uni_d = e["pred"].to(dev), e["uniform"].to(dev)      # keep the device tensors alive across the launch
+    check(lib.pg_categorical_step(rows, 6, P(pred_d), P(log_vt), P(pm.tables["edge_transition.q_mats"]),
+                                  P(pm.tables["edge_transition.transpopse_q_onestep_mats"]), P(t), P(rg), P(uni_d),
                                   0, 2, None, P(oh), P(cl), None, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "cat")
     assert_close(log_vt, e["post"], "edge posterior", rtol=1e-5, atol=1e-5)
     safe = e["margin"] > 1e-4
