@@ -9,7 +9,8 @@ struct GemmArgs {
     const float* A2; long long lda2;     // SUM2: second input; LNRELU: optional gather-add rows A2[gidx[m]]
     const int* gidx;                     // optional row gather for A2
     const float* ln_g; const float* ln_b;
-    const float* Wt; long long ldw;      // [128][ldw] (k-major); column block nt starts at nt*128
+    const float* Wt; long long ldw;      // [128][ldw] (k-major); column block nt starts at nt*128   (fp32 SIMT kernel)
+    const float* Wbf;                    // bf16 hi|lo split of the same weight, [2][ntiles*128][128] K-major (tcgen05 kernel)
     const float* bias;                   // [ntiles*128] or null
     float* C; long long ldc;
     int ntiles;
@@ -17,4 +18,5 @@ struct GemmArgs {
     int relu;
 };
 
-int pg_launch_gemm(const GemmArgs& a, int pro, cudaStream_t stream);
+int pg_launch_gemm(const GemmArgs& a, int pro, cudaStream_t stream);      // fp32 FFMA reference kernel (PG_GEMM=simt)
+int pg_launch_gemm_tc(const GemmArgs& a, int pro, cudaStream_t stream);   // tcgen05 / TMEM bf16x3 kernel (default)

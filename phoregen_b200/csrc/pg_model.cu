@@ -25,25 +25,25 @@ std::vector<PgSlotDesc> build_slots() {
     add("G.node_emb_t", 12 * 118); add("G.edge_emb_t", 6 * 118);
     add("G.time_coeff", 10); add("G.time_offset", 10);
     add("G.ph_emb_wt", 18 * 128); add("G.ph_emb_b", 128);
-    add("PE.wcat_t", 128 * 640); add("PE.bcat", 640);
+    add("PE.wcat_t", 128 * 640); add("PE.wcat_t.bf", 128 * 640); add("PE.bcat", 640);
     add("PE.wd_k", 128); add("PE.wd_v", 128);
     add("PE.lnk_g", 128); add("PE.lnk_b", 128); add("PE.lnv_g", 128); add("PE.lnv_b", 128);
-    add("PE.lnq_g", 128); add("PE.lnq_b", 128); add("PE.w2q_t", 128 * 128); add("PE.b2q", 128);
+    add("PE.lnq_g", 128); add("PE.lnq_b", 128); add("PE.w2q_t", 128 * 128); add("PE.w2q_t.bf", 128 * 128); add("PE.b2q", 128);
     add("PE.w2k", 128 * 128); add("PE.b2k", 128); add("PE.w2v", 128 * 128); add("PE.b2v", 128);
     add("G.ew.w1t", 20 * 128); add("G.ew.b1", 128); add("G.ew.ln_g", 128); add("G.ew.ln_b", 128);
     add("G.ew.w2", 128); add("G.ew.b2", 4);
-    add("G.vinf.w1t", 128 * 128); add("G.vinf.b1", 128); add("G.vinf.w2", 12 * 128); add("G.vinf.b2", 12);
-    add("G.binf.w1t", 128 * 128); add("G.binf.b1", 128); add("G.binf.w2", 6 * 128); add("G.binf.b2", 8);
+    add("G.vinf.w1t", 128 * 128); add("G.vinf.w1t.bf", 128 * 128); add("G.vinf.b1", 128); add("G.vinf.w2", 12 * 128); add("G.vinf.b2", 12);
+    add("G.binf.w1t", 128 * 128); add("G.binf.w1t.bf", 128 * 128); add("G.binf.b1", 128); add("G.binf.w2", 6 * 128); add("G.binf.b2", 8);
     for (int l = 0; l < PG_NUM_LAYERS; l++) {
         std::string L = "L" + std::to_string(l) + ".";
-        add(L + "n1.wt", 128 * 1920); add(L + "n1.b", 1920);
-        add(L + "e1.wt", 128 * 640); add(L + "e1.b", 640);
-        add(L + "n2.wt", 128 * 1280); add(L + "n2.b", 1280);
-        add(L + "e2.wt", 128 * 256); add(L + "e2.b", 256);
-        add(L + "lin.wt", 128 * 128); add(L + "lin.b", 128);
+        add(L + "n1.wt", 128 * 1920); add(L + "n1.wt.bf", 128 * 1920); add(L + "n1.b", 1920);
+        add(L + "e1.wt", 128 * 640); add(L + "e1.wt.bf", 128 * 640); add(L + "e1.b", 640);
+        add(L + "n2.wt", 128 * 1280); add(L + "n2.wt.bf", 128 * 1280); add(L + "n2.b", 1280);
+        add(L + "e2.wt", 128 * 256); add(L + "e2.wt.bf", 128 * 256); add(L + "e2.b", 256);
+        add(L + "lin.wt", 128 * 128); add(L + "lin.wt.bf", 128 * 128); add(L + "lin.b", 128);
         for (int s = 0; s < 5; s++) {
             std::string S = L + kSub[s] + ".";
-            add(S + "lnq_g", 128); add(S + "lnq_b", 128); add(S + "w2q_t", 128 * 128); add(S + "b2q", 128);
+            add(S + "lnq_g", 128); add(S + "lnq_b", 128); add(S + "w2q_t", 128 * 128); add(S + "w2q_t.bf", 128 * 128); add(S + "b2q", 128);
             add(S + "lnk_g", 128); add(S + "lnk_b", 128); add(S + "lnv_g", 128); add(S + "lnv_b", 128);
             add(S + "w2k", 128 * 128); add(S + "b2k", 128);
             const bool pos = s >= 3;
@@ -244,16 +244,24 @@ namespace {
 
 inline int round4(int v) { return (v + 3) & ~3; }
 
-int gemm(PgPlan* p, cudaStream_t s, int pro, long long M, const float* A, long long lda, const float* Wt, long long ldw,
-         const float* bias, float* C, long long ldc, int ntiles, const float* A2 = nullptr, long long lda2 = 0,
+bool use_simt_gemm() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PG_GEMM"); v = (e && !strcmp(e, "simt")) ? 1 : 0; }
+    return v == 1;
+}
+
+// `wname` is the slot of the k-major fp32 weight; "<wname>.bf" holds its bf16 hi/lo split for the tcgen05 kernel
+int gemm(PgPlan* p, cudaStream_t s, int pro, long long M, const float* A, long long lda, const W& w, const std::string& wname,
+         long long ldw, const float* bias, float* C, long long ldc, int ntiles, const float* A2 = nullptr, long long lda2 = 0,
          const int* gidx = nullptr, const float* lng = nullptr, const float* lnb = nullptr, const float* resid = nullptr,
          long long ldr = 0) {
     GemmArgs a;
     a.M = M; a.A = A; a.lda = lda; a.A2 = A2; a.lda2 = lda2; a.gidx = gidx; a.ln_g = lng; a.ln_b = lnb;
-    a.Wt = Wt; a.ldw = ldw; a.bias = bias; a.C = C; a.ldc = ldc; a.ntiles = ntiles; a.resid = resid; a.ldr = ldr; a.relu = 0;
+    a.Wt = w(wname); a.Wbf = w(wname + ".bf"); a.ldw = ldw; a.bias = bias; a.C = C; a.ldc = ldc; a.ntiles = ntiles;
+    a.resid = resid; a.ldr = ldr; a.relu = 0;
     p->launches++;
     PgTimed timed(p, KC_GEMM, s);
-    return pg_launch_gemm(a, pro, s);
+    return use_simt_gemm() ? pg_launch_gemm(a, pro, s) : pg_launch_gemm_tc(a, pro, s);
 }
 
 AttnW attn_w(const W& w, const std::string& S, bool tabs) {
@@ -291,14 +299,14 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
         // direction vectors (k=3 ligand kNN) of this layer's coordinates
         PG_TRY(pg_launch_knn(p, p->x, phore_norm, 1, nullptr, p->comb, nullptr, s));
         // first Linear of every MLP, node and bond parts
-        PG_TRY(gemm(p, s, PRO_PLAIN, N, p->h, 128, w(L + "n1.wt"), N1_COLS, w(L + "n1.b"), p->nbuf, N1_COLS, N1_COLS / 128));
-        PG_TRY(gemm(p, s, PRO_PLAIN, Eb, p->hb, 128, w(L + "e1.wt"), E1_COLS, w(L + "e1.b"), p->ebuf, E1_COLS, E1_COLS / 128));
+        PG_TRY(gemm(p, s, PRO_PLAIN, N, p->h, 128, w, L + "n1.wt", N1_COLS, w(L + "n1.b"), p->nbuf, N1_COLS, N1_COLS / 128));
+        PG_TRY(gemm(p, s, PRO_PLAIN, Eb, p->hb, 128, w, L + "e1.wt", E1_COLS, w(L + "e1.b"), p->ebuf, E1_COLS, E1_COLS / 128));
         // queries: LN -> ReLU -> second Linear
-        PG_TRY(gemm(p, s, PRO_LNRELU, N, p->nbuf + N1_NK_Q, N1_COLS, w(L + "nk.w2q_t"), 128, w(L + "nk.b2q"), p->qn1, 128, 1,
+        PG_TRY(gemm(p, s, PRO_LNRELU, N, p->nbuf + N1_NK_Q, N1_COLS, w, L + "nk.w2q_t", 128, w(L + "nk.b2q"), p->qn1, 128, 1,
                     nullptr, 0, nullptr, w(L + "nk.lnq_g"), w(L + "nk.lnq_b")));
-        PG_TRY(gemm(p, s, PRO_LNRELU, N, p->nbuf + N1_NB_Q, N1_COLS, w(L + "nb.w2q_t"), 128, w(L + "nb.b2q"), p->qn2, 128, 1,
+        PG_TRY(gemm(p, s, PRO_LNRELU, N, p->nbuf + N1_NB_Q, N1_COLS, w, L + "nb.w2q_t", 128, w(L + "nb.b2q"), p->qn2, 128, 1,
                     nullptr, 0, nullptr, w(L + "nb.lnq_g"), w(L + "nb.lnq_b")));
-        PG_TRY(gemm(p, s, PRO_LNRELU, Eb, p->ebuf + E1_TR_Q, E1_COLS, w(L + "tr.w2q_t"), 128, w(L + "tr.b2q"), p->qt, 128, 1,
+        PG_TRY(gemm(p, s, PRO_LNRELU, Eb, p->ebuf + E1_TR_Q, E1_COLS, w, L + "tr.w2q_t", 128, w(L + "tr.b2q"), p->qt, 128, 1,
                     p->nbuf + N1_TR_Q, N1_COLS, d.edst_node, w(L + "tr.lnq_g"), w(L + "tr.lnq_b")));
         {   // node update over the kNN graph
             KnnAttnArgs a;
@@ -324,14 +332,14 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
             { PgTimed timed(p, KC_TRIP, s); PG_TRY(pg_launch_trip(a, s)); } p->launches++;
         }
         // h <- h + lin_node(o1 + o2)
-        PG_TRY(gemm(p, s, PRO_SUM2, N, p->o1, 128, w(L + "lin.wt"), 128, w(L + "lin.b"), p->h, 128, 1, p->o2, 128, nullptr,
+        PG_TRY(gemm(p, s, PRO_SUM2, N, p->o1, 128, w, L + "lin.wt", 128, w(L + "lin.b"), p->h, 128, 1, p->o2, 128, nullptr,
                     nullptr, nullptr, p->h, 128));
         // position update with the new h / h_bond and the old coordinates
-        PG_TRY(gemm(p, s, PRO_PLAIN, N, p->h, 128, w(L + "n2.wt"), N2_COLS, w(L + "n2.b"), p->nbuf, N2_COLS, N2_COLS / 128));
-        PG_TRY(gemm(p, s, PRO_PLAIN, Eb, p->hb, 128, w(L + "e2.wt"), 256, w(L + "e2.b"), p->ebuf, 256, 2));
-        PG_TRY(gemm(p, s, PRO_LNRELU, N, p->nbuf + N2_PK_Q, N2_COLS, w(L + "pk.w2q_t"), 128, w(L + "pk.b2q"), p->qn1, 128, 1,
+        PG_TRY(gemm(p, s, PRO_PLAIN, N, p->h, 128, w, L + "n2.wt", N2_COLS, w(L + "n2.b"), p->nbuf, N2_COLS, N2_COLS / 128));
+        PG_TRY(gemm(p, s, PRO_PLAIN, Eb, p->hb, 128, w, L + "e2.wt", 256, w(L + "e2.b"), p->ebuf, 256, 2));
+        PG_TRY(gemm(p, s, PRO_LNRELU, N, p->nbuf + N2_PK_Q, N2_COLS, w, L + "pk.w2q_t", 128, w(L + "pk.b2q"), p->qn1, 128, 1,
                     nullptr, 0, nullptr, w(L + "pk.lnq_g"), w(L + "pk.lnq_b")));
-        PG_TRY(gemm(p, s, PRO_LNRELU, N, p->nbuf + N2_PB_Q, N2_COLS, w(L + "pb.w2q_t"), 128, w(L + "pb.b2q"), p->qn2, 128, 1,
+        PG_TRY(gemm(p, s, PRO_LNRELU, N, p->nbuf + N2_PB_Q, N2_COLS, w, L + "pb.w2q_t", 128, w(L + "pb.b2q"), p->qn2, 128, 1,
                     nullptr, 0, nullptr, w(L + "pb.lnq_g"), w(L + "pb.lnq_b")));
         {
             KnnAttnArgs a;
@@ -363,8 +371,8 @@ extern "C" int pg_phore_encode(const PgModel* m, PgPlan* p, const float* d_h_pho
     if (d.max_p > 256) { pg_set_error("phore encoder: more than 256 pharmacophore nodes per graph"); return PG_ELIMIT; }
     phore_embed_kernel<<<(unsigned)((d.P + 7) / 8), 256, 0, s>>>(d.P, d_h_phore, w("G.ph_emb_wt"), w("G.ph_emb_b"), p->pemb);
     PG_LAUNCH_CHECK(); p->launches++;
-    PG_TRY(gemm(p, s, PRO_PLAIN, d.P, p->pemb, 128, w("PE.wcat_t"), 640, w("PE.bcat"), p->pbuf, 640, 5));
-    PG_TRY(gemm(p, s, PRO_LNRELU, d.P, p->pbuf + 512, 640, w("PE.w2q_t"), 128, w("PE.b2q"), p->pq, 128, 1, nullptr, 0, nullptr,
+    PG_TRY(gemm(p, s, PRO_PLAIN, d.P, p->pemb, 128, w, "PE.wcat_t", 640, w("PE.bcat"), p->pbuf, 640, 5));
+    PG_TRY(gemm(p, s, PRO_LNRELU, d.P, p->pbuf + 512, 640, w, "PE.w2q_t", 128, w("PE.b2q"), p->pq, 128, 1, nullptr, 0, nullptr,
                 w("PE.lnq_g"), w("PE.lnq_b")));
     KnnAttnArgs a;
     a.d = d; a.x = d_pos_phore; a.comb = nullptr; a.knn_src = nullptr; a.ew = nullptr;
@@ -410,11 +418,11 @@ extern "C" int pg_phorediff_forward(const PgModel* m, PgPlan* p, const float* d_
     PG_LAUNCH_CHECK(); p->launches++;
     PG_TRY(run_denoiser(m, p, d_phore_norm, s));
     // output heads
-    PG_TRY(gemm(p, s, PRO_PLAIN, d.N, p->h, 128, w("G.vinf.w1t"), 128, w("G.vinf.b1"), p->qn1, 128, 1));
+    PG_TRY(gemm(p, s, PRO_PLAIN, d.N, p->h, 128, w, "G.vinf.w1t", 128, w("G.vinf.b1"), p->qn1, 128, 1));
     head_out_kernel<PG_NODE_CLASSES, 0><<<(unsigned)((d.Nl + 7) / 8), 256, 0, s>>>(d, p->qn1, w("G.vinf.w2"), w("G.vinf.b2"),
                                                                                    d_logits_node, p->x, d_pos_out);
     PG_LAUNCH_CHECK(); p->launches++;
-    PG_TRY(gemm(p, s, PRO_PLAIN, d.Eb, p->hb, 128, w("G.binf.w1t"), 128, w("G.binf.b1"), p->qt, 128, 1));
+    PG_TRY(gemm(p, s, PRO_PLAIN, d.Eb, p->hb, 128, w, "G.binf.w1t", 128, w("G.binf.b1"), p->qt, 128, 1));
     head_out_kernel<PG_EDGE_CLASSES, 1><<<(unsigned)((d.Eb + 7) / 8), 256, 0, s>>>(d, p->qt, w("G.binf.w2"), w("G.binf.b2"),
                                                                                    d_logits_edge, nullptr, nullptr);
     PG_LAUNCH_CHECK(); p->launches++;

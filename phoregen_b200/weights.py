@@ -122,21 +122,40 @@ def pack_state_dict(sd):
     return out
 
 
+def _bf16_bits(x32):
+    """Round-to-nearest-even fp32 -> bf16 bit patterns (uint16)."""
+    u = np.ascontiguousarray(x32, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    return ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
+
+
+def bf16_split(wt):
+    """k-major fp32 weight [128][N] -> fp32-typed carrier of [hi|lo][N][128] bf16 (K-major), hi + lo ~ w to 2^-17.
+    This is the B operand of the tcgen05 'bf16x3' contraction (csrc/pg_gemm_tc.cu)."""
+    w = np.ascontiguousarray(np.asarray(wt, dtype=np.float64).T, dtype=np.float32)      # [N][128]
+    hi = _bf16_bits(w)
+    hi_f = (hi.astype(np.uint32) << 16).view(np.float32)
+    lo = _bf16_bits(w - hi_f)
+    return np.concatenate([hi.reshape(-1), lo.reshape(-1)]).view(np.float32)
+
+
 def build_blob(sd):
     """-> (fp32 numpy blob, int64 offsets in floats) following the library's own slot table."""
     packed = pack_state_dict(sd)
+    for name in [k for k in packed if k.endswith((".wt", "w2q_t", "wcat_t", "w1t")) and k != "G.ew.w1t"]:
+        packed[name + ".bf"] = bf16_split(packed[name])
     table = _lib.slot_table()
     offsets = np.zeros(len(table), dtype=np.int64)
     chunks, cur = [], 0
     for i, (name, numel) in enumerate(table):
         if name not in packed:
             raise KeyError(f"weight packer does not produce slot {name!r}")
-        arr = np.ascontiguousarray(packed[name], dtype=np.float64).reshape(-1)
+        raw = packed[name]
+        arr = raw.reshape(-1) if raw.dtype == np.float32 else np.ascontiguousarray(raw, dtype=np.float64).reshape(-1).astype(np.float32)
         if arr.size != numel:
             raise ValueError(f"slot {name}: expected {numel} values, packed {arr.size}")
         pad = (-arr.size) % 4
         offsets[i] = cur
-        chunks.append(arr.astype(np.float32))
+        chunks.append(arr)
         if pad:
             chunks.append(np.zeros(pad, dtype=np.float32))
         cur += arr.size + pad
