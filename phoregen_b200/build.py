@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libphoregen_b200.so")
-SOURCES = ["pg_graph.cu", "pg_gemm.cu", "pg_gemm_tc.cu", "pg_attn.cu", "pg_model.cu", "pg_transition.cu"]
+SOURCES = ["pg_graph.cu", "pg_gemm.cu", "pg_gemm_tc.cu", "pg_attn.cu", "pg_trip_tc.cu", "pg_model.cu", "pg_transition.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xptxas=-v", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",

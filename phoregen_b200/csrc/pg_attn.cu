@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(TRIP_WARPS * 32) trip_kernel(TripArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = d.lig_graph[u];
     const int n = d.g_n[g], jl = u - d.lig_off[g];
-    if (n < 3) return;
+    if (n < 3 || n < a.min_atoms) return;
     const int ctx0 = d.ctx_off[g] + d.g_p[g];
     const int cj = ctx0 + jl;
     const long long eoff = d.eoff[g];

@@ -48,7 +48,27 @@ struct TripArgs {
     AttnW w;
     float* hb;               // [Eb,128] updated in place: hb += attention output
     int maxr, maxn;
+    int min_atoms;           // units of molecules with fewer atoms are skipped (they ran on the tcgen05 kernel)
 };
+
+// tcgen05 version of the triplet layer (csrc/pg_trip_tc.cu); handles molecules with n - 2 <= 32 rows per segment
+struct TripTcArgs {
+    PlanDev d;
+    const float* x;
+    const float* T; long long ldt; int t_k, t_v;
+    const float* H; long long ldh; int hk_k, hj_k, hk_v, hj_v;
+    const float* q;                        // [Eb,128]
+    float* R;                              // [Eb,256] work space: smear(d_e) @ Wrji
+    const float *wrkj, *wrji;              // [20][256] fp32
+    const uint16_t *w2k_bf, *w2v_bf;       // [hi|lo][128][128] bf16, K-major
+    const uint16_t* wa_bf;                 // [hi|lo][256][16] bf16 (angle slice, 13 used)
+    const float *lnk_g, *lnk_b, *lnv_g, *lnv_b, *b2k, *b2v;
+    float* hb;
+    int maxn;
+};
+constexpr int PG_TRIP_TC_MAX_ATOMS = 34;
+int pg_launch_trip_tc(const TripTcArgs& a, int num_sms, cudaStream_t s);
+size_t pg_trip_tc_smem(int maxn);
 
 int pg_launch_knn_attn(const KnnAttnArgs& a, int feat, int pos, cudaStream_t s);
 int pg_launch_bond_attn(const BondAttnArgs& a, int pos, cudaStream_t s);

@@ -1,6 +1,8 @@
 // Packed-weight slot table, embedding / head kernels and the forward orchestration
 // (call stack §3.2).
+#include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 #include "pg_attn.h"
 #include "pg_gemm.h"
@@ -49,7 +51,10 @@ std::vector<PgSlotDesc> build_slots() {
             const bool pos = s >= 3;
             add(S + "w2v", (pos ? 16 : 128) * 128); add(S + "b2v", pos ? 16 : 128);
             if (s == 0 || s == 3) { add(S + "tab_k", 4 * 24 * 128); add(S + "tab_v", 4 * 24 * 128); }
-            if (s == 2) { add(S + "wrkj", 20 * 256); add(S + "wrji", 20 * 256); add(S + "wa", 13 * 256); }
+            if (s == 2) {
+                add(S + "wrkj", 20 * 256); add(S + "wrji", 20 * 256); add(S + "wa", 13 * 256);
+                add(S + "w2k.bf", 128 * 128); add(S + "w2v.bf", 128 * 128); add(S + "wa.bf", 2 * 256 * 16 / 2);
+            }
         }
     }
     return v;
@@ -244,6 +249,18 @@ namespace {
 
 inline int round4(int v) { return (v + 3) & ~3; }
 
+int num_sms() {
+    static int v = 0;
+    if (!v) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); if (v <= 0) v = 148; }
+    return v;
+}
+// tcgen05 triplet kernel unless PG_TRIP=fp32; molecules above its segment-length limit take the fp32 kernel
+bool use_tc_trip(const PlanDev& d) {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PG_TRIP"); v = (e && !strcmp(e, "fp32")) ? 0 : 1; }
+    return v == 1 && d.max_n >= 3;
+}
+
 bool use_simt_gemm() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("PG_GEMM"); v = (e && !strcmp(e, "simt")) ? 1 : 0; }
@@ -329,7 +346,20 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
             a.H = p->nbuf; a.ldh = N1_COLS; a.hk_k = N1_TR_HK_K; a.hj_k = N1_TR_HJ_K; a.hk_v = N1_TR_HK_V; a.hj_v = N1_TR_HJ_V;
             a.q = p->qt; a.wrkj = w(L + "tr.wrkj"); a.wrji = w(L + "tr.wrji"); a.wa = w(L + "tr.wa");
             a.w = attn_w(w, L + "tr.", false); a.hb = p->hb; a.maxr = maxr_trip; a.maxn = d.max_n;
-            { PgTimed timed(p, KC_TRIP, s); PG_TRY(pg_launch_trip(a, s)); } p->launches++;
+            a.min_atoms = 0;
+            if (use_tc_trip(d)) {
+                TripTcArgs t;
+                t.d = d; t.x = p->x; t.T = a.T; t.ldt = a.ldt; t.t_k = a.t_k; t.t_v = a.t_v; t.H = a.H; t.ldh = a.ldh;
+                t.hk_k = a.hk_k; t.hj_k = a.hj_k; t.hk_v = a.hk_v; t.hj_v = a.hj_v; t.q = p->qt; t.R = p->rbuf;
+                t.wrkj = a.wrkj; t.wrji = a.wrji;
+                t.w2k_bf = (const uint16_t*)w(L + "tr.w2k.bf"); t.w2v_bf = (const uint16_t*)w(L + "tr.w2v.bf");
+                t.wa_bf = (const uint16_t*)w(L + "tr.wa.bf");
+                t.lnk_g = a.w.lnk_g; t.lnk_b = a.w.lnk_b; t.lnv_g = a.w.lnv_g; t.lnv_b = a.w.lnv_b; t.b2k = a.w.b2k; t.b2v = a.w.b2v;
+                t.hb = p->hb; t.maxn = std::min(d.max_n, PG_TRIP_TC_MAX_ATOMS);
+                { PgTimed timed(p, KC_TRIP, s); PG_TRY(pg_launch_trip_tc(t, num_sms(), s)); } p->launches += 2;
+                a.min_atoms = PG_TRIP_TC_MAX_ATOMS + 1;
+            }
+            if (a.min_atoms == 0 || d.max_n >= a.min_atoms) { PgTimed timed(p, KC_TRIP, s); PG_TRY(pg_launch_trip(a, s)); p->launches++; }
         }
         // h <- h + lin_node(o1 + o2)
         PG_TRY(gemm(p, s, PRO_SUM2, N, p->o1, 128, w, L + "lin.wt", 128, w(L + "lin.b"), p->h, 128, 1, p->o2, 128, nullptr,

@@ -17,6 +17,7 @@ struct PgPlan {
     float *dx1, *dx2;             // [N,3]
     float* ebuf;                  // [Eb,640] edge GEMM outputs
     float* qt;                    // [Eb,128] per-edge triplet queries / head hidden
+    float* rbuf;                  // [Eb,256] r_ji slice of the triplet MLPs (tcgen05 triplet kernel)
     float *ew, *comb;             // [Ek], [N,3]
     int* knn_src;                 // [Ek]
     float *pbuf, *pq, *pemb;      // phore encoder: [P,640], [P,128], [P,128]

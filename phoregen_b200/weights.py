@@ -143,6 +143,12 @@ def build_blob(sd):
     packed = pack_state_dict(sd)
     for name in [k for k in packed if k.endswith((".wt", "w2q_t", "wcat_t", "w1t")) and k != "G.ew.w1t"]:
         packed[name + ".bf"] = bf16_split(packed[name])
+    for name in [k for k in packed if k.endswith(".tr.w2k") or k.endswith(".tr.w2v")]:
+        packed[name + ".bf"] = bf16_split(np.asarray(packed[name]).T)          # already [out][in] = [N][K]
+    for name in [k for k in packed if k.endswith(".tr.wa")]:
+        wa = np.zeros((16, 256))
+        wa[:13] = packed[name]                                                  # [13][256] -> pad K to 16
+        packed[name + ".bf"] = bf16_split(wa)                                   # -> [hi|lo][256][16]
     table = _lib.slot_table()
     offsets = np.zeros(len(table), dtype=np.int64)
     chunks, cur = [], 0
