@@ -59,6 +59,7 @@ struct TripTcArgs {
     const float* H; long long ldh; int hk_k, hj_k, hk_v, hj_v;
     const float* q;                        // [Eb,128]
     float* R;                              // [Eb,256] work space: smear(d_e) @ Wrji
+    float* P;                              // [Eb,256] work space: per-edge partial of the first Linear (k->j role)
     const float *wrkj, *wrji;              // [20][256] fp32
     const uint16_t *w2k_bf, *w2v_bf;       // [hi|lo][128][128] bf16, K-major
     const uint16_t* wa_bf;                 // [hi|lo][256][16] bf16 (angle slice, 13 used)

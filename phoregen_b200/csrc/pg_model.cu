@@ -350,7 +350,7 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
             if (use_tc_trip(d)) {
                 TripTcArgs t;
                 t.d = d; t.x = p->x; t.T = a.T; t.ldt = a.ldt; t.t_k = a.t_k; t.t_v = a.t_v; t.H = a.H; t.ldh = a.ldh;
-                t.hk_k = a.hk_k; t.hj_k = a.hj_k; t.hk_v = a.hk_v; t.hj_v = a.hj_v; t.q = p->qt; t.R = p->rbuf;
+                t.hk_k = a.hk_k; t.hj_k = a.hj_k; t.hk_v = a.hk_v; t.hj_v = a.hj_v; t.q = p->qt; t.R = p->rbuf; t.P = p->pbuf2;
                 t.wrkj = a.wrkj; t.wrji = a.wrji;
                 t.w2k_bf = (const uint16_t*)w(L + "tr.w2k.bf"); t.w2v_bf = (const uint16_t*)w(L + "tr.w2v.bf");
                 t.wa_bf = (const uint16_t*)w(L + "tr.wa.bf");

@@ -18,6 +18,7 @@ struct PgPlan {
     float* ebuf;                  // [Eb,640] edge GEMM outputs
     float* qt;                    // [Eb,128] per-edge triplet queries / head hidden
     float* rbuf;                  // [Eb,256] r_ji slice of the triplet MLPs (tcgen05 triplet kernel)
+    float* pbuf2;                 // [Eb,256] per-edge first-Linear partials P[k->j] (tcgen05 triplet kernel)
     float *ew, *comb;             // [Ek], [N,3]
     int* knn_src;                 // [Ek]
     float *pbuf, *pq, *pemb;      // phore encoder: [P,640], [P,128], [P,128]

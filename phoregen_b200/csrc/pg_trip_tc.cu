@@ -22,42 +22,135 @@
 #include "pg_attn.h"
 #include "pg_tc.cuh"
 
+// Optional phase tracing (debug builds only): cycle stamps of CTA 0 into a.trace[role][tile][slot]
+#ifdef PG_TRIP_TRACE
+__device__ long long g_trip_trace[3 * 64 * 16];
+extern "C" int pg_debug_trip_trace(long long* h_out) { return cudaMemcpyFromSymbol(h_out, g_trip_trace, sizeof(g_trip_trace)) == cudaSuccess ? 0 : -2; }
+#define TRACE(role, slot) do { if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == 8) && tcount < 64) g_trip_trace[((role) * 64 + tcount) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define TRACE(role, slot) do {} while (0)
+#endif
+
 namespace {
 constexpr int PS_LD = 260;                 // padded row stride of the staged P rows (conflict-free LDS.128 across rows)
 constexpr int W_TILE = 32768;              // one [128 x 128] bf16 matrix in two 128B-swizzled K blocks
 constexpr int SM_W = 4 * W_TILE;           // (k,v) x (hi,lo)
 constexpr int SM_WA = 2 * 8192;            // angle slice of the first Linear: (hi,lo) x [256 x 16] bf16, no swizzle
 constexpr int SM_FEAT = 2 * 4096;          // (hi,lo) x [128 x 16] bf16, no swizzle
-constexpr int SM_FIXED = SM_W + SM_WA + SM_FEAT + 4 * 128 * 4 /*q*/ + 6 * 128 * 4 /*ln + b2*/ + 64 /*barriers*/;
+constexpr int SM_QR = 2 * (4 * 128 + 4 * 256) * 4;   // double-buffered query rows + r_ji rows of a tile's 4 segments
+constexpr int SM_ALPHA = 128 * 16 * 4;     // attention weights of the tile [row][head]
+constexpr int SM_FIXED = SM_W + SM_WA + SM_FEAT + SM_QR + SM_ALPHA + 6 * 128 * 4 /*ln + b2*/ + 128 /*barriers*/;
 constexpr float kInvSqrtD = 0.35355339059327373f;
+constexpr int NTHREADS = 384;              // warpgroups: 0 = key rows, 1 = value rows, 2 = MMA issue + q/R loader (warp 8; 9-11 idle)
 
-__global__ void __launch_bounds__(256, 1) trip_tc_kernel(TripTcArgs a) {
+// mbarrier slots
+enum { B_FEAT = 0, B_PRE, B_HIDK, B_HIDV, B_OUTK, B_OUTV, B_PS, B_FREE, B_COUNT };
+
+// the sequence of (unit, tile) a CTA walks; every role steps through it redundantly
+struct TileIter {
+    int u, tile, ntile, n, jl, ctx0;
+    long long eoff;
+    bool valid;
+};
+__device__ __forceinline__ void iter_load_unit(const PlanDev& d, TileIter& it) {
+    it.valid = false;
+    while (it.u < d.Nl) {
+        const int g = d.lig_graph[it.u];
+        const int n = d.g_n[g];
+        if (n >= 3 && n - 2 <= 32) {        // larger molecules take the fp32 kernel
+            it.n = n; it.jl = it.u - d.lig_off[g]; it.ctx0 = d.ctx_off[g] + d.g_p[g]; it.eoff = d.eoff[g];
+            it.ntile = (n - 1 + 3) >> 2; it.tile = 0; it.valid = true;
+            return;
+        }
+        it.u += gridDim.x;
+    }
+}
+__device__ __forceinline__ void iter_next(const PlanDev& d, TileIter& it) {
+    if (++it.tile < it.ntile) return;
+    it.u += gridDim.x;
+    iter_load_unit(d, it);
+}
+// segment handled by lane quadrant wq in this tile
+struct Seg { bool valid; int il, ti; long long eji; };
+__device__ __forceinline__ Seg seg_of(const TileIter& it, int wq) {
+    Seg s;
+    const int sidx = it.tile * 4 + wq;
+    s.valid = sidx < it.n - 1;
+    s.il = s.valid ? sidx + (sidx >= it.jl) : (it.jl == 0 ? 1 : 0);
+    s.ti = s.il - (s.il > it.jl);
+    s.eji = it.eoff + (long long)s.il * (it.n - 1) + (it.jl - (it.jl > s.il));
+    return s;
+}
+
+// angular encoding of this thread's triplet row -> bf16 hi/lo A tile (common.py:67-87; uni_denoiser.py:131-135)
+// xs: coordinates of the molecule's ligand atoms, [n][4] floats (shared memory copy)
+__device__ __forceinline__ void write_features(const float* xs, const TileIter& it, int wq, int lane, uint8_t* sFeat) {
+    const Seg sg = seg_of(it, wq);
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) f[i] = 0.f;
+    if (sg.valid && lane < it.n - 2) {
+        const int trow = lane + (lane >= sg.ti);
+        const float4 xj = ld4(xs + it.jl * 4), xi = ld4(xs + sg.il * 4), xk = ld4(xs + (trow + (trow >= it.jl)) * 4);
+        const float xi0 = xi.x, xi1 = xi.y, xi2 = xi.z;
+        const float pj0 = xj.x - xi0, pj1 = xj.y - xi1, pj2 = xj.z - xi2;
+        const float pk0 = xk.x - xi0, pk1 = xk.y - xi1, pk2 = xk.z - xi2;
+        const float dotv = pj0 * pk0 + pj1 * pk1 + pj2 * pk2;
+        const float c0 = pj1 * pk2 - pj2 * pk1, c1 = pj2 * pk0 - pj0 * pk2, c2 = pj0 * pk1 - pj1 * pk0;
+        const float th = atan2f(sqrtf(c0 * c0 + c1 * c1 + c2 * c2), dotv);
+        // th in [0, pi]: fast sincos is accurate to ~5e-7 there; double / triple angle by identities
+        float s1, k1, sh, kh, st, kt;
+        __sincosf(th, &s1, &k1); __sincosf(th * 0.5f, &sh, &kh); __sincosf(th * (1.0f / 3.0f), &st, &kt);
+        const float s2 = 2.0f * s1 * k1, k2 = fmaf(-2.0f * s1, s1, 1.0f);
+        const float s3 = s1 * fmaf(-4.0f * s1, s1, 3.0f), k3 = k1 * fmaf(4.0f * k1, k1, -3.0f);
+        f[0] = th; f[1] = s1; f[2] = s2; f[3] = s3; f[4] = s1; f[5] = sh; f[6] = st;
+        f[7] = k1; f[8] = k2; f[9] = k3; f[10] = k1; f[11] = kh; f[12] = kt;
+    }
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) tc::split_pair_trunc(f[2 * i], f[2 * i + 1], hi[i], lo[i]);
+    const int r = wq * 32 + lane;
+    uint8_t* ph = sFeat + (r >> 3) * 256 + (r & 7) * 16;
+    *reinterpret_cast<uint4*>(ph) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(ph + 128) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    *reinterpret_cast<uint4*>(ph + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(ph + 4096 + 128) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sW = smem;
     uint8_t* sWa = sW + SM_W;
     uint8_t* sFeat = sWa + SM_WA;
-    float* sQ = (float*)(sFeat + SM_FEAT);          // [4][128]
-    float* sLn = sQ + 4 * 128;                      // gk, bk, gv, bv
+    float* sQR = (float*)(sFeat + SM_FEAT);         // [2][ q: 4x128 | R: 4x256 ]
+    float* sStat = sQR + SM_QR / 4;                 // [2 mlp][128 rows][2 halves][2]  partial LayerNorm sums
+    float* sLn = sStat + SM_ALPHA / 4;              // gk, bk, gv, bv
     float* sB2 = sLn + 4 * 128;                     // b2k, b2v
-    uint64_t* bars = (uint64_t*)(sB2 + 2 * 128);    // 3 mbarriers
-    uint32_t* tmem_slot = (uint32_t*)(bars + 4);
+    uint64_t* bars = (uint64_t*)(sB2 + 2 * 128);
+    uint32_t* tmem_slot = (uint32_t*)(bars + B_COUNT);
     float* sPs = (float*)(smem + SM_FIXED);         // [(maxn-1)][260]
-    float* sSmr = sPs + (size_t)(a.maxn - 1) * PS_LD;   // [(maxn-1)][20]
+    float* sX = sPs + (size_t)(a.maxn - 1) * PS_LD; // [2][maxn][4] ligand coordinates of the current / next unit
     const PlanDev& d = a.d;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wq = warp & 3, half = warp >> 2;
+    const int wq = warp & 3;
 
-    if (warp == 0) tc::tmem_alloc<512>(tmem_slot);
-    if (tid == 32) { tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1); tc::mbar_init(&bars[2], 1); tc::fence_barrier_init(); }
+    if (warp == 8) tc::tmem_alloc<512>(tmem_slot);
+    if (tid == 0) {
+        tc::mbar_init(&bars[B_FEAT], 128 + 32); tc::mbar_init(&bars[B_PRE], 1);
+        tc::mbar_init(&bars[B_HIDK], 256); tc::mbar_init(&bars[B_HIDV], 256);
+        tc::mbar_init(&bars[B_OUTK], 1); tc::mbar_init(&bars[B_OUTV], 1);
+        tc::mbar_init(&bars[B_PS], 1); tc::mbar_init(&bars[B_FREE], 256);
+        tc::fence_barrier_init();
+    }
     // ---- resident weights
-    for (int idx = tid; idx < 4 * 128 * 16; idx += 256) {     // 16-byte chunks: [mat 4][n 128][chunk 16]
+    for (int idx = tid; idx < 4 * 128 * 16; idx += NTHREADS) {     // 16-byte chunks: [mat 4][n 128][chunk 16]
         const int mat = idx >> 11, n = (idx >> 4) & 127, c = idx & 15;
         const uint16_t* src = ((mat >> 1) ? a.w2v_bf : a.w2k_bf) + ((size_t)(mat & 1) * 128 + n) * 128 + c * 8;
         const uint32_t dst = tc::smem_u32(sW) + mat * W_TILE + (c >> 3) * 16384 + tc::sw128_chunk(n, c & 7);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
     }
-    for (int idx = tid; idx < 2 * 256 * 2; idx += 256) {      // [part 2][n 256][kc 2]
+    for (int idx = tid; idx < 2 * 256 * 2; idx += NTHREADS) {      // [part 2][n 256][kc 2]
         const int part = idx >> 9, n = (idx >> 1) & 255, kc = idx & 1;
         const uint16_t* src = a.wa_bf + ((size_t)part * 256 + n) * 16 + kc * 8;
         const uint32_t dst = tc::smem_u32(sWa) + part * 8192 + (n >> 3) * 256 + kc * 128 + (n & 7) * 16;
@@ -74,166 +167,85 @@ __global__ void __launch_bounds__(256, 1) trip_tc_kernel(TripTcArgs a) {
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-    constexpr uint32_t idesc_feat = tc::umma_idesc_bf16(128, 256);
-    constexpr uint32_t idesc_w2 = tc::umma_idesc_bf16(128, 128);
-    const uint32_t sW_u32 = tc::smem_u32(sW), sWa_u32 = tc::smem_u32(sWa), sFeat_u32 = tc::smem_u32(sFeat);
-    uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
+    // TMEM columns: pre_k [0,128) pre_v [128,256) (later out_k / out_v) ; hid_k [256,384) ; hid_v [384,512)
+    constexpr uint32_t C_PRE = 0, C_OUT = 0, C_HIDK = 256, C_HIDV = 384;
 
-    for (int u = blockIdx.x; u < d.Nl; u += gridDim.x) {
-        const int g = d.lig_graph[u];
-        const int n = d.g_n[g], jl = u - d.lig_off[g];
-        if (n < 3 || n - 2 > 32) continue;                  // larger molecules take the fp32 kernel
-        const int ctx0 = d.ctx_off[g] + d.g_p[g];
-        const int cj = ctx0 + jl;
-        const long long eoff = d.eoff[g];
-        const float xj0 = a.x[(size_t)cj * 3], xj1 = a.x[(size_t)cj * 3 + 1], xj2 = a.x[(size_t)cj * 3 + 2];
-        // ---- stage P rows of the edges k -> j
-        for (int t = tid; t < n - 1; t += 256) {
-            const int ck = ctx0 + t + (t >= jl);
-            const float d0 = xj0 - a.x[(size_t)ck * 3], d1 = xj1 - a.x[(size_t)ck * 3 + 1], d2 = xj2 - a.x[(size_t)ck * 3 + 2];
-            const float dist = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
-#pragma unroll
-            for (int gg = 0; gg < 20; gg++) sSmr[t * 20 + gg] = smear_val(dist, gg);
-        }
+    TileIter it;
+    it.u = blockIdx.x;
+    iter_load_unit(d, it);
+    if (!it.valid) {
         __syncthreads();
-        {
-            const int c = tid, cc = c & 127;
-            const bool isv = c >= 128;
-            const float hjb = __ldg(a.H + (size_t)cj * a.ldh + (isv ? a.hj_v : a.hj_k) + cc);
-            float wr[20];
-#pragma unroll
-            for (int gg = 0; gg < 20; gg++) wr[gg] = __ldg(a.wrkj + gg * 256 + c);
-            const int tcol = (isv ? a.t_v : a.t_k) + cc, hcol = (isv ? a.hk_v : a.hk_k) + cc;
-            for (int t = 0; t < n - 1; t++) {
-                const int ck = ctx0 + t + (t >= jl);
-                const long long e = eoff + (long long)jl * (n - 1) + t;
-                float val = __ldg(a.T + (size_t)e * a.ldt + tcol) + __ldg(a.H + (size_t)ck * a.ldh + hcol) + hjb;
-#pragma unroll
-                for (int gg = 0; gg < 20; gg++) val = fmaf(sSmr[t * 20 + gg], wr[gg], val);
-                sPs[t * PS_LD + c] = val;
-            }
-        }
-        __syncthreads();
+        if (warp == 8) tc::tmem_dealloc<512>(tmem);
+        return;
+    }
 
-        const int R = n - 2;
-        const int ntile = (n - 1 + 3) >> 2;
-        for (int tile = 0; tile < ntile; tile++) {
-            const int sidx = tile * 4 + wq;
-            const bool segvalid = sidx < n - 1;
-            const int il = segvalid ? sidx + (sidx >= jl) : (jl == 0 ? 1 : 0);
-            const int ti = il - (il > jl);
-            const bool rowvalid = segvalid && lane < R;
-            const int trow = rowvalid ? lane + (lane >= ti) : 0;
-            const long long eji = eoff + (long long)il * (n - 1) + (jl - (jl > il));
-            // ---- phase 0: angular features (warps 0-3), query rows (warps 4-7)
-            if (half == 0) {
-                float f[16];
+    if (warp >= 8) {
+        // registers move from this (nearly idle) warpgroup to the two row warpgroups
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+      if (warp == 8) {
+        // ================= MMA issue + loaders (query / r_ji rows via cp.async, P rows via bulk copy) =================
+        constexpr uint32_t idesc_feat = tc::umma_idesc_bf16(128, 256);
+        constexpr uint32_t idesc_w2 = tc::umma_idesc_bf16(128, 128);
+        const uint32_t sW_u32 = tc::smem_u32(sW), sWa_u32 = tc::smem_u32(sWa), sFeat_u32 = tc::smem_u32(sFeat);
+        auto load_qr = [&](const TileIter& t, int buf) {
+            const uint32_t q = tc::smem_u32(sQR + buf * (SM_QR / 8));
+            const uint32_t r = q + 4 * 128 * 4;
 #pragma unroll
-                for (int i = 0; i < 16; i++) f[i] = 0.f;
-                if (rowvalid) {
-                    const int ci = ctx0 + il, ck = ctx0 + trow + (trow >= jl);
-                    const float xi0 = a.x[(size_t)ci * 3], xi1 = a.x[(size_t)ci * 3 + 1], xi2 = a.x[(size_t)ci * 3 + 2];
-                    const float pj0 = xj0 - xi0, pj1 = xj1 - xi1, pj2 = xj2 - xi2;
-                    const float pk0 = a.x[(size_t)ck * 3] - xi0, pk1 = a.x[(size_t)ck * 3 + 1] - xi1, pk2 = a.x[(size_t)ck * 3 + 2] - xi2;
-                    const float dotv = pj0 * pk0 + pj1 * pk1 + pj2 * pk2;
-                    const float c0 = pj1 * pk2 - pj2 * pk1, c1 = pj2 * pk0 - pj0 * pk2, c2 = pj0 * pk1 - pj1 * pk0;
-                    const float th = atan2f(sqrtf(c0 * c0 + c1 * c1 + c2 * c2), dotv);
-                    float s1, k1, s2, k2, s3, k3, sh, kh, st, kt;
-                    sincosf(th, &s1, &k1); sincosf(th * 2.0f, &s2, &k2); sincosf(th * 3.0f, &s3, &k3);
-                    sincosf(th * 0.5f, &sh, &kh); sincosf(th * (1.0f / 3.0f), &st, &kt);
-                    f[0] = th; f[1] = s1; f[2] = s2; f[3] = s3; f[4] = s1; f[5] = sh; f[6] = st;
-                    f[7] = k1; f[8] = k2; f[9] = k3; f[10] = k1; f[11] = kh; f[12] = kt;
-                }
-                uint32_t hi[8], lo[8];
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    __nv_bfloat16 h0, l0, h1, l1;
-                    tc::split_bf16(f[2 * i], h0, l0); tc::split_bf16(f[2 * i + 1], h1, l1);
-                    hi[i] = tc::pack_bf16(h0, h1); lo[i] = tc::pack_bf16(l0, l1);
-                }
-                const int r = wq * 32 + lane;
-                uint8_t* ph = sFeat + (r >> 3) * 256 + (r & 7) * 16;
-                *reinterpret_cast<uint4*>(ph) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(ph + 128) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                *reinterpret_cast<uint4*>(ph + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                *reinterpret_cast<uint4*>(ph + 4096 + 128) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-            } else {
-                st4(sQ + wq * 128 + lane * 4, segvalid ? ldg4(a.q + (size_t)eji * 128 + lane * 4) : make_float4(0, 0, 0, 0));
+            for (int s4 = 0; s4 < 4; s4++) {
+                const Seg sg = seg_of(t, s4);
+                const float* qs = a.q + (size_t)sg.eji * 128 + lane * 4;
+                const float* rs = a.R + (size_t)sg.eji * 256 + lane * 4;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(q + (s4 * 128 + lane * 4) * 4), "l"(qs) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(r + (s4 * 256 + lane * 4) * 4), "l"(rs) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(r + (s4 * 256 + 128 + lane * 4) * 4), "l"(rs + 128) : "memory");
             }
-            tc::fence_proxy_async_smem();
-            __syncthreads();
-            if (tid == 0) {
-                tc::tc_fence_after();
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        // P rows of the edges k -> j of a unit: n-1 contiguous 1 KB rows -> padded smem rows, one mbarrier transaction
+        auto load_ps = [&](const TileIter& t) {
+            if (lane == 0) tc::mbar_arrive_expect_tx(&bars[B_PS], (uint32_t)(t.n - 1) * 1024u);
+            __syncwarp();
+            const float* src = a.P + (size_t)(t.eoff + (long long)t.jl * (t.n - 1)) * 256;
+            for (int r = lane; r < t.n - 1; r += 32) tc::bulk_copy_g2s(sPs + (size_t)r * PS_LD, src + (size_t)r * 256, 1024u, &bars[B_PS]);
+        };
+        load_ps(it);
+        load_qr(it, 0);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        tc::mbar_arrive(&bars[B_FEAT]);
+        uint32_t ph = 0;
+        int buf = 0;
+        int tcount = 0;
+        while (it.valid) {
+            TRACE(2, 0);
+            tc::mbar_wait(&bars[B_FEAT], ph);          // features + q/R rows of this tile are in smem
+            TRACE(2, 1);
+            tc::mbar_wait(&bars[B_FREE], ph);          // previous tile's accumulators have been read
+            TRACE(2, 2);
+            tc::tc_fence_after();
+            if (lane == 0) {
                 const uint64_t fh = tc::umma_desc_k16_noswizzle(sFeat_u32), fl = tc::umma_desc_k16_noswizzle(sFeat_u32 + 4096);
                 const uint64_t wh = tc::umma_desc_k16_noswizzle(sWa_u32), wl = tc::umma_desc_k16_noswizzle(sWa_u32 + 8192);
-                tc::umma_bf16(tmem, fh, wh, idesc_feat, 0);
-                tc::umma_bf16(tmem, fh, wl, idesc_feat, 1);
-                tc::umma_bf16(tmem, fl, wh, idesc_feat, 1);
-                tc::umma_commit(&bars[0]);
+                tc::umma_bf16(tmem + C_PRE, fh, wh, idesc_feat, 0);
+                tc::umma_bf16(tmem + C_PRE, fh, wl, idesc_feat, 1);
+                tc::umma_bf16(tmem + C_PRE, fl, wh, idesc_feat, 1);
+                tc::umma_commit(&bars[B_PRE]);
             }
-            tc::mbar_wait(&bars[0], ph0); ph0 ^= 1;
-            tc::tc_fence_after();
-            // ---- phase 1: pre-activation row -> LayerNorm + ReLU -> bf16 hi/lo A operand in TMEM
-            {
-                const int mlp = half;                       // warps 0-3: key MLP, warps 4-7: value MLP
-                float xr[128];
+            __syncwarp();
+            TRACE(2, 3);
+            TileIter nx = it;
+            iter_next(d, nx);
+            if (nx.valid) load_qr(nx, buf ^ 1);
+            TRACE(2, 4);
 #pragma unroll
-                for (int c4 = 0; c4 < 4; c4++) {
-                    float v[32];
-                    tc::tmem_ld32(tmem + lane_base + mlp * 128 + c4 * 32, v);
-#pragma unroll
-                    for (int q8 = 0; q8 < 8; q8++) {
-                        const int c = c4 * 32 + q8 * 4;
-                        const float4 p = ld4(sPs + trow * PS_LD + mlp * 128 + c);
-                        const float4 rr = ldg4(a.R + (size_t)eji * 256 + mlp * 128 + c);
-                        xr[c] = v[q8 * 4] + p.x + rr.x; xr[c + 1] = v[q8 * 4 + 1] + p.y + rr.y;
-                        xr[c + 2] = v[q8 * 4 + 2] + p.z + rr.z; xr[c + 3] = v[q8 * 4 + 3] + p.w + rr.w;
-                    }
-                }
-                float s1 = 0.f;
-#pragma unroll
-                for (int c = 0; c < 128; c++) s1 += xr[c];
-                const float mu = s1 * (1.0f / 128.0f);
-                float s2 = 0.f;
-#pragma unroll
-                for (int c = 0; c < 128; c++) { const float dd = xr[c] - mu; s2 = fmaf(dd, dd, s2); }
-                const float rstd = rsqrtf(s2 * (1.0f / 128.0f) + 1e-5f);
-                const float nmr = -mu * rstd;
-                tc::tc_fence_before();
-                __syncthreads();                             // every pre_* column has been read: safe to overwrite pre_k with hid_v
+            for (int mlp = 0; mlp < 2; mlp++) {
+                tc::mbar_wait(&bars[mlp == 0 ? B_HIDK : B_HIDV], ph);
+                TRACE(2, 5 + mlp * 2);
                 tc::tc_fence_after();
-                const float* gam = sLn + mlp * 256;
-                const float* bet = gam + 128;
-                const uint32_t hid = tmem + lane_base + (mlp == 0 ? 384 : 0);
-#pragma unroll
-                for (int q4 = 0; q4 < 4; q4++) {             // channels [32*q4, 32*q4+32)
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int c = q4 * 32 + 4 * i;
-                        const float4 g4 = ld4(gam + c), b4 = ld4(bet + c);
-                        const float y0 = fmaxf(fmaf(fmaf(xr[c], rstd, nmr), g4.x, b4.x), 0.f);
-                        const float y1 = fmaxf(fmaf(fmaf(xr[c + 1], rstd, nmr), g4.y, b4.y), 0.f);
-                        const float y2 = fmaxf(fmaf(fmaf(xr[c + 2], rstd, nmr), g4.z, b4.z), 0.f);
-                        const float y3 = fmaxf(fmaf(fmaf(xr[c + 3], rstd, nmr), g4.w, b4.w), 0.f);
-                        __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
-                        tc::split_bf16(y0, h0, l0); tc::split_bf16(y1, h1, l1); tc::split_bf16(y2, h2, l2); tc::split_bf16(y3, h3, l3);
-                        hi[2 * i] = tc::pack_bf16(h0, h1); hi[2 * i + 1] = tc::pack_bf16(h2, h3);
-                        lo[2 * i] = tc::pack_bf16(l0, l1); lo[2 * i + 1] = tc::pack_bf16(l2, l3);
-                    }
-                    tc::tmem_st16(hid + q4 * 16, hi);
-                    tc::tmem_st16(hid + 64 + q4 * 16, lo);
-                }
-                tc::tmem_st_wait();
-            }
-            tc::tc_fence_before();
-            __syncthreads();
-            if (tid == 0) {
-                tc::tc_fence_after();
-#pragma unroll
-                for (int mlp = 0; mlp < 2; mlp++) {
-                    const uint32_t hid = tmem + (mlp == 0 ? 384 : 0);
-                    const uint32_t dcol = tmem + (mlp == 0 ? 256 : 128);
+                // both LayerNorm passes of this tile are done: the P rows of the next unit may overwrite the current ones
+                if (mlp == 1 && nx.valid && nx.u != it.u) load_ps(nx);
+                if (lane == 0) {
+                    const uint32_t hid = tmem + (mlp == 0 ? C_HIDK : C_HIDV);
+                    const uint32_t dcol = tmem + C_OUT + mlp * 128;
                     uint32_t acc = 0;
 #pragma unroll
                     for (int combo = 0; combo < 3; combo++) {       // hi*hi, hi*lo, lo*hi
@@ -246,85 +258,223 @@ __global__ void __launch_bounds__(256, 1) trip_tc_kernel(TripTcArgs a) {
                             acc = 1;
                         }
                     }
-                    tc::umma_commit(&bars[1 + mlp]);
+                    tc::umma_commit(&bars[mlp == 0 ? B_OUTK : B_OUTV]);
                 }
+                __syncwarp();
+                TRACE(2, 6 + mlp * 2);
             }
-            // ---- phase 2: logits, segment softmax (rows = lanes), alpha-weighted sum of values
-            float alpha[8];
-            {
-                tc::mbar_wait(&bars[1], ph1); ph1 ^= 1;
-                tc::tc_fence_after();
-                float kk[64];
+            if (nx.valid) { asm volatile("cp.async.wait_group 0;" ::: "memory"); tc::mbar_arrive(&bars[B_FEAT]); }
+            it = nx; ph ^= 1; buf ^= 1; tcount++;
+        }
+      }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        // ================= row warps: thread = (row, channel half) =================
+        // warp w: rows 32*(w&3)..+31, channels [64*(w>>2), +64) of the key MLP, then of the value MLP; heads 8*(w>>2)..+7
+        const int half = warp >> 2;
+        int xb = 0;                                     // coordinate buffer of the current unit
+        auto stage_x = [&](const TileIter& t, int b) {  // warps 4-7 only (128 threads)
+            for (int i = tid - 128; i < t.n; i += 128) {
+                const float* src = a.x + (size_t)(t.ctx0 + i) * 3;
+                st4(sX + ((size_t)b * a.maxn + i) * 4, make_float4(src[0], src[1], src[2], 0.f));
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+        };
+        if (half == 1) {
+            stage_x(it, 0);
+            write_features(sX, it, wq, lane, sFeat);
+            tc::fence_proxy_async_smem();
+            tc::mbar_arrive(&bars[B_FEAT]);
+        }
+        tc::mbar_arrive(&bars[B_FREE]);                 // TMEM starts free
+        uint32_t ph = 0, psph = 0;
+        int buf = 0, staged_u = -1;
+        int tcount = 0;
+        const int role = half;
+        while (it.valid) {
+            TRACE(role, 0);
+            if (staged_u != it.u) {                     // P rows of this unit have landed (bulk copy issued by warp 8)
+                if (staged_u >= 0) xb ^= 1;
+                tc::mbar_wait(&bars[B_PS], psph);
+                psph ^= 1;
+                staged_u = it.u;
+            }
+            const Seg sg = seg_of(it, wq);
+            const bool rowvalid = sg.valid && lane < it.n - 2;
+            const int trow = rowvalid ? lane + (lane >= sg.ti) : 0;
+            const float* sQ = sQR + buf * (SM_QR / 8);
+            const float* sR = sQ + 4 * 128;
+            TRACE(role, 1);
+            tc::mbar_wait(&bars[B_PRE], ph);
+            TRACE(role, 2);
+            tc::tc_fence_after();
+            // ---- key MLP then value MLP: pre-activation half row -> LayerNorm + ReLU -> bf16 hi/lo A operand in TMEM
+#pragma unroll
+            for (int mlp = 0; mlp < 2; mlp++) {
+                const int c0 = mlp * 128 + half * 64;    // first of this thread's 64 channels inside the 256-wide (k|v) row
+                float2 x2[32];
                 {
-                    float v[32];
-                    tc::tmem_ld32(tmem + lane_base + 256 + half * 64, v);
+                    uint32_t xu[64];
+                    tc::tmem_ld32_nowait(tmem + lane_base + C_PRE + c0, xu);
+                    tc::tmem_ld32_nowait(tmem + lane_base + C_PRE + c0 + 32, xu + 32);
+                    tc::tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; i++) kk[i] = v[i];
-                    tc::tmem_ld32(tmem + lane_base + 256 + half * 64 + 32, v);
-#pragma unroll
-                    for (int i = 0; i < 32; i++) kk[32 + i] = v[i];
+                    for (int i = 0; i < 32; i++) x2[i] = make_float2(__uint_as_float(xu[2 * i]), __uint_as_float(xu[2 * i + 1]));
                 }
+                float2 s1 = make_float2(0.f, 0.f), s2 = s1, s1b = s1, s2b = s1;
+                const float* prow = sPs + trow * PS_LD + c0;
+                const float* rrow = sR + wq * 256 + c0;
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float4 p = ld4(prow + 2 * i), rr = ld4(rrow + 2 * i);
+                    x2[i] = tc::add2(x2[i], tc::add2(make_float2(p.x, p.y), make_float2(rr.x, rr.y)));
+                    x2[i + 1] = tc::add2(x2[i + 1], tc::add2(make_float2(p.z, p.w), make_float2(rr.z, rr.w)));
+                    s1 = tc::add2(s1, x2[i]); s1b = tc::add2(s1b, x2[i + 1]);
+                    s2 = tc::fma2(x2[i], x2[i], s2); s2b = tc::fma2(x2[i + 1], x2[i + 1], s2b);
+                }
+                s1 = tc::add2(s1, s1b); s2 = tc::add2(s2, s2b);
+                // combine with the other channel half of the same row (warp w +- 4, same lane)
+                float* st = sStat + ((mlp * 128 + wq * 32 + lane) * 2) * 2;
+                *reinterpret_cast<float2*>(st + half * 2) = make_float2(s1.x + s1.y, s2.x + s2.y);
+                asm volatile("bar.sync %0, 64;" ::"r"(3 + wq) : "memory");
+                const float4 both = ld4(st);
+                const float mu = (both.x + both.z) * (1.0f / 128.0f);
+                const float rstd = rsqrtf(fmaxf(fmaf(-mu, mu, (both.y + both.w) * (1.0f / 128.0f)), 0.f) + 1e-5f);
+                const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mu * rstd, -mu * rstd);
+                const float* gam = sLn + mlp * 256 + half * 64;
+                const float* bet = gam + 128;
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float4 g4 = ld4(gam + 2 * i), b4 = ld4(bet + 2 * i);
+                    float2 y0 = tc::fma2(tc::fma2(x2[i], rs2, nm2), make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
+                    float2 y1 = tc::fma2(tc::fma2(x2[i + 1], rs2, nm2), make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
+                    tc::split_pair_trunc(fmaxf(y0.x, 0.f), fmaxf(y0.y, 0.f), hi[i], lo[i]);
+                    tc::split_pair_trunc(fmaxf(y1.x, 0.f), fmaxf(y1.y, 0.f), hi[i + 1], lo[i + 1]);
+                }
+                const uint32_t hid = tmem + lane_base + (mlp == 0 ? C_HIDK : C_HIDV);
+                tc::tmem_st32(hid + half * 32, hi);
+                tc::tmem_st32(hid + 64 + half * 32, lo);
+                tc::tmem_st_wait();
+                tc::tc_fence_before();
+                tc::mbar_arrive(&bars[mlp == 0 ? B_HIDK : B_HIDV]);
+                if (mlp == 0) TRACE(role, 3);
+            }
+            TRACE(role, 4);
+            TileIter nx = it;
+            iter_next(d, nx);
+            if (half == 1 && nx.valid) {
+                // ---- features of the NEXT tile while the tensor pipe works on this one
+                const int nb = nx.u != it.u ? (xb ^ 1) : xb;
+                if (nx.u != it.u) stage_x(nx, nb);
+                write_features(sX + (size_t)nb * a.maxn * 4, nx, wq, lane, sFeat);
+                tc::fence_proxy_async_smem();
+                tc::mbar_arrive(&bars[B_FEAT]);
+            }
+            TRACE(role, 5);
+            // ---- logits of this thread's 8 heads, segment softmax across the 32 lanes (rows) of the warp
+            float al[8];
+            {
+                tc::mbar_wait(&bars[B_OUTK], ph);
+                tc::tc_fence_after();
+                uint32_t v0[32], v1[32];
+                tc::tmem_ld32_nowait(tmem + lane_base + C_OUT + half * 64, v0);
+                tc::tmem_ld32_nowait(tmem + lane_base + C_OUT + half * 64 + 32, v1);
+                tc::tmem_ld_wait();
                 const float* qrow = sQ + wq * 128 + half * 64;
                 const float* b2 = sB2 + half * 64;
 #pragma unroll
                 for (int h = 0; h < 8; h++) {
-                    float s = 0.f;
-#pragma unroll
-                    for (int dd = 0; dd < 8; dd++) s = fmaf(qrow[h * 8 + dd], kk[h * 8 + dd] + b2[h * 8 + dd], s);
-                    const float lg = rowvalid ? s * kInvSqrtD : -INFINITY;
-                    const float m = warp_max(lg);
-                    const float e = rowvalid ? expf(lg - m) : 0.f;
-                    const float tot = warp_sum(e);
-                    alpha[h] = e / tot;
+                    float sa = 0.f, sb = 0.f;
+                    const uint32_t* vv = h < 4 ? v0 : v1;
+                    const int o = (h & 3) * 8;
+                    const float4 qa = ld4(qrow + h * 8), qb = ld4(qrow + h * 8 + 4), ba = ld4(b2 + h * 8), bb = ld4(b2 + h * 8 + 4);
+                    sa = fmaf(qa.x, __uint_as_float(vv[o]) + ba.x, sa); sb = fmaf(qa.y, __uint_as_float(vv[o + 1]) + ba.y, sb);
+                    sa = fmaf(qa.z, __uint_as_float(vv[o + 2]) + ba.z, sa); sb = fmaf(qa.w, __uint_as_float(vv[o + 3]) + ba.w, sb);
+                    sa = fmaf(qb.x, __uint_as_float(vv[o + 4]) + bb.x, sa); sb = fmaf(qb.y, __uint_as_float(vv[o + 5]) + bb.y, sb);
+                    sa = fmaf(qb.z, __uint_as_float(vv[o + 6]) + bb.z, sa); sb = fmaf(qb.w, __uint_as_float(vv[o + 7]) + bb.w, sb);
+                    al[h] = rowvalid ? (sa + sb) * kInvSqrtD : -INFINITY;
                 }
+                float mx[8], sm[8];
+#pragma unroll
+                for (int h = 0; h < 8; h++) mx[h] = al[h];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int h = 0; h < 8; h++) mx[h] = fmaxf(mx[h], __shfl_xor_sync(PG_FULL, mx[h], o));
+#pragma unroll
+                for (int h = 0; h < 8; h++) { al[h] = rowvalid ? __expf(al[h] - mx[h]) : 0.f; sm[h] = al[h]; }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int h = 0; h < 8; h++) sm[h] += __shfl_xor_sync(PG_FULL, sm[h], o);
+#pragma unroll
+                for (int h = 0; h < 8; h++) al[h] *= __frcp_rn(sm[h]);
             }
+            TRACE(role, 6);
+            // ---- alpha-weighted sum of the value rows over the segment (lanes), residual add into h_bond
             {
-                tc::mbar_wait(&bars[2], ph2); ph2 ^= 1;
+                tc::mbar_wait(&bars[B_OUTV], ph);
                 tc::tc_fence_after();
-                const float* b2 = sB2 + 128 + half * 64;
 #pragma unroll
                 for (int ch = 0; ch < 2; ch++) {
                     float v[32];
-                    tc::tmem_ld32(tmem + lane_base + 128 + half * 64 + ch * 32, v);
+                    tc::tmem_ld32(tmem + lane_base + C_OUT + 128 + half * 64 + ch * 32, v);
 #pragma unroll
-                    for (int i = 0; i < 32; i++) v[i] = rowvalid ? alpha[ch * 4 + (i >> 3)] * v[i] : 0.f;
+                    for (int i = 0; i < 32; i++) v[i] = al[ch * 4 + (i >> 3)] * v[i];       // alpha is 0 on padded rows
                     const float o = transpose_reduce32(v, lane);
-                    if (segvalid) {
+                    if (sg.valid) {
                         const int c = half * 64 + ch * 32 + lane;
-                        a.hb[(size_t)eji * 128 + c] += o + b2[ch * 32 + lane];     // sum(alpha) = 1; residual (uni_denoiser.py:285)
+                        a.hb[(size_t)sg.eji * 128 + c] += o + sB2[128 + c];     // sum(alpha) = 1; residual (uni_denoiser.py:285)
                     }
                 }
+                tc::tc_fence_before();
+                tc::mbar_arrive(&bars[B_FREE]);
             }
-            tc::tc_fence_before();
-            __syncthreads();                                 // TMEM columns, sFeat and sQ are reused by the next tile
+            TRACE(role, 7);
+            it = nx; ph ^= 1; buf ^= 1; tcount++;
         }
     }
-    if (warp == 0) { tc::tc_fence_after(); tc::tmem_dealloc<512>(tmem); }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 8) { tc::tc_fence_after(); tc::tmem_dealloc<512>(tmem); }
 }
 
-// R[e] = smear(|x_dst - x_src|) @ Wrji  for every bond edge (the r_ji slice of the triplet MLPs' first Linear)
-__global__ void __launch_bounds__(256) trip_r_kernel(PlanDev d, const float* __restrict__ x, const float* __restrict__ wrji,
-                                                     float* __restrict__ R) {
+// Per-edge partials of the triplet MLPs' first Linear, for every bond edge e = (src -> dst):
+//   P[e] = h_bond[e] Wb (edge GEMM output T) + h_src Whk + h_dst Whj + b1 + smear(|x_dst - x_src|) Wrkj   (edge in the k->j role)
+//   R[e] = smear(|x_dst - x_src|) Wrji                                                                    (edge in the j->i role)
+// Both k|v halves (256 channels).  P rows of the edges into one atom are contiguous -> one bulk copy per unit.
+__global__ void __launch_bounds__(256) trip_pr_kernel(TripTcArgs a) {
+    const PlanDev& d = a.d;
     const int lane = threadIdx.x & 31;
     const long long e = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (e >= d.Eb) return;
     const int s = d.esrc_node[e], t = d.edst_node[e];
-    const float d0 = x[(size_t)t * 3] - x[(size_t)s * 3], d1 = x[(size_t)t * 3 + 1] - x[(size_t)s * 3 + 1], d2 = x[(size_t)t * 3 + 2] - x[(size_t)s * 3 + 2];
+    const float d0 = a.x[(size_t)t * 3] - a.x[(size_t)s * 3], d1 = a.x[(size_t)t * 3 + 1] - a.x[(size_t)s * 3 + 1],
+                d2 = a.x[(size_t)t * 3 + 2] - a.x[(size_t)s * 3 + 2];
     const float dist = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
     const float mine = lane < 20 ? smear_val(dist, lane) : 0.f;
-    float4 a0 = make_float4(0, 0, 0, 0), a1 = a0;
+    float4 r0 = make_float4(0, 0, 0, 0), r1 = r0;
+    float4 p0 = f4add(f4add(ldg4(a.T + (size_t)e * a.ldt + a.t_k + lane * 4), ldg4(a.H + (size_t)s * a.ldh + a.hk_k + lane * 4)),
+                      ldg4(a.H + (size_t)t * a.ldh + a.hj_k + lane * 4));
+    float4 p1 = f4add(f4add(ldg4(a.T + (size_t)e * a.ldt + a.t_v + lane * 4), ldg4(a.H + (size_t)s * a.ldh + a.hk_v + lane * 4)),
+                      ldg4(a.H + (size_t)t * a.ldh + a.hj_v + lane * 4));
 #pragma unroll
     for (int gg = 0; gg < 20; gg++) {
         const float sg = __shfl_sync(PG_FULL, mine, gg);
-        a0 = f4fma(sg, ldg4(wrji + gg * 256 + lane * 4), a0);
-        a1 = f4fma(sg, ldg4(wrji + gg * 256 + 128 + lane * 4), a1);
+        r0 = f4fma(sg, ldg4(a.wrji + gg * 256 + lane * 4), r0);
+        r1 = f4fma(sg, ldg4(a.wrji + gg * 256 + 128 + lane * 4), r1);
+        p0 = f4fma(sg, ldg4(a.wrkj + gg * 256 + lane * 4), p0);
+        p1 = f4fma(sg, ldg4(a.wrkj + gg * 256 + 128 + lane * 4), p1);
     }
-    st4(R + (size_t)e * 256 + lane * 4, a0);
-    st4(R + (size_t)e * 256 + 128 + lane * 4, a1);
+    st4(a.R + (size_t)e * 256 + lane * 4, r0);
+    st4(a.R + (size_t)e * 256 + 128 + lane * 4, r1);
+    st4(a.P + (size_t)e * 256 + lane * 4, p0);
+    st4(a.P + (size_t)e * 256 + 128 + lane * 4, p1);
 }
 }  // namespace
 
-size_t pg_trip_tc_smem(int maxn) { return (size_t)SM_FIXED + (size_t)(maxn - 1) * (PS_LD + 20) * sizeof(float) + 1024; }
+size_t pg_trip_tc_smem(int maxn) { return (size_t)SM_FIXED + ((size_t)(maxn - 1) * PS_LD + 2 * (size_t)maxn * 4) * sizeof(float) + 1024; }
 
 int pg_launch_trip_tc(const TripTcArgs& a, int num_sms, cudaStream_t s) {
     if (a.d.Nl <= 0) return PG_OK;
@@ -332,10 +482,10 @@ int pg_launch_trip_tc(const TripTcArgs& a, int num_sms, cudaStream_t s) {
     if (smem > 227 * 1024) { pg_set_error("trip_tc: shared memory budget exceeded"); return PG_ELIMIT; }
     static size_t cur = 0;
     if (smem > cur) { PG_CUDA_CHECK(cudaFuncSetAttribute(trip_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cur = smem; }
-    trip_r_kernel<<<(unsigned)((a.d.Eb + 7) / 8), 256, 0, s>>>(a.d, a.x, a.wrji, a.R);
+    trip_pr_kernel<<<(unsigned)((a.d.Eb + 7) / 8), 256, 0, s>>>(a);
     PG_LAUNCH_CHECK();
     const unsigned grid = (unsigned)std::min<long long>(a.d.Nl, num_sms);
-    trip_tc_kernel<<<grid, 256, smem, s>>>(a);
+    trip_tc_kernel<<<grid, NTHREADS, smem, s>>>(a);
     PG_LAUNCH_CHECK();
     return PG_OK;
 }
