@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(128) knn_attn_kernel(KnnAttnArgs a) {
 // NodeUpdateLayer / PosUpdateLayer over the complete ligand bond graph (uni_denoiser.py:284,294): the
 // segment of ligand atom i is the contiguous block of its n-1 incoming edges in the internal order.
 template <int POS>
-__global__ void __launch_bounds__(128) bond_attn_kernel(BondAttnArgs a) {
+__global__ void __launch_bounds__(128, 4) bond_attn_kernel(BondAttnArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int u = blockIdx.x * 4 + warp;

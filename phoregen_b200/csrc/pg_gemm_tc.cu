@@ -5,154 +5,226 @@
 // keeps ~16 mantissa bits (rel. error ~2^-16) — needed for the 1e-3 / 1e-4 parity bar, which plain bf16
 // (2^-9) does not meet through six residual layers.
 //
-// CTA = 128 rows.  The A tile is produced once by all threads (fused prologue: sum of two inputs, or
-// gather-add + LayerNorm + ReLU), split to bf16 hi/lo and written in the canonical K-major 128B-swizzled UMMA
-// layout; weights arrive pre-split (bf16 hi/lo, [N][128] K-major) and are staged per 64-column block with
-// cp.async.  One elected thread issues the 24 tcgen05.mma (M=128, N=64, K=16) of a column block and commits to
-// an mbarrier; all 8 warps then read the accumulator with tcgen05.ld (32 lanes x 32 columns each), add bias /
-// residual and store.  2 CTAs per SM (96 KB smem, 64 TMEM columns each) overlap each other's phases.
+// Persistent, warp-specialised CTA (one per SM) walking 128-row tiles:
+//   warps 0-3  epilogue      : accumulator (TMEM, double buffered) -> registers -> bias / residual / ReLU -> global
+//   warps 4-7  A producer    : fused prologue (sum of two inputs, or gather-add + LayerNorm + ReLU), bf16 hi/lo split,
+//                              canonical K-major 128B-swizzled UMMA layout, double buffered (next tile while MMAs run)
+//   warp  8    B loader      : weights are stored pre-swizzled, one 32 KB image per 64-column block -> a single
+//                              cp.async.bulk (TMA unit) per block into a 2-stage ring, mbarrier transaction counts
+//   warp  9    MMA issuer    : 24 tcgen05.mma (M=128, N=64, K=16) per block, tcgen05.commit releases smem / signals epilogue
+#include <algorithm>
 #include "pg_gemm.h"
 #include "pg_tc.cuh"
 
 namespace {
-constexpr int TM = 128, TN = 64, TK = 128;
-constexpr int A_KBLK_BYTES = TM * 128;       // one 64-wide K block of the A tile: 128 rows x 128 B
-constexpr int B_KBLK_BYTES = TN * 128;       // one 64-wide K block of the B tile:  64 rows x 128 B
-constexpr int SMEM_A = 2 * 2 * A_KBLK_BYTES;   // hi/lo x 2 K blocks = 64 KB
-constexpr int SMEM_B = 2 * 2 * B_KBLK_BYTES;   // 32 KB
-constexpr int SMEM_TOTAL = SMEM_A + SMEM_B + 1024 /*alignment slack*/ + 64;
+constexpr int TM = 128, TN = 64;
+constexpr int A_KBLK = TM * 128;             // one 64-wide K block of the A tile: 128 rows x 128 B
+constexpr int A_BUF = 4 * A_KBLK;            // (hi,lo) x 2 K blocks = 64 KB
+constexpr int B_KBLK = TN * 128;             // 8 KB
+constexpr int B_BUF = 4 * B_KBLK;            // (hi,lo) x 2 K blocks = 32 KB  (== one pre-swizzled weight image)
+constexpr int NB = 2;                        // B ring stages
+constexpr int EPI_LD = 36;                     // padded row stride (floats) of the per-warp epilogue staging tile [32 rows x 32 cols]
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;   // four epilogue warps
+constexpr int SMEM_TOTAL = 2 * A_BUF + NB * B_BUF + EPI_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int NTHREADS = 320;
+
+enum { A_FULL = 0, A_EMPTY = 2, B_FULL = 4, B_EMPTY = 4 + NB, ACC_FULL = 4 + 2 * NB, ACC_EMPTY = 6 + 2 * NB, NBARS = 8 + 2 * NB };
 
 template <int PRO>
-__global__ void __launch_bounds__(256, 2) gemm_tc_kernel(GemmArgs a) {
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(GemmArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    // SWIZZLE_128B tiles need 1024-byte alignment
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = smem;                       // [hi|lo][kb][128 rows x 128 B]
-    uint8_t* sB = smem + SMEM_A;              // [hi|lo][kb][ 64 rows x 128 B]
-    uint64_t* bar = (uint64_t*)(smem + SMEM_A + SMEM_B);
-    uint32_t* tmem_slot = (uint32_t*)(bar + 1);
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + 2 * A_BUF;
+    float* sEpi = (float*)(sB + NB * B_BUF);
+    uint64_t* bars = (uint64_t*)(sB + NB * B_BUF + EPI_BYTES);
+    uint32_t* tmem_slot = (uint32_t*)(bars + NBARS);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long m0 = (long long)blockIdx.x * TM;
+    const long long n_mtiles = (a.M + TM - 1) / TM;
 
-    if (warp == 0) tc::tmem_alloc<TN>(tmem_slot);
-    if (tid == 32) { tc::mbar_init(bar, 1); tc::fence_barrier_init(); }
-
-    // ---- A tile: fused prologue, bf16 hi/lo split, swizzled K-major layout
-    float4 g4 = make_float4(1, 1, 1, 1), b4 = make_float4(0, 0, 0, 0);
-    if (PRO == PRO_LNRELU) { g4 = ldg4(a.ln_g + lane * 4); b4 = ldg4(a.ln_b + lane * 4); }
-    for (int r = warp; r < TM; r += 8) {
-        const long long m = m0 + r;
-        float4 v = make_float4(0, 0, 0, 0);
-        if (m < a.M) {
-            v = ld4(a.A + m * a.lda + lane * 4);
-            if (PRO == PRO_SUM2) v = f4add(v, ld4(a.A2 + m * a.lda2 + lane * 4));
-            if (PRO == PRO_LNRELU) {
-                if (a.A2) {
-                    const long long idx = a.gidx ? (long long)a.gidx[m] : m;
-                    v = f4add(v, ld4(a.A2 + idx * a.lda2 + lane * 4));
-                }
-                v = ln_relu_row(v, g4, b4);
-            }
+    if (warp == 9) tc::tmem_alloc<2 * TN>(tmem_slot);
+    if (tid == 0) {
+        for (int i = 0; i < 2; i++) {
+            tc::mbar_init(&bars[A_FULL + i], 128); tc::mbar_init(&bars[A_EMPTY + i], 1);
+            tc::mbar_init(&bars[ACC_FULL + i], 1); tc::mbar_init(&bars[ACC_EMPTY + i], 128);
         }
-        __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-        tc::split_bf16(v.x, h0, l0); tc::split_bf16(v.y, h1, l1); tc::split_bf16(v.z, h2, l2); tc::split_bf16(v.w, h3, l3);
-        // lane covers k = 4*lane .. 4*lane+3: K block kb = lane/16, 16-byte chunk j = (lane%16)/2, half = lane%2
-        const int kb = lane >> 4, j = (lane & 15) >> 1, half = lane & 1;
-        const uint32_t off = kb * A_KBLK_BYTES + tc::sw128_chunk(r, j) + half * 8;
-        *reinterpret_cast<uint2*>(sA + off) = make_uint2(tc::pack_bf16(h0, h1), tc::pack_bf16(h2, h3));
-        *reinterpret_cast<uint2*>(sA + 2 * A_KBLK_BYTES + off) = make_uint2(tc::pack_bf16(l0, l1), tc::pack_bf16(l2, l3));
+        for (int i = 0; i < NB; i++) { tc::mbar_init(&bars[B_FULL + i], 1); tc::mbar_init(&bars[B_EMPTY + i], 1); }
+        tc::fence_barrier_init();
     }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t sA_u32 = tc::smem_u32(sA), sB_u32 = tc::smem_u32(sB);
-    constexpr uint32_t idesc = tc::umma_idesc_bf16(TM, TN);
-    uint32_t parity = 0;
 
-    for (int nt = 0; nt < a.ntiles; nt++) {
-        // ---- weights of this 64-column block: [hi|lo][64 n][128 k] bf16, 16-byte chunks -> swizzled smem
-        {
-            const uint16_t* wsrc = reinterpret_cast<const uint16_t*>(a.Wbf);
-            const long long nrows_total = (long long)a.ntiles * TN;
+    if (warp < 4) {
+        // ================= epilogue =================
+        // TMEM row (thread = row) -> per-warp smem tile -> row-contiguous global stores (4 rows x 128 B per instruction)
+        long long cnt = 0;
+        float* stg = sEpi + warp * 32 * EPI_LD;
+        const int rsub = lane >> 3, csub = (lane & 7) * 4;
+        for (long long mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
+            const long long mw = mt * TM + warp * 32;               // first row of this warp
+            for (int nt = 0; nt < a.ntiles; nt++, cnt++) {
+                const int ab = cnt & 1;
+                tc::mbar_wait(&bars[ACC_FULL + ab], (cnt >> 1) & 1);
+                tc::tc_fence_after();
+                uint32_t v[64];
+                tc::tmem_ld32_nowait(tmem_base + ((uint32_t)(warp * 32) << 16) + ab * TN, v);
+                tc::tmem_ld32_nowait(tmem_base + ((uint32_t)(warp * 32) << 16) + ab * TN + 32, v + 32);
+                tc::tmem_ld_wait();
+                tc::tc_fence_before();
+                tc::mbar_arrive(&bars[ACC_EMPTY + ab]);            // accumulator is in registers: the MMA warp may reuse it
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int idx = tid + i * 256;              // 2048 chunks: [part 2][n 64][chunk 16]
-                const int part = idx >> 10, n = (idx >> 4) & 63, c = idx & 15;
-                const int kb = c >> 3, j = c & 7;
-                const uint16_t* src = wsrc + ((long long)part * nrows_total + (long long)nt * TN + n) * TK + c * 8;
-                const uint32_t dst = sB_u32 + part * 2 * B_KBLK_BYTES + kb * B_KBLK_BYTES + tc::sw128_chunk(n, j);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                for (int hh = 0; hh < 2; hh++) {
+                    const int c0 = nt * TN + hh * 32 + csub;
+#pragma unroll
+                    for (int q = 0; q < 8; q++)
+                        st4(stg + lane * EPI_LD + q * 4, make_float4(__uint_as_float(v[hh * 32 + q * 4]), __uint_as_float(v[hh * 32 + q * 4 + 1]),
+                                                                     __uint_as_float(v[hh * 32 + q * 4 + 2]), __uint_as_float(v[hh * 32 + q * 4 + 3])));
+                    __syncwarp();
+                    float4 bb = make_float4(0, 0, 0, 0);
+                    if (a.bias) bb = ldg4(a.bias + c0);
+#pragma unroll
+                    for (int rr = 0; rr < 8; rr++) {
+                        const int r = rr * 4 + rsub;
+                        const long long m = mw + r;
+                        if (m < a.M) {
+                            float4 o = f4add(ld4(stg + r * EPI_LD + csub), bb);
+                            if (a.resid) o = f4add(o, ld4(a.resid + m * a.ldr + c0));
+                            if (a.relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+                            st4(a.C + m * a.ldc + c0, o);
+                        }
+                    }
+                    __syncwarp();
+                }
             }
-            asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
         }
-        tc::fence_proxy_async_smem();     // generic-proxy writes (A tile, cp.async) -> async proxy
-        __syncthreads();
-        if (tid == 0) {
-            tc::tc_fence_after();
-            uint32_t acc = 0;
+    } else if (warp < 8) {
+        // ================= A producer: fused prologue, bf16 hi/lo split, swizzled K-major layout =================
+        const int pw = warp - 4;
+        float4 g4 = make_float4(1, 1, 1, 1), b4 = make_float4(0, 0, 0, 0);
+        if (PRO == PRO_LNRELU) { g4 = ldg4(a.ln_g + lane * 4); b4 = ldg4(a.ln_b + lane * 4); }
+        long long it = 0;
+        for (long long mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x, it++) {
+            const int buf = it & 1;
+            tc::mbar_wait(&bars[A_EMPTY + buf], ((it >> 1) & 1) ^ 1);   // MMAs that read this buffer two tiles ago are done
+            uint8_t* dstA = sA + buf * A_BUF;
+            const long long m0 = mt * TM;
+            // rows pw, pw+4, ...: loads of a whole batch are issued before any is consumed (enough bytes in flight per SM
+            // to cover HBM latency: Little's law needs ~28 KB at 23 B/clk/SM)
+            constexpr int BATCH = (PRO == PRO_PLAIN) ? 16 : 8;
+            for (int rb = 0; rb < TM / 4; rb += BATCH) {
+                float4 v[BATCH], w[BATCH];
 #pragma unroll
-            for (int combo = 0; combo < 3; combo++) {       // hi*hi, hi*lo, lo*hi
-                const uint32_t abase = sA_u32 + (combo == 2 ? 2 * A_KBLK_BYTES : 0);
-                const uint32_t bbase = sB_u32 + (combo == 1 ? 2 * B_KBLK_BYTES : 0);
-#pragma unroll
-                for (int kb = 0; kb < 2; kb++) {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {           // 4 x K=16 slices (32 B) inside the 128-byte swizzle row
-                        const uint64_t ad = tc::umma_desc_sw128(abase + kb * A_KBLK_BYTES + k * 32);
-                        const uint64_t bd = tc::umma_desc_sw128(bbase + kb * B_KBLK_BYTES + k * 32);
-                        tc::umma_bf16(tmem_base, ad, bd, idesc, acc);
-                        acc = 1;
+                for (int i = 0; i < BATCH; i++) {
+                    const long long m = m0 + pw + (rb + i) * 4;
+                    v[i] = make_float4(0, 0, 0, 0); w[i] = v[i];
+                    if (m < a.M) {
+                        v[i] = ld4(a.A + m * a.lda + lane * 4);
+                        if (PRO == PRO_SUM2) w[i] = ld4(a.A2 + m * a.lda2 + lane * 4);
+                        if (PRO == PRO_LNRELU && a.A2) {
+                            const long long idx = a.gidx ? (long long)a.gidx[m] : m;
+                            w[i] = ld4(a.A2 + idx * a.lda2 + lane * 4);
+                        }
                     }
                 }
-            }
-            tc::umma_commit(bar);
-        }
-        tc::mbar_wait(bar, parity);
-        parity ^= 1;
-        tc::tc_fence_after();
-        // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., columns 32*(w/4)..; thread = one row x 32 columns
-        {
-            const int row = (warp & 3) * 32 + lane, ch = warp >> 2;
-            float v[32];
-            tc::tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + ch * 32, v);
-            const long long m = m0 + row;
-            const int c0 = nt * TN + ch * 32;
-            if (m < a.M) {
 #pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-                    if (a.bias) o = f4add(o, ldg4(a.bias + c0 + q * 4));
-                    if (a.resid) o = f4add(o, ld4(a.resid + m * a.ldr + c0 + q * 4));
-                    if (a.relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
-                    st4(a.C + m * a.ldc + c0 + q * 4, o);
+                for (int i = 0; i < BATCH; i++) {
+                    const int r = pw + (rb + i) * 4;
+                    float4 x = v[i];
+                    if (PRO != PRO_PLAIN) x = f4add(x, w[i]);
+                    if (PRO == PRO_LNRELU && (m0 + r) < a.M) x = ln_relu_row(x, g4, b4);
+                    uint32_t h0, l0, h1, l1;
+                    tc::split_pair_trunc(x.x, x.y, h0, l0);
+                    tc::split_pair_trunc(x.z, x.w, h1, l1);
+                    // lane covers k = 4*lane .. 4*lane+3: K block kb = lane/16, 16-byte chunk j = (lane%16)/2, half = lane%2
+                    const int kb = lane >> 4, j = (lane & 15) >> 1, half = lane & 1;
+                    const uint32_t off = kb * A_KBLK + tc::sw128_chunk(r, j) + half * 8;
+                    *reinterpret_cast<uint2*>(dstA + off) = make_uint2(h0, h1);
+                    *reinterpret_cast<uint2*>(dstA + 2 * A_KBLK + off) = make_uint2(l0, l1);
                 }
             }
+            tc::fence_proxy_async_smem();                               // generic-proxy writes -> async proxy (tensor core reads)
+            tc::mbar_arrive(&bars[A_FULL + buf]);
         }
-        tc::tc_fence_before();
-        __syncthreads();        // accumulator drained and B tile free before the next column block
+    } else if (warp == 8) {
+        // ================= B loader: one bulk copy of a pre-swizzled 32 KB weight image per 64-column block =================
+        long long cnt = 0;
+        for (long long mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
+            for (int nt = 0; nt < a.ntiles; nt++, cnt++) {
+                const int s = cnt % NB;
+                tc::mbar_wait(&bars[B_EMPTY + s], ((cnt / NB) & 1) ^ 1);
+                if (lane == 0) {
+                    tc::mbar_arrive_expect_tx(&bars[B_FULL + s], B_BUF);
+                    tc::bulk_copy_g2s(sB + s * B_BUF, reinterpret_cast<const uint8_t*>(a.Wbf) + (size_t)nt * B_BUF, B_BUF, &bars[B_FULL + s]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================= MMA issuer =================
+        constexpr uint32_t idesc = tc::umma_idesc_bf16(TM, TN);
+        const uint32_t sA_u32 = tc::smem_u32(sA), sB_u32 = tc::smem_u32(sB);
+        long long cnt = 0, it = 0;
+        for (long long mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x, it++) {
+            const int buf = it & 1;
+            tc::mbar_wait(&bars[A_FULL + buf], (it >> 1) & 1);
+            for (int nt = 0; nt < a.ntiles; nt++, cnt++) {
+                const int s = cnt % NB, ab = cnt & 1;
+                tc::mbar_wait(&bars[B_FULL + s], (cnt / NB) & 1);
+                tc::mbar_wait(&bars[ACC_EMPTY + ab], ((cnt >> 1) & 1) ^ 1);
+                tc::tc_fence_after();
+                if (lane == 0) {
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int combo = 0; combo < 3; combo++) {       // hi*hi, hi*lo, lo*hi
+                        const uint32_t abase = sA_u32 + buf * A_BUF + (combo == 2 ? 2 * A_KBLK : 0);
+                        const uint32_t bbase = sB_u32 + s * B_BUF + (combo == 1 ? 2 * B_KBLK : 0);
+#pragma unroll
+                        for (int kb = 0; kb < 2; kb++) {
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {           // 4 x K=16 slices (32 B) inside the 128-byte swizzle row
+                                const uint64_t ad = tc::umma_desc_sw128(abase + kb * A_KBLK + k * 32);
+                                const uint64_t bd = tc::umma_desc_sw128(bbase + kb * B_KBLK + k * 32);
+                                tc::umma_bf16(tmem_base + ab * TN, ad, bd, idesc, acc);
+                                acc = 1;
+                            }
+                        }
+                    }
+                    tc::umma_commit(&bars[ACC_FULL + ab]);          // accumulator ready for the epilogue
+                    tc::umma_commit(&bars[B_EMPTY + s]);            // weight stage may be refilled
+                    if (nt == a.ntiles - 1) tc::umma_commit(&bars[A_EMPTY + buf]);
+                }
+                __syncwarp();
+            }
+        }
     }
-    if (warp == 0) { tc::tc_fence_after(); tc::tmem_dealloc<TN>(tmem_base); }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 9) { tc::tc_fence_after(); tc::tmem_dealloc<2 * TN>(tmem_base); }
 }
 }  // namespace
 
 int pg_launch_gemm_tc(const GemmArgs& a, int pro, cudaStream_t stream) {
     if (a.M <= 0) return PG_OK;
     if (!a.Wbf) { pg_set_error("tcgen05 GEMM needs the bf16 hi/lo weights"); return PG_EINVAL; }
-    static bool configured = false;
-    if (!configured) {
+    static int sms = 0;
+    if (!sms) {
         PG_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<PRO_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
         PG_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<PRO_SUM2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
         PG_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<PRO_LNRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-        configured = true;
+        int dev = 0;
+        PG_CUDA_CHECK(cudaGetDevice(&dev));
+        PG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    const unsigned grid = (unsigned)((a.M + TM - 1) / TM);
+    const long long n_mtiles = (a.M + TM - 1) / TM;
+    const unsigned grid = (unsigned)std::min<long long>(n_mtiles, sms);
     GemmArgs b = a;
     b.ntiles = a.ntiles * 2;      // callers count 128-column blocks; this kernel walks 64-column blocks
     switch (pro) {
-        case PRO_PLAIN: gemm_tc_kernel<PRO_PLAIN><<<grid, 256, SMEM_TOTAL, stream>>>(b); break;
-        case PRO_SUM2: gemm_tc_kernel<PRO_SUM2><<<grid, 256, SMEM_TOTAL, stream>>>(b); break;
-        case PRO_LNRELU: gemm_tc_kernel<PRO_LNRELU><<<grid, 256, SMEM_TOTAL, stream>>>(b); break;
+        case PRO_PLAIN: gemm_tc_kernel<PRO_PLAIN><<<grid, NTHREADS, SMEM_TOTAL, stream>>>(b); break;
+        case PRO_SUM2: gemm_tc_kernel<PRO_SUM2><<<grid, NTHREADS, SMEM_TOTAL, stream>>>(b); break;
+        case PRO_LNRELU: gemm_tc_kernel<PRO_LNRELU><<<grid, NTHREADS, SMEM_TOTAL, stream>>>(b); break;
         default: pg_set_error("bad gemm prologue"); return PG_EINVAL;
     }
     PG_LAUNCH_CHECK();

@@ -138,11 +138,30 @@ def bf16_split(wt):
     return np.concatenate([hi.reshape(-1), lo.reshape(-1)]).view(np.float32)
 
 
+def bf16_tiles64(wt):
+    """k-major fp32 weight [128][N] -> the exact shared-memory images the tcgen05 GEMM bulk-copies: for every block of 64
+    output columns a 32 KB image [hi|lo][K block 0|1][64 rows x 128 B], rows K-major with the 128-byte swizzle applied
+    (16-byte chunk j of row r stored at chunk j ^ (r % 8)); see csrc/pg_gemm_tc.cu and tc::sw128_chunk."""
+    w = np.ascontiguousarray(np.asarray(wt, dtype=np.float64).T, dtype=np.float32)      # [N][128]
+    N = w.shape[0]
+    assert N % 64 == 0 and w.shape[1] == 128
+    hi = _bf16_bits(w)
+    lo = _bf16_bits(w - (hi.astype(np.uint32) << 16).view(np.float32))
+    r = np.arange(64)[:, None]
+    j = np.arange(8)[None, :]
+    out = np.empty((N // 64, 2, 2, 64, 8, 8), dtype=np.uint16)
+    for part, bits in enumerate((hi, lo)):
+        t = bits.reshape(N // 64, 64, 2, 8, 8)                 # [tile][row][kb][chunk][8]
+        for kb in range(2):
+            out[:, part, kb][:, r, j ^ (r % 8)] = t[:, :, kb][:, r, j]
+    return out.reshape(-1).view(np.float32)
+
+
 def build_blob(sd):
     """-> (fp32 numpy blob, int64 offsets in floats) following the library's own slot table."""
     packed = pack_state_dict(sd)
     for name in [k for k in packed if k.endswith((".wt", "w2q_t", "wcat_t", "w1t")) and k != "G.ew.w1t"]:
-        packed[name + ".bf"] = bf16_split(packed[name])
+        packed[name + ".bf"] = bf16_tiles64(packed[name])
     for name in [k for k in packed if k.endswith(".tr.w2k") or k.endswith(".tr.w2v")]:
         packed[name + ".bf"] = bf16_split(np.asarray(packed[name]).T)          # already [out][in] = [N][K]
     for name in [k for k in packed if k.endswith(".tr.wa")]:
