@@ -48,12 +48,13 @@ def f_ref_flops(n, p):
 
 
 def f_exec_trip_flops(n):
-    """FLOPs the factorised triplet kernel actually issues per molecule-layer (DESIGN.md 'Factorisation')."""
-    Eb, E3 = n * (n - 1), n * (n - 1) * (n - 2)
-    per_row = 2 * (13 * 128 + 2 * 128) + 2 * 6 * 128 + 16 * 128 + 16 * 128          # angle part, LN x2, logits, aggregate
-    per_seg = 2 * 20 * 128 + 128 * 128 + 128 * 128                                  # r_ji part, query fold, value second Linear
-    per_unit_row = 2 * (20 * 128 + 3 * 128)                                         # staging of P rows
-    return 2.0 * (E3 * per_row + Eb * per_seg + Eb * per_unit_row)
+    """bf16 tensor FLOPs the tcgen05 triplet kernel actually issues per molecule-layer (DESIGN.md 'Triplet kernel'):
+    per 128-row tile (4 segments x 32 lanes) 3 MMAs M128 N256 K16 (angle slice, bf16x3) + 2 x 24 MMAs M128 N128 K16
+    (second Linear of the key / value MLPs, bf16x3); ceil((n-1)/4) tiles per ligand atom.  Includes the padding rows and
+    the x3 of the hi/lo split, so it is the work the tensor pipe really performs."""
+    tiles = n * ((n - 1 + 3) // 4)
+    macs_per_tile = 3 * 128 * 256 * 16 + 48 * 128 * 128 * 16
+    return 2.0 * tiles * macs_per_tile
 
 
 class ClockSampler:
@@ -278,21 +279,28 @@ def run_ours(args):
         trip_launch_ms = trip_ms / max(trip_n, 1)
         achieved = f_trip_layer * G / (trip_launch_ms * 1e-3) / 1e12
         exec_tf = f_exec_trip_flops(n) * G / (trip_launch_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "trip_kernel (BondUpdateLayer, uni_denoiser.py:123-165)",
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "trip_tc_traffic.json")      # dram bytes of one launch from the committed ncu --set full capture
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("molecules") == G and tj.get("atoms") == n:
+                traffic = tj["dram_bytes_per_launch"]
+        roof = {"bound": "tensor", "kernel": "trip_tc_kernel (BondUpdateLayer, uni_denoiser.py:123-165)",
                 "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
-                "traffic": None, "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                "traffic": traffic, "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "launch_ms": trip_launch_ms, "launches_timed": trip_n,
                 "algorithmic_flops_per_launch": f_trip_layer * G, "executed_flops_per_launch": f_exec_trip_flops(n) * G,
                 "achieved_executed": exec_tf,
-                "note": "achieved counts the reference formulation's FLOPs (SURVEY.md §8(d) term C); the kernel executes the exactly "
-                        "factorised form in fp32 on the FFMA pipe (round-1 kernel; tcgen05 version is the next step), so the "
-                        "executed-FLOP rate is `achieved_executed`",
+                "note": "achieved = reference-formulation FLOPs of the triplet layer (SURVEY.md §8(d) term C: per-triplet 437->128->128 k/v MLPs and "
+                        "256->128->128 q MLP) / measured launch time of trip_tc_kernel; the kernel evaluates the exactly factorised form "
+                        "(first Linear split over its concatenated input, q per edge) with tcgen05 bf16x3 MMAs; `achieved_executed` counts "
+                        "the bf16 tensor FLOPs actually issued (hi/lo x3 and padding rows included)",
                 "step_share": trip_ms / n_prof / max(sum(class_ms.values()), 1e-9), "ms_per_step_by_kernel_class": class_ms,
                 "whole_step_f_ref_tflops": f_ref * G / (ms_per_step * 1e-3) / 1e12}
         line = {
             "metric": "molecules/sec (full 1000-step reverse trajectory)", "value": value, "unit": "molecules/s", "n_gpus": world,
             "steps": K, "warmup": max(W, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "bf16x3 tensor-core contractions (bf16 hi/lo split operands, fp32 accumulate) + f32 elsewhere", "data": "synthetic",
             "config": {"workload": f"configs[1]: {G} molecules/GPU x {n} heavy atoms, 6-8 pharmacophore features (mean {p_mean:.2f}), "
                                    "random-init weights, seed 2032", "molecules_per_gpu": G, "atoms": n, "trajectory_steps": TRAJ_STEPS,
                        "step": "PhoreDiff.forward + categorical/Gaussian posterior update (diffusion.py:432-517), whole step replayed as one CUDA graph",

@@ -68,7 +68,8 @@ struct TripTcArgs {
     int maxn;
 };
 constexpr int PG_TRIP_TC_MAX_ATOMS = 34;
-int pg_launch_trip_tc(const TripTcArgs& a, int num_sms, cudaStream_t s);
+int pg_launch_trip_pr(const TripTcArgs& a, cudaStream_t s);               // per-edge partials P, R (elementwise, HBM-bound)
+int pg_launch_trip_tc(const TripTcArgs& a, int num_sms, cudaStream_t s);  // the tcgen05 triplet kernel proper
 size_t pg_trip_tc_smem(int maxn);
 
 int pg_launch_knn_attn(const KnnAttnArgs& a, int feat, int pos, cudaStream_t s);

@@ -356,6 +356,7 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
                 t.wa_bf = (const uint16_t*)w(L + "tr.wa.bf");
                 t.lnk_g = a.w.lnk_g; t.lnk_b = a.w.lnk_b; t.lnv_g = a.w.lnv_g; t.lnv_b = a.w.lnv_b; t.b2k = a.w.b2k; t.b2v = a.w.b2v;
                 t.hb = p->hb; t.maxn = std::min(d.max_n, PG_TRIP_TC_MAX_ATOMS);
+                { PgTimed timed(p, KC_OTHER, s); PG_TRY(pg_launch_trip_pr(t, s)); }
                 { PgTimed timed(p, KC_TRIP, s); PG_TRY(pg_launch_trip_tc(t, num_sms(), s)); } p->launches += 2;
                 a.min_atoms = PG_TRIP_TC_MAX_ATOMS + 1;
             }

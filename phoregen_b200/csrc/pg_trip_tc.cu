@@ -474,6 +474,13 @@ __global__ void __launch_bounds__(256) trip_pr_kernel(TripTcArgs a) {
 }
 }  // namespace
 
+int pg_launch_trip_pr(const TripTcArgs& a, cudaStream_t s) {
+    if (a.d.Eb <= 0) return PG_OK;
+    trip_pr_kernel<<<(unsigned)((a.d.Eb + 7) / 8), 256, 0, s>>>(a);
+    PG_LAUNCH_CHECK();
+    return PG_OK;
+}
+
 size_t pg_trip_tc_smem(int maxn) { return (size_t)SM_FIXED + ((size_t)(maxn - 1) * PS_LD + 2 * (size_t)maxn * 4) * sizeof(float) + 1024; }
 
 int pg_launch_trip_tc(const TripTcArgs& a, int num_sms, cudaStream_t s) {
@@ -482,8 +489,6 @@ int pg_launch_trip_tc(const TripTcArgs& a, int num_sms, cudaStream_t s) {
     if (smem > 227 * 1024) { pg_set_error("trip_tc: shared memory budget exceeded"); return PG_ELIMIT; }
     static size_t cur = 0;
     if (smem > cur) { PG_CUDA_CHECK(cudaFuncSetAttribute(trip_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cur = smem; }
-    trip_pr_kernel<<<(unsigned)((a.d.Eb + 7) / 8), 256, 0, s>>>(a);
-    PG_LAUNCH_CHECK();
     const unsigned grid = (unsigned)std::min<long long>(a.d.Nl, num_sms);
     trip_tc_kernel<<<grid, NTHREADS, smem, s>>>(a);
     PG_LAUNCH_CHECK();
