@@ -128,12 +128,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(GemmArgs a) {
                         }
                     }
                 }
+                if (PRO != PRO_PLAIN) {
+#pragma unroll
+                    for (int i = 0; i < BATCH; i++) v[i] = f4add(v[i], w[i]);
+                }
+                if (PRO == PRO_LNRELU) {
+                    // LayerNorm + ReLU of the whole batch: the BATCH rows walk through the shuffle butterflies together (ILP)
+                    float s1[BATCH], s2[BATCH];
+#pragma unroll
+                    for (int i = 0; i < BATCH; i++) s1[i] = (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                        for (int i = 0; i < BATCH; i++) s1[i] += __shfl_xor_sync(PG_FULL, s1[i], o);
+#pragma unroll
+                    for (int i = 0; i < BATCH; i++) {
+                        const float mu = s1[i] * (1.0f / 128.0f);
+                        v[i] = make_float4(v[i].x - mu, v[i].y - mu, v[i].z - mu, v[i].w - mu);
+                        s2[i] = fmaf(v[i].x, v[i].x, fmaf(v[i].y, v[i].y, fmaf(v[i].z, v[i].z, v[i].w * v[i].w)));
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                        for (int i = 0; i < BATCH; i++) s2[i] += __shfl_xor_sync(PG_FULL, s2[i], o);
+#pragma unroll
+                    for (int i = 0; i < BATCH; i++) {
+                        const float rstd = rsqrtf(s2[i] * (1.0f / 128.0f) + 1e-5f);
+                        v[i] = make_float4(fmaxf(fmaf(v[i].x * rstd, g4.x, b4.x), 0.f), fmaxf(fmaf(v[i].y * rstd, g4.y, b4.y), 0.f),
+                                           fmaxf(fmaf(v[i].z * rstd, g4.z, b4.z), 0.f), fmaxf(fmaf(v[i].w * rstd, g4.w, b4.w), 0.f));
+                        if (m0 + pw + (rb + i) * 4 >= a.M) v[i] = make_float4(0, 0, 0, 0);
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < BATCH; i++) {
                     const int r = pw + (rb + i) * 4;
-                    float4 x = v[i];
-                    if (PRO != PRO_PLAIN) x = f4add(x, w[i]);
-                    if (PRO == PRO_LNRELU && (m0 + r) < a.M) x = ln_relu_row(x, g4, b4);
+                    const float4 x = v[i];
                     uint32_t h0, l0, h1, l1;
                     tc::split_pair_trunc(x.x, x.y, h0, l0);
                     tc::split_pair_trunc(x.z, x.w, h1, l1);

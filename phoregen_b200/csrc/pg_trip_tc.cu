@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
 
     if (warp >= 8) {
         // registers move from this (nearly idle) warpgroup to the two row warpgroups
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
       if (warp == 8) {
         // ================= MMA issue + loaders (query / r_ji rows via cp.async, P rows via bulk copy) =================
         constexpr uint32_t idesc_feat = tc::umma_idesc_bf16(128, 256);
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
         }
       }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
         // ================= row warps: thread = (row, channel half) =================
         // warp w: rows 32*(w&3)..+31, channels [64*(w>>2), +64) of the key MLP, then of the value MLP; heads 8*(w>>2)..+7
         const int half = warp >> 2;
@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
 //   P[e] = h_bond[e] Wb (edge GEMM output T) + h_src Whk + h_dst Whj + b1 + smear(|x_dst - x_src|) Wrkj   (edge in the k->j role)
 //   R[e] = smear(|x_dst - x_src|) Wrji                                                                    (edge in the j->i role)
 // Both k|v halves (256 channels).  P rows of the edges into one atom are contiguous -> one bulk copy per unit.
-__global__ void __launch_bounds__(256) trip_pr_kernel(TripTcArgs a) {
+__global__ void __launch_bounds__(256, 4) trip_pr_kernel(TripTcArgs a) {
     const PlanDev& d = a.d;
     const int lane = threadIdx.x & 31;
     const long long e = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -454,23 +454,28 @@ __global__ void __launch_bounds__(256) trip_pr_kernel(TripTcArgs a) {
                 d2 = a.x[(size_t)t * 3 + 2] - a.x[(size_t)s * 3 + 2];
     const float dist = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
     const float mine = lane < 20 ? smear_val(dist, lane) : 0.f;
-    float4 r0 = make_float4(0, 0, 0, 0), r1 = r0;
-    float4 p0 = f4add(f4add(ldg4(a.T + (size_t)e * a.ldt + a.t_k + lane * 4), ldg4(a.H + (size_t)s * a.ldh + a.hk_k + lane * 4)),
-                      ldg4(a.H + (size_t)t * a.ldh + a.hj_k + lane * 4));
-    float4 p1 = f4add(f4add(ldg4(a.T + (size_t)e * a.ldt + a.t_v + lane * 4), ldg4(a.H + (size_t)s * a.ldh + a.hk_v + lane * 4)),
-                      ldg4(a.H + (size_t)t * a.ldh + a.hj_v + lane * 4));
+    const float4 p0 = f4add(f4add(ldg4(a.T + (size_t)e * a.ldt + a.t_k + lane * 4), ldg4(a.H + (size_t)s * a.ldh + a.hk_k + lane * 4)),
+                            ldg4(a.H + (size_t)t * a.ldh + a.hj_k + lane * 4));
+    const float4 p1 = f4add(f4add(ldg4(a.T + (size_t)e * a.ldt + a.t_v + lane * 4), ldg4(a.H + (size_t)s * a.ldh + a.hk_v + lane * 4)),
+                            ldg4(a.H + (size_t)t * a.ldh + a.hj_v + lane * 4));
+    // accumulators stay packed (two fp32 per 64-bit register pair) through the 20-term loop: FFMA2 halves the issue count
+    unsigned long long acc[8] = {0ull, 0ull, 0ull, 0ull, pk2(p0.x, p0.y), pk2(p0.z, p0.w), pk2(p1.x, p1.y), pk2(p1.z, p1.w)};
 #pragma unroll
     for (int gg = 0; gg < 20; gg++) {
         const float sg = __shfl_sync(PG_FULL, mine, gg);
-        r0 = f4fma(sg, ldg4(a.wrji + gg * 256 + lane * 4), r0);
-        r1 = f4fma(sg, ldg4(a.wrji + gg * 256 + 128 + lane * 4), r1);
-        p0 = f4fma(sg, ldg4(a.wrkj + gg * 256 + lane * 4), p0);
-        p1 = f4fma(sg, ldg4(a.wrkj + gg * 256 + 128 + lane * 4), p1);
+        const unsigned long long ss = pk2(sg, sg);
+        const float4 w0 = ldg4(a.wrji + gg * 256 + lane * 4), w1 = ldg4(a.wrji + gg * 256 + 128 + lane * 4);
+        const float4 w2 = ldg4(a.wrkj + gg * 256 + lane * 4), w3 = ldg4(a.wrkj + gg * 256 + 128 + lane * 4);
+        acc[0] = fma2_raw(ss, pk2(w0.x, w0.y), acc[0]); acc[1] = fma2_raw(ss, pk2(w0.z, w0.w), acc[1]);
+        acc[2] = fma2_raw(ss, pk2(w1.x, w1.y), acc[2]); acc[3] = fma2_raw(ss, pk2(w1.z, w1.w), acc[3]);
+        acc[4] = fma2_raw(ss, pk2(w2.x, w2.y), acc[4]); acc[5] = fma2_raw(ss, pk2(w2.z, w2.w), acc[5]);
+        acc[6] = fma2_raw(ss, pk2(w3.x, w3.y), acc[6]); acc[7] = fma2_raw(ss, pk2(w3.z, w3.w), acc[7]);
     }
-    st4(a.R + (size_t)e * 256 + lane * 4, r0);
-    st4(a.R + (size_t)e * 256 + 128 + lane * 4, r1);
-    st4(a.P + (size_t)e * 256 + lane * 4, p0);
-    st4(a.P + (size_t)e * 256 + 128 + lane * 4, p1);
+    auto f4 = [](unsigned long long lo, unsigned long long hi) { const float2 x = up2(lo), y = up2(hi); return make_float4(x.x, x.y, y.x, y.y); };
+    st4(a.R + (size_t)e * 256 + lane * 4, f4(acc[0], acc[1]));
+    st4(a.R + (size_t)e * 256 + 128 + lane * 4, f4(acc[2], acc[3]));
+    st4(a.P + (size_t)e * 256 + lane * 4, f4(acc[4], acc[5]));
+    st4(a.P + (size_t)e * 256 + 128 + lane * 4, f4(acc[6], acc[7]));
 }
 }  // namespace
 
