@@ -134,6 +134,16 @@ int pg_position_step(int rows, const float* d_x_t, const float* d_x_recon, const
 int pg_guidance_grad(const PgPlan* p, const float* d_pos, const int32_t* d_edge_cls, int flags, float min_d,
                      float max_d, const float* d_phore_center, float* d_grad, void* stream);
 
+/* ---------------------------------------------------------------- M1 building block: K = 128 contraction
+ * C[M, 128*ntiles128] = pro(A)[M,128] @ W + bias (+ resid): the Linear layers of models/common.py:99-119 after the
+ * factorisation of DESIGN.md §3.  prologue 0: A ; 1: A + A2 ; 2: ReLU(LayerNorm(A + A2[gather])) (A2 / gather optional).
+ * impl 0 = tcgen05 bf16x3 kernel (d_w_bf16_tiles: pre-swizzled bf16 hi/lo images, weights.bf16_tiles64),
+ * impl 1 = fp32 FFMA reference kernel (d_wt: fp32 [128][128*ntiles128], k-major). */
+int pg_gemm_k128(int impl, int prologue, int64_t M, const float* d_a, int64_t lda, const float* d_a2, int64_t lda2,
+                 const int32_t* d_gather, const float* d_ln_g, const float* d_ln_b, const float* d_wt,
+                 const float* d_w_bf16_tiles, const float* d_bias, const float* d_resid, int64_t ldr, float* d_c, int64_t ldc,
+                 int ntiles128, void* stream);
+
 /* plan accessors used by the host mirror */
 const int32_t* pg_plan_ligand_graph(const PgPlan* p);   /* device [Nl]  atom -> graph */
 const int32_t* pg_plan_edge_graph(const PgPlan* p);     /* device [E_b] reference-order edge -> graph */

@@ -110,6 +110,37 @@ def knn_graph(x, k, batch):
     return torch.from_numpy(np.stack([np.concatenate(src_all), np.concatenate(dst_all)]).astype(np.int64))
 
 
+def knn_margin(x, k, batch):
+    """Conditioning of the kNN selection: min over query nodes of d_(k+1) - d_(k) (squared distances, self excluded)
+    for graphs with more than k candidates.  The kNN graph is a discontinuous function of the coordinates: an
+    implementation whose coordinates differ by ~1e-5 can legitimately pick a different neighbour when this margin is
+    that small, so parity fixtures are generated with a comfortable margin and tests report it."""
+    xn = x.detach().cpu().numpy().astype(np.float64)
+    bn = batch.detach().cpu().numpy()
+    best = np.inf
+    for g in np.unique(bn):
+        pts = xn[bn == g]
+        if pts.shape[0] - 1 <= k:
+            continue
+        d = ((pts[:, None, :] - pts[None, :, :]) ** 2).sum(-1)
+        np.fill_diagonal(d, np.inf)
+        ds = np.sort(d, axis=1)
+        best = min(best, float((ds[:, k] - ds[:, k - 1]).min()))
+    return best
+
+
+def forward_knn_margin(stages):
+    """Smallest kNN selection margin met during one phorediff_forward (stages collected by it): the k=32 graph on the
+    input coordinates and the k=3 ligand graph on every layer's input coordinates."""
+    ctx = stages[0]
+    mask, batch = ctx["mask_ligand"], ctx["batch_all"]
+    xs = [ctx["pos_all"]] + [st["x"] for st in stages[2:]]
+    m = knn_margin(xs[0], 32, batch)
+    for x in xs[:-1]:
+        m = min(m, knn_margin(x[mask], 3, batch[mask]))
+    return m
+
+
 def make_edge_data(num_atoms):
     """utils/sample_utils.py:40-54 — sampling edge order: per molecule the upper-triangular
     pairs (a<b) row-major as (src=a,dst=b), followed by the flipped copies."""

@@ -278,7 +278,9 @@ int gemm(PgPlan* p, cudaStream_t s, int pro, long long M, const float* A, long l
     a.resid = resid; a.ldr = ldr; a.relu = 0;
     p->launches++;
     PgTimed timed(p, KC_GEMM, s);
-    return use_simt_gemm() ? pg_launch_gemm(a, pro, s) : pg_launch_gemm_tc(a, pro, s);
+    static const char* only = getenv("PG_GEMM_SIMT_ONLY");      // debug: fp32 kernel for weights whose slot name contains this substring
+    const bool simt = use_simt_gemm() || (only && strstr(wname.c_str(), only));
+    return simt ? pg_launch_gemm(a, pro, s) : pg_launch_gemm_tc(a, pro, s);
 }
 
 AttnW attn_w(const W& w, const std::string& S, bool tabs) {
@@ -458,4 +460,19 @@ extern "C" int pg_phorediff_forward(const PgModel* m, PgPlan* p, const float* d_
                                                                                    d_logits_edge, nullptr, nullptr);
     PG_LAUNCH_CHECK(); p->launches++;
     return PG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ stand-alone contraction
+// C[M, 128*ntiles128] = pro(A)[M,128] @ W + bias (+ resid), the building block of every first / second Linear here.
+// impl 0: tcgen05 bf16x3 kernel (needs d_w_bf16_tiles = weights.bf16_tiles64 image), impl 1: fp32 FFMA kernel (needs d_wt).
+extern "C" int pg_gemm_k128(int impl, int prologue, int64_t M, const float* d_a, int64_t lda, const float* d_a2, int64_t lda2,
+                            const int32_t* d_gather, const float* d_ln_g, const float* d_ln_b, const float* d_wt,
+                            const float* d_w_bf16_tiles, const float* d_bias, const float* d_resid, int64_t ldr, float* d_c,
+                            int64_t ldc, int ntiles128, void* stream) {
+    if (prologue < 0 || prologue > 2 || ntiles128 <= 0) { pg_set_error("pg_gemm_k128: bad argument"); return PG_EINVAL; }
+    GemmArgs a;
+    a.M = M; a.A = d_a; a.lda = lda; a.A2 = d_a2; a.lda2 = lda2; a.gidx = d_gather; a.ln_g = d_ln_g; a.ln_b = d_ln_b;
+    a.Wt = d_wt; a.Wbf = d_w_bf16_tiles; a.ldw = 128LL * ntiles128; a.bias = d_bias; a.C = d_c; a.ldc = ldc; a.ntiles = ntiles128;
+    a.resid = d_resid; a.ldr = ldr; a.relu = 0;
+    return impl == 1 ? pg_launch_gemm(a, prologue, (cudaStream_t)stream) : pg_launch_gemm_tc(a, prologue, (cudaStream_t)stream);
 }
