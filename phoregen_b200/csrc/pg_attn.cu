@@ -96,6 +96,33 @@ __device__ __forceinline__ void value_out_transform(const float4 (&s)[16], const
     }
 }
 
+// first-Linear contribution of the 24 edge features of two rows; when both rows have the same edge type the four
+// 20x128 slices are read once for the pair (halves the L1 traffic of this table, the kernel's busiest data path)
+__device__ __forceinline__ void edge_feature_pair(const float* __restrict__ tab, int t0, int t1, const float* f0, const float* f1,
+                                                  int lane, float4& p0, float4& p1) {
+    const float* tb0 = tab + (size_t)t0 * (24 * 128) + lane * 4;
+    if (t0 == t1) {
+#pragma unroll
+        for (int f4 = 0; f4 < 6; f4++) {
+            const float4 a = ld4(f0 + f4 * 4), b = ld4(f1 + f4 * 4);
+            float4 w = ldg4(tb0 + (f4 * 4 + 0) * 128); p0 = f4fma(a.x, w, p0); p1 = f4fma(b.x, w, p1);
+            w = ldg4(tb0 + (f4 * 4 + 1) * 128); p0 = f4fma(a.y, w, p0); p1 = f4fma(b.y, w, p1);
+            w = ldg4(tb0 + (f4 * 4 + 2) * 128); p0 = f4fma(a.z, w, p0); p1 = f4fma(b.z, w, p1);
+            w = ldg4(tb0 + (f4 * 4 + 3) * 128); p0 = f4fma(a.w, w, p0); p1 = f4fma(b.w, w, p1);
+        }
+    } else {
+        const float* tb1 = tab + (size_t)t1 * (24 * 128) + lane * 4;
+#pragma unroll
+        for (int f4 = 0; f4 < 6; f4++) {
+            const float4 a = ld4(f0 + f4 * 4), b = ld4(f1 + f4 * 4);
+            p0 = f4fma(a.x, ldg4(tb0 + (f4 * 4 + 0) * 128), p0); p1 = f4fma(b.x, ldg4(tb1 + (f4 * 4 + 0) * 128), p1);
+            p0 = f4fma(a.y, ldg4(tb0 + (f4 * 4 + 1) * 128), p0); p1 = f4fma(b.y, ldg4(tb1 + (f4 * 4 + 1) * 128), p1);
+            p0 = f4fma(a.z, ldg4(tb0 + (f4 * 4 + 2) * 128), p0); p1 = f4fma(b.z, ldg4(tb1 + (f4 * 4 + 2) * 128), p1);
+            p0 = f4fma(a.w, ldg4(tb0 + (f4 * 4 + 3) * 128), p0); p1 = f4fma(b.w, ldg4(tb1 + (f4 * 4 + 3) * 128), p1);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ kNN / phore
 // FEAT 0: joint ligand+pharmacophore kNN graph (NodeUpdateLayer / PosUpdateLayer with edge features,
 //         uni_denoiser.py:264-281,291).  FEAT 1: pharmacophore encoder (p^2 edges incl. self loops, feature =
@@ -110,7 +137,7 @@ __global__ void __launch_bounds__(128) knn_attn_kernel(KnnAttnArgs a) {
     if (v >= nrows) return;
     constexpr int FW = FEAT == 0 ? 24 : 4;
     const int maxr = a.maxr;
-    const int per_warp = 128 + maxr * 16 + maxr * FW + maxr * 4 + maxr + maxr + maxr + 16;
+    const int per_warp = 128 + maxr * 16 + maxr * FW + maxr * 4 + maxr + maxr + maxr + maxr + 16;
     float* qs = sm + (size_t)warp * per_warp;
     float* lg = qs + 128;
     float* feat = lg + maxr * 16;
@@ -118,7 +145,8 @@ __global__ void __launch_bounds__(128) knn_attn_kernel(KnnAttnArgs a) {
     float* ewr = rel + maxr * 4;
     int* srcs = (int*)(ewr + maxr);
     int* typ = srcs + maxr;
-    float* swv = (float*)(typ + maxr);
+    int* ord = typ + maxr;           // rows regrouped by edge type so that two rows can share one pass over the feature table
+    float* swv = (float*)(ord + maxr);
 
     int R, src0 = 0;
     long long e0 = 0;
@@ -156,6 +184,17 @@ __global__ void __launch_bounds__(128) knn_attn_kernel(KnnAttnArgs a) {
             feat[r * FW] = dist;
         }
     }
+    if (FEAT == 0) {      // R <= 32: lane = row.  Stable partition of the rows by edge type (4 ballots).
+        const int myt = lane < R ? typ[lane] : 4;
+        int pos = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const unsigned m = __ballot_sync(PG_FULL, myt == t);
+            if (myt == t) pos += __popc(m & ((1u << lane) - 1));
+            else if (myt > t) pos += __popc(m);
+        }
+        if (lane < R) ord[pos] = lane;
+    }
     __syncwarp();
 
     // ---- pass 1: keys -> logits
@@ -167,22 +206,21 @@ __global__ void __launch_bounds__(128) knn_attn_kernel(KnnAttnArgs a) {
         const float4 gk = ldg4(a.w.lnk_g + lane * 4), bk = ldg4(a.w.lnk_b + lane * 4);
         float4 wd = make_float4(0, 0, 0, 0);
         if (FEAT == 1) wd = ldg4(a.w.tab_k + lane * 4);
-        for (int r = 0; r < R; r++) {
-            float4 pre = f4add(base, ldg4(a.nc.A + (size_t)srcs[r] * a.nc.lda + a.nc.src_k + lane * 4));
-            if (FEAT == 0) {
-                const float* tb = a.w.tab_k + (size_t)typ[r] * (24 * 128) + lane * 4;
-#pragma unroll
-                for (int f4 = 0; f4 < 6; f4++) {
-                    const float4 fv = ld4(feat + r * FW + f4 * 4);
-                    pre = f4fma(fv.x, ldg4(tb + (f4 * 4 + 0) * 128), pre);
-                    pre = f4fma(fv.y, ldg4(tb + (f4 * 4 + 1) * 128), pre);
-                    pre = f4fma(fv.z, ldg4(tb + (f4 * 4 + 2) * 128), pre);
-                    pre = f4fma(fv.w, ldg4(tb + (f4 * 4 + 3) * 128), pre);
-                }
-            } else {
-                pre = f4fma(feat[r * FW], wd, pre);
+        if (FEAT == 0) {
+            for (int i = 0; i < R; i += 2) {
+                const int r0 = ord[i], r1 = ord[min(i + 1, R - 1)];
+                float4 p0 = f4add(base, ldg4(a.nc.A + (size_t)srcs[r0] * a.nc.lda + a.nc.src_k + lane * 4));
+                float4 p1 = f4add(base, ldg4(a.nc.A + (size_t)srcs[r1] * a.nc.lda + a.nc.src_k + lane * 4));
+                edge_feature_pair(a.w.tab_k, typ[r0], typ[r1], feat + r0 * FW, feat + r1 * FW, lane, p0, p1);
+                store_logits(ln_relu_row(p0, gk, bk), qt, lb, lg + r0 * 16, lane);
+                if (i + 1 < R) store_logits(ln_relu_row(p1, gk, bk), qt, lb, lg + r1 * 16, lane);
             }
-            store_logits(ln_relu_row(pre, gk, bk), qt, lb, lg + r * 16, lane);
+        } else {
+            for (int r = 0; r < R; r++) {
+                float4 pre = f4add(base, ldg4(a.nc.A + (size_t)srcs[r] * a.nc.lda + a.nc.src_k + lane * 4));
+                pre = f4fma(feat[r * FW], wd, pre);
+                store_logits(ln_relu_row(pre, gk, bk), qt, lb, lg + r * 16, lane);
+            }
         }
     }
     __syncwarp();
@@ -194,36 +232,38 @@ __global__ void __launch_bounds__(128) knn_attn_kernel(KnnAttnArgs a) {
     const float4 gv = ldg4(a.w.lnv_g + lane * 4), bv = ldg4(a.w.lnv_b + lane * 4);
     float4 wd = make_float4(0, 0, 0, 0);
     if (FEAT == 1) wd = ldg4(a.w.tab_v + lane * 4);
-    auto value_hidden = [&](int r) {
-        float4 pre = f4add(base, ldg4(a.nc.A + (size_t)srcs[r] * a.nc.lda + a.nc.src_v + lane * 4));
+    // value-MLP hidden rows of a pair of rows (same pass over the feature table when both have the same edge type)
+    auto value_hidden_pair = [&](int r0, int r1, float4& h0, float4& h1) {
+        float4 p0 = f4add(base, ldg4(a.nc.A + (size_t)srcs[r0] * a.nc.lda + a.nc.src_v + lane * 4));
+        float4 p1 = f4add(base, ldg4(a.nc.A + (size_t)srcs[r1] * a.nc.lda + a.nc.src_v + lane * 4));
         if (FEAT == 0) {
-            const float* tb = a.w.tab_v + (size_t)typ[r] * (24 * 128) + lane * 4;
-#pragma unroll
-            for (int f4 = 0; f4 < 6; f4++) {
-                const float4 fv = ld4(feat + r * FW + f4 * 4);
-                pre = f4fma(fv.x, ldg4(tb + (f4 * 4 + 0) * 128), pre);
-                pre = f4fma(fv.y, ldg4(tb + (f4 * 4 + 1) * 128), pre);
-                pre = f4fma(fv.z, ldg4(tb + (f4 * 4 + 2) * 128), pre);
-                pre = f4fma(fv.w, ldg4(tb + (f4 * 4 + 3) * 128), pre);
-            }
+            edge_feature_pair(a.w.tab_v, typ[r0], typ[r1], feat + r0 * FW, feat + r1 * FW, lane, p0, p1);
         } else {
-            pre = f4fma(feat[r * FW], wd, pre);
+            p0 = f4fma(feat[r0 * FW], wd, p0);
+            p1 = f4fma(feat[r1 * FW], wd, p1);
         }
-        return ln_relu_row(pre, gv, bv);
+        h0 = ln_relu_row(p0, gv, bv);
+        h1 = ln_relu_row(p1, gv, bv);
     };
+    auto row_at = [&](int i) { return FEAT == 0 ? ord[i] : i; };
     if (POS == 0) {
         float4 s[16];
 #pragma unroll
         for (int h = 0; h < 16; h++) s[h] = make_float4(0, 0, 0, 0);
-        for (int r = 0; r < R; r++) {
-            const float4 hid = value_hidden(r);
+        for (int i = 0; i < R; i += 2) {
+            const int r0 = row_at(i), r1 = row_at(min(i + 1, R - 1));
+            float4 hid0, hid1;
+            value_hidden_pair(r0, r1, hid0, hid1);
+            const float w1 = (i + 1 < R) ? 1.f : 0.f;
 #pragma unroll
             for (int h4 = 0; h4 < 4; h4++) {
-                const float4 al = ld4(lg + r * 16 + h4 * 4);
-                s[h4 * 4 + 0] = f4fma(al.x, hid, s[h4 * 4 + 0]);
-                s[h4 * 4 + 1] = f4fma(al.y, hid, s[h4 * 4 + 1]);
-                s[h4 * 4 + 2] = f4fma(al.z, hid, s[h4 * 4 + 2]);
-                s[h4 * 4 + 3] = f4fma(al.w, hid, s[h4 * 4 + 3]);
+                const float4 al = ld4(lg + r0 * 16 + h4 * 4);
+                float4 bl = ld4(lg + r1 * 16 + h4 * 4);
+                bl = make_float4(bl.x * w1, bl.y * w1, bl.z * w1, bl.w * w1);
+                s[h4 * 4 + 0] = f4fma(bl.x, hid1, f4fma(al.x, hid0, s[h4 * 4 + 0]));
+                s[h4 * 4 + 1] = f4fma(bl.y, hid1, f4fma(al.y, hid0, s[h4 * 4 + 1]));
+                s[h4 * 4 + 2] = f4fma(bl.z, hid1, f4fma(al.z, hid0, s[h4 * 4 + 2]));
+                s[h4 * 4 + 3] = f4fma(bl.w, hid1, f4fma(al.w, hid0, s[h4 * 4 + 3]));
             }
         }
         float* orow = a.out + (size_t)v * 128;
@@ -235,14 +275,22 @@ __global__ void __launch_bounds__(128) knn_attn_kernel(KnnAttnArgs a) {
         const int hh = (lane >> 1) & 15;
         const float b2 = __ldg(a.w.b2v + hh);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-        for (int r = 0; r < R; r++) {
-            const float4 hid = value_hidden(r);
-            float p[16];
+        for (int i = 0; i < R; i += 2) {
+            const int r0 = row_at(i), r1 = row_at(min(i + 1, R - 1));
+            float4 hid0, hid1;
+            value_hidden_pair(r0, r1, hid0, hid1);
+            float p[16], pb[16];
 #pragma unroll
-            for (int h = 0; h < 16; h++) p[h] = f4dot(hid, xv[h]);
-            float c = (transpose_reduce16(p, lane) + b2) * lg[r * 16 + hh];   // alpha (already times e_w) * v_h
-            c = warp_sum((lane & 1) ? 0.f : c);
-            a0 = fmaf(c, rel[r * 4], a0); a1 = fmaf(c, rel[r * 4 + 1], a1); a2 = fmaf(c, rel[r * 4 + 2], a2);
+            for (int h = 0; h < 16; h++) { p[h] = f4dot(hid0, xv[h]); pb[h] = f4dot(hid1, xv[h]); }
+            float c0 = (transpose_reduce16(p, lane) + b2) * lg[r0 * 16 + hh];   // alpha (already times e_w) * v_h
+            float c1 = (transpose_reduce16(pb, lane) + b2) * lg[r1 * 16 + hh];
+            c0 = (lane & 1) ? 0.f : c0;
+            c1 = ((lane & 1) || i + 1 >= R) ? 0.f : c1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { c0 += __shfl_xor_sync(PG_FULL, c0, o); c1 += __shfl_xor_sync(PG_FULL, c1, o); }
+            a0 = fmaf(c1, rel[r1 * 4], fmaf(c0, rel[r0 * 4], a0));
+            a1 = fmaf(c1, rel[r1 * 4 + 1], fmaf(c0, rel[r0 * 4 + 1], a1));
+            a2 = fmaf(c1, rel[r1 * 4 + 2], fmaf(c0, rel[r0 * 4 + 2], a2));
         }
         if (lane == 0) {
             a.out[(size_t)v * 3] = a0 * (1.0f / 16.0f);
@@ -508,7 +556,7 @@ int pg_launch_knn_attn(const KnnAttnArgs& a, int feat, int pos, cudaStream_t s) 
     const int rows = feat == 0 ? a.d.N : a.d.P;
     if (rows <= 0) return PG_OK;
     const int FW = feat == 0 ? 24 : 4;
-    const size_t smem = (size_t)4 * (128 + a.maxr * 16 + a.maxr * FW + a.maxr * 4 + a.maxr * 3 + 16) * sizeof(float);
+    const size_t smem = (size_t)4 * (128 + a.maxr * 16 + a.maxr * FW + a.maxr * 4 + a.maxr * 4 + 16) * sizeof(float);
     const unsigned grid = (unsigned)((rows + 3) / 4);
     if (smem > 200 * 1024) { pg_set_error("knn_attn: segment too long (%d rows)", a.maxr); return PG_ELIMIT; }
 #define PG_KA(F, P)                                                                                                   \

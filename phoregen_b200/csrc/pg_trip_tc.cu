@@ -444,44 +444,62 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
 //   P[e] = h_bond[e] Wb (edge GEMM output T) + h_src Whk + h_dst Whj + b1 + smear(|x_dst - x_src|) Wrkj   (edge in the k->j role)
 //   R[e] = smear(|x_dst - x_src|) Wrji                                                                    (edge in the j->i role)
 // Both k|v halves (256 channels).  P rows of the edges into one atom are contiguous -> one bulk copy per unit.
-__global__ void __launch_bounds__(256, 4) trip_pr_kernel(TripTcArgs a) {
+constexpr int PR_EDGES = 4;      // edges per warp: every weight row read from L1 is used for 4 edges
+__global__ void __launch_bounds__(256, 2) trip_pr_kernel(TripTcArgs a) {
     const PlanDev& d = a.d;
     const int lane = threadIdx.x & 31;
-    const long long e = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (e >= d.Eb) return;
-    const int s = d.esrc_node[e], t = d.edst_node[e];
-    const float d0 = a.x[(size_t)t * 3] - a.x[(size_t)s * 3], d1 = a.x[(size_t)t * 3 + 1] - a.x[(size_t)s * 3 + 1],
-                d2 = a.x[(size_t)t * 3 + 2] - a.x[(size_t)s * 3 + 2];
-    const float dist = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
-    const float mine = lane < 20 ? smear_val(dist, lane) : 0.f;
-    const float4 p0 = f4add(f4add(ldg4(a.T + (size_t)e * a.ldt + a.t_k + lane * 4), ldg4(a.H + (size_t)s * a.ldh + a.hk_k + lane * 4)),
-                            ldg4(a.H + (size_t)t * a.ldh + a.hj_k + lane * 4));
-    const float4 p1 = f4add(f4add(ldg4(a.T + (size_t)e * a.ldt + a.t_v + lane * 4), ldg4(a.H + (size_t)s * a.ldh + a.hk_v + lane * 4)),
-                            ldg4(a.H + (size_t)t * a.ldh + a.hj_v + lane * 4));
-    // accumulators stay packed (two fp32 per 64-bit register pair) through the 20-term loop: FFMA2 halves the issue count
-    unsigned long long acc[8] = {0ull, 0ull, 0ull, 0ull, pk2(p0.x, p0.y), pk2(p0.z, p0.w), pk2(p1.x, p1.y), pk2(p1.z, p1.w)};
+    const long long e0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * PR_EDGES;
+    if (e0 >= d.Eb) return;
+    float mine[PR_EDGES];
+    unsigned long long acc[PR_EDGES][8];
 #pragma unroll
+    for (int k = 0; k < PR_EDGES; k++) {
+        const long long e = min(e0 + k, d.Eb - 1);
+        const int s = d.esrc_node[e], t = d.edst_node[e];
+        const float d0 = a.x[(size_t)t * 3] - a.x[(size_t)s * 3], d1 = a.x[(size_t)t * 3 + 1] - a.x[(size_t)s * 3 + 1],
+                    d2 = a.x[(size_t)t * 3 + 2] - a.x[(size_t)s * 3 + 2];
+        const float dist = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+        mine[k] = lane < 20 ? smear_val(dist, lane) : 0.f;
+        const float4 p0 = f4add(f4add(ldg4(a.T + (size_t)e * a.ldt + a.t_k + lane * 4), ldg4(a.H + (size_t)s * a.ldh + a.hk_k + lane * 4)),
+                                ldg4(a.H + (size_t)t * a.ldh + a.hj_k + lane * 4));
+        const float4 p1 = f4add(f4add(ldg4(a.T + (size_t)e * a.ldt + a.t_v + lane * 4), ldg4(a.H + (size_t)s * a.ldh + a.hk_v + lane * 4)),
+                                ldg4(a.H + (size_t)t * a.ldh + a.hj_v + lane * 4));
+        acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0ull;
+        acc[k][4] = pk2(p0.x, p0.y); acc[k][5] = pk2(p0.z, p0.w); acc[k][6] = pk2(p1.x, p1.y); acc[k][7] = pk2(p1.z, p1.w);
+    }
+    // accumulators stay packed (two fp32 per 64-bit register pair) through the 20-term loop (FFMA2)
+#pragma unroll 2
     for (int gg = 0; gg < 20; gg++) {
-        const float sg = __shfl_sync(PG_FULL, mine, gg);
-        const unsigned long long ss = pk2(sg, sg);
         const float4 w0 = ldg4(a.wrji + gg * 256 + lane * 4), w1 = ldg4(a.wrji + gg * 256 + 128 + lane * 4);
         const float4 w2 = ldg4(a.wrkj + gg * 256 + lane * 4), w3 = ldg4(a.wrkj + gg * 256 + 128 + lane * 4);
-        acc[0] = fma2_raw(ss, pk2(w0.x, w0.y), acc[0]); acc[1] = fma2_raw(ss, pk2(w0.z, w0.w), acc[1]);
-        acc[2] = fma2_raw(ss, pk2(w1.x, w1.y), acc[2]); acc[3] = fma2_raw(ss, pk2(w1.z, w1.w), acc[3]);
-        acc[4] = fma2_raw(ss, pk2(w2.x, w2.y), acc[4]); acc[5] = fma2_raw(ss, pk2(w2.z, w2.w), acc[5]);
-        acc[6] = fma2_raw(ss, pk2(w3.x, w3.y), acc[6]); acc[7] = fma2_raw(ss, pk2(w3.z, w3.w), acc[7]);
+        const unsigned long long u0 = pk2(w0.x, w0.y), u1 = pk2(w0.z, w0.w), u2 = pk2(w1.x, w1.y), u3 = pk2(w1.z, w1.w);
+        const unsigned long long u4 = pk2(w2.x, w2.y), u5 = pk2(w2.z, w2.w), u6 = pk2(w3.x, w3.y), u7 = pk2(w3.z, w3.w);
+#pragma unroll
+        for (int k = 0; k < PR_EDGES; k++) {
+            const float sg = __shfl_sync(PG_FULL, mine[k], gg);
+            const unsigned long long ss = pk2(sg, sg);
+            acc[k][0] = fma2_raw(ss, u0, acc[k][0]); acc[k][1] = fma2_raw(ss, u1, acc[k][1]);
+            acc[k][2] = fma2_raw(ss, u2, acc[k][2]); acc[k][3] = fma2_raw(ss, u3, acc[k][3]);
+            acc[k][4] = fma2_raw(ss, u4, acc[k][4]); acc[k][5] = fma2_raw(ss, u5, acc[k][5]);
+            acc[k][6] = fma2_raw(ss, u6, acc[k][6]); acc[k][7] = fma2_raw(ss, u7, acc[k][7]);
+        }
     }
     auto f4 = [](unsigned long long lo, unsigned long long hi) { const float2 x = up2(lo), y = up2(hi); return make_float4(x.x, x.y, y.x, y.y); };
-    st4(a.R + (size_t)e * 256 + lane * 4, f4(acc[0], acc[1]));
-    st4(a.R + (size_t)e * 256 + 128 + lane * 4, f4(acc[2], acc[3]));
-    st4(a.P + (size_t)e * 256 + lane * 4, f4(acc[4], acc[5]));
-    st4(a.P + (size_t)e * 256 + 128 + lane * 4, f4(acc[6], acc[7]));
+#pragma unroll
+    for (int k = 0; k < PR_EDGES; k++) {
+        const long long e = e0 + k;
+        if (e >= d.Eb) break;
+        st4(a.R + (size_t)e * 256 + lane * 4, f4(acc[k][0], acc[k][1]));
+        st4(a.R + (size_t)e * 256 + 128 + lane * 4, f4(acc[k][2], acc[k][3]));
+        st4(a.P + (size_t)e * 256 + lane * 4, f4(acc[k][4], acc[k][5]));
+        st4(a.P + (size_t)e * 256 + 128 + lane * 4, f4(acc[k][6], acc[k][7]));
+    }
 }
 }  // namespace
 
 int pg_launch_trip_pr(const TripTcArgs& a, cudaStream_t s) {
     if (a.d.Eb <= 0) return PG_OK;
-    trip_pr_kernel<<<(unsigned)((a.d.Eb + 7) / 8), 256, 0, s>>>(a);
+    trip_pr_kernel<<<(unsigned)((a.d.Eb + 8 * PR_EDGES - 1) / (8 * PR_EDGES)), 256, 0, s>>>(a);
     PG_LAUNCH_CHECK();
     return PG_OK;
 }
