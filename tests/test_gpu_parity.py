@@ -358,3 +358,64 @@ def test_sampler_statistics_of_philox_draws(model, dev):
     xp = plan.position_step(pm, z, z, t5, seed=7, step_counter=ctr)
     sd_ = float(pm.tables["pos_transition.std"][500])
     assert abs(float(xp.std()) / sd_ - 1.0) < 0.05 and abs(float(xp.mean())) < 0.05 * sd_
+
+
+def test_sample_with_guidance_and_atom_count_head(model, dev):
+    """The reference's sample() entry (diffusion.py:390-525) with its optional pieces: atom-count head
+    (sample_nodes), validity guidance (atom_prox + center_prox, sample.sh:21), exclusion-volume nodes."""
+    from phoregen_b200.testing import PhoreData
+    m, _ = model
+    rng = np.random.default_rng(5)
+    x, pos, nrm = O.synthetic_phore(rng, 6, n_ex=40)
+    data = PhoreData(torch.from_numpy(x), torch.from_numpy(pos), torch.from_numpy(nrm), center=torch.tensor([-3.0, 0.5, 2.0]))
+    opts = [dict(type="atom_prox", min_d=1.2, max_d=1.9), dict(type="center_prox")]
+    torch.manual_seed(0)
+    res = m.sample(data, 3, dev, pos_guidance_opt=opts, seed=11, num_steps=3)
+    n_atoms = res["lig_info"][0]
+    assert n_atoms.shape == (3,) and int(n_atoms.min()) >= 4 and int(n_atoms.max()) <= 78
+    Nl = int(n_atoms.sum())
+    assert res["pred"][0].shape == (Nl, 12) and res["pred"][1].shape == (Nl, 3)
+    assert all(bool(torch.isfinite(t).all()) for t in res["pred"])
+    # guidance changes the position update and only that
+    res0 = m.sample(data, 3, dev, ligand_num_atoms=n_atoms, seed=11, num_steps=1)
+    res1 = m.sample(data, 3, dev, ligand_num_atoms=n_atoms, pos_guidance_opt=opts, seed=11, num_steps=1)
+    assert torch.equal(res0["traj"][0][:2], res1["traj"][0][:2]) and torch.equal(res0["traj"][2][:2], res1["traj"][2][:2])
+    assert not torch.equal(res0["traj"][1][1], res1["traj"][1][1])
+    # eager and graph replay agree with guidance on
+    r_e = m.sample(data, 3, dev, ligand_num_atoms=n_atoms, pos_guidance_opt=opts, seed=11, num_steps=3, use_cuda_graph=False)
+    r_g = m.sample(data, 3, dev, ligand_num_atoms=n_atoms, pos_guidance_opt=opts, seed=11, num_steps=3, use_cuda_graph=True)
+    for a_, b_ in zip(r_e["traj"], r_g["traj"]):
+        assert torch.equal(a_, b_)
+
+
+def test_tcgen05_gemm_matches_fp32_kernel_and_fp64(dev):
+    """pg_gemm_k128: the bf16x3 tensor-core contraction against the fp32 FFMA kernel and an fp64 reference, for ragged
+    M, many column blocks and every fused prologue."""
+    import ctypes
+    from phoregen_b200._lib import check, lib
+    from phoregen_b200.weights import bf16_tiles64
+    rng = np.random.default_rng(0)
+    P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for M, nt, pro in ((1, 1, 0), (53, 15, 2), (129, 2, 1), (40000, 5, 2), (20000, 10, 0)):
+        N = 128 * nt
+        A = torch.from_numpy(rng.normal(size=(M, 192)).astype(np.float32)).to(dev)
+        A2 = torch.from_numpy(rng.normal(size=(max(M, 64), 128)).astype(np.float32)).to(dev)
+        gidx = torch.from_numpy(rng.integers(0, A2.shape[0], size=M).astype(np.int32)).to(dev)
+        g = torch.from_numpy(rng.normal(size=128).astype(np.float32)).to(dev)
+        b = torch.from_numpy(rng.normal(size=128).astype(np.float32)).to(dev)
+        Wt = rng.normal(size=(128, N)).astype(np.float32) / 11
+        bias = torch.from_numpy(rng.normal(size=N).astype(np.float32)).to(dev)
+        Wt_d, Wbf = torch.from_numpy(Wt).to(dev), torch.from_numpy(bf16_tiles64(Wt)).to(dev)
+        x = A[:, :128].double()
+        if pro == 1:
+            x = x + A2[:M].double()
+        if pro == 2:
+            x = torch.relu(F.layer_norm(x + A2[gidx.long()].double(), (128,), g.double(), b.double(), 1e-5))
+        want = x @ Wt_d.double() + bias.double()
+        for impl, tol in ((0, 3e-4), (1, 2e-5)):
+            C = torch.full((M, N), float("nan"), device=dev)
+            check(lib.pg_gemm_k128(impl, pro, M, P(A), 192, P(A2) if pro else None, 128, P(gidx) if pro == 2 else None, P(g), P(b),
+                                   P(Wt_d), P(Wbf), P(bias), None, 0, P(C), N, nt, st), "pg_gemm_k128")
+            err = float((C.double() - want).abs().max())
+            assert err < tol, f"impl {impl} M={M} N={N} pro={pro}: max err {err:.2e}"
