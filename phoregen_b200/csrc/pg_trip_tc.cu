@@ -84,7 +84,9 @@ __device__ __forceinline__ Seg seg_of(const TileIter& it, int wq) {
 
 // angular encoding of this thread's triplet row -> bf16 hi/lo A tile (common.py:67-87; uni_denoiser.py:131-135)
 // xs: coordinates of the molecule's ligand atoms, [n][4] floats (shared memory copy)
-__device__ __forceinline__ void write_features(const float* xs, const TileIter& it, int wq, int lane, uint8_t* sFeat) {
+// called by lanes 0-15 of the two warps of lane quadrant wq: `row` = row inside the segment (0..31)
+__device__ __forceinline__ void write_features(const float* xs, const TileIter& it, int wq, int row, uint8_t* sFeat) {
+    const int lane = row;
     const Seg sg = seg_of(it, wq);
     float f[16];
 #pragma unroll
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
 
     if (warp == 8) tc::tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
-        tc::mbar_init(&bars[B_FEAT], 128 + 32); tc::mbar_init(&bars[B_PRE], 1);
+        tc::mbar_init(&bars[B_FEAT], 256 + 32); tc::mbar_init(&bars[B_PRE], 1);
         tc::mbar_init(&bars[B_HIDK], 256); tc::mbar_init(&bars[B_HIDV], 256);
         tc::mbar_init(&bars[B_OUTK], 1); tc::mbar_init(&bars[B_OUTV], 1);
         tc::mbar_init(&bars[B_PS], 1); tc::mbar_init(&bars[B_FREE], 256);
@@ -280,12 +282,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             }
             asm volatile("bar.sync 2, 128;" ::: "memory");
         };
-        if (half == 1) {
-            stage_x(it, 0);
-            write_features(sX, it, wq, lane, sFeat);
-            tc::fence_proxy_async_smem();
-            tc::mbar_arrive(&bars[B_FEAT]);
-        }
+        if (half == 1) stage_x(it, 0);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (lane < 16) write_features(sX, it, wq, half * 16 + lane, sFeat);
+        tc::fence_proxy_async_smem();
+        tc::mbar_arrive(&bars[B_FEAT]);
         tc::mbar_arrive(&bars[B_FREE]);                 // TMEM starts free
         uint32_t ph = 0, psph = 0;
         int buf = 0, staged_u = -1;
@@ -363,11 +364,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             TRACE(role, 4);
             TileIter nx = it;
             iter_next(d, nx);
-            if (half == 1 && nx.valid) {
-                // ---- features of the NEXT tile while the tensor pipe works on this one
+            if (nx.valid) {
+                // ---- features of the NEXT tile while the tensor pipe works on this one (16 rows per warp)
                 const int nb = nx.u != it.u ? (xb ^ 1) : xb;
-                if (nx.u != it.u) stage_x(nx, nb);
-                write_features(sX + (size_t)nb * a.maxn * 4, nx, wq, lane, sFeat);
+                if (nx.u != it.u) {
+                    if (half == 1) stage_x(nx, nb);
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                }
+                if (lane < 16) write_features(sX + (size_t)nb * a.maxn * 4, nx, wq, half * 16 + lane, sFeat);
                 tc::fence_proxy_async_smem();
                 tc::mbar_arrive(&bars[B_FEAT]);
             }
@@ -416,12 +420,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             {
                 tc::mbar_wait(&bars[B_OUTV], ph);
                 tc::tc_fence_after();
+                uint32_t vu[64];
+                tc::tmem_ld32_nowait(tmem + lane_base + C_OUT + 128 + half * 64, vu);
+                tc::tmem_ld32_nowait(tmem + lane_base + C_OUT + 128 + half * 64 + 32, vu + 32);
+                tc::tmem_ld_wait();
 #pragma unroll
                 for (int ch = 0; ch < 2; ch++) {
                     float v[32];
-                    tc::tmem_ld32(tmem + lane_base + C_OUT + 128 + half * 64 + ch * 32, v);
 #pragma unroll
-                    for (int i = 0; i < 32; i++) v[i] = al[ch * 4 + (i >> 3)] * v[i];       // alpha is 0 on padded rows
+                    for (int i = 0; i < 32; i++) v[i] = al[ch * 4 + (i >> 3)] * __uint_as_float(vu[ch * 32 + i]);   // alpha is 0 on padded rows
                     const float o = transpose_reduce32(v, lane);
                     if (sg.valid) {
                         const int c = half * 64 + ch * 32 + lane;
