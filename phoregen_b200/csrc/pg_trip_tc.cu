@@ -84,7 +84,7 @@ __device__ __forceinline__ Seg seg_of(const TileIter& it, int wq) {
 
 // angular encoding of this thread's triplet row -> bf16 hi/lo A tile (common.py:67-87; uni_denoiser.py:131-135)
 // xs: coordinates of the molecule's ligand atoms, [n][4] floats (shared memory copy)
-// called by lanes 0-15 of the two warps of lane quadrant wq: `row` = row inside the segment (0..31)
+// `wq` = segment slot of the tile (0..3), `row` = row inside the segment (0..31)
 __device__ __forceinline__ void write_features(const float* xs, const TileIter& it, int wq, int row, uint8_t* sFeat) {
     const int lane = row;
     const Seg sg = seg_of(it, wq);
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
 
     if (warp == 8) tc::tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
-        tc::mbar_init(&bars[B_FEAT], 256 + 32); tc::mbar_init(&bars[B_PRE], 1);
+        tc::mbar_init(&bars[B_FEAT], 96 + 32); tc::mbar_init(&bars[B_PRE], 1);
         tc::mbar_init(&bars[B_HIDK], 256); tc::mbar_init(&bars[B_HIDV], 256);
         tc::mbar_init(&bars[B_OUTK], 1); tc::mbar_init(&bars[B_OUTV], 1);
         tc::mbar_init(&bars[B_PS], 1); tc::mbar_init(&bars[B_FREE], 256);
@@ -268,25 +268,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             if (nx.valid) { asm volatile("cp.async.wait_group 0;" ::: "memory"); tc::mbar_arrive(&bars[B_FEAT]); }
             it = nx; ph ^= 1; buf ^= 1; tcount++;
         }
+      } else {
+        // ================= warps 9-11: angular features of the NEXT tile (off every critical path) =================
+        // 96 threads cover the 128 rows of a tile in two passes; they also stage the next unit's coordinates.
+        const int ft = tid - 288;                       // 0..95
+        auto stage_x = [&](const TileIter& t, int b) {
+            for (int i = ft; i < t.n; i += 96) {
+                const float* src = a.x + (size_t)(t.ctx0 + i) * 3;
+                st4(sX + ((size_t)b * a.maxn + i) * 4, make_float4(src[0], src[1], src[2], 0.f));
+            }
+            asm volatile("bar.sync 2, 96;" ::: "memory");
+        };
+        auto features = [&](const TileIter& t, int b) {
+            for (int r = ft; r < 128; r += 96) write_features(sX + (size_t)b * a.maxn * 4, t, r >> 5, r & 31, sFeat);
+            tc::fence_proxy_async_smem();
+            tc::mbar_arrive(&bars[B_FEAT]);
+        };
+        int xb = 0;
+        stage_x(it, 0);
+        features(it, 0);
+        uint32_t ph = 0;
+        while (it.valid) {
+            TileIter nx = it;
+            iter_next(d, nx);
+            tc::mbar_wait(&bars[B_PRE], ph);            // the tensor pipe has consumed this tile's feature operand
+            if (nx.valid) {
+                if (nx.u != it.u) { xb ^= 1; stage_x(nx, xb); }
+                features(nx, xb);
+            }
+            it = nx; ph ^= 1;
+        }
       }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
         // ================= row warps: thread = (row, channel half) =================
         // warp w: rows 32*(w&3)..+31, channels [64*(w>>2), +64) of the key MLP, then of the value MLP; heads 8*(w>>2)..+7
         const int half = warp >> 2;
-        int xb = 0;                                     // coordinate buffer of the current unit
-        auto stage_x = [&](const TileIter& t, int b) {  // warps 4-7 only (128 threads)
-            for (int i = tid - 128; i < t.n; i += 128) {
-                const float* src = a.x + (size_t)(t.ctx0 + i) * 3;
-                st4(sX + ((size_t)b * a.maxn + i) * 4, make_float4(src[0], src[1], src[2], 0.f));
-            }
-            asm volatile("bar.sync 2, 128;" ::: "memory");
-        };
-        if (half == 1) stage_x(it, 0);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (lane < 16) write_features(sX, it, wq, half * 16 + lane, sFeat);
-        tc::fence_proxy_async_smem();
-        tc::mbar_arrive(&bars[B_FEAT]);
         tc::mbar_arrive(&bars[B_FREE]);                 // TMEM starts free
         uint32_t ph = 0, psph = 0;
         int buf = 0, staged_u = -1;
@@ -295,7 +312,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
         while (it.valid) {
             TRACE(role, 0);
             if (staged_u != it.u) {                     // P rows of this unit have landed (bulk copy issued by warp 8)
-                if (staged_u >= 0) xb ^= 1;
                 tc::mbar_wait(&bars[B_PS], psph);
                 psph ^= 1;
                 staged_u = it.u;
@@ -364,17 +380,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             TRACE(role, 4);
             TileIter nx = it;
             iter_next(d, nx);
-            if (nx.valid) {
-                // ---- features of the NEXT tile while the tensor pipe works on this one (16 rows per warp)
-                const int nb = nx.u != it.u ? (xb ^ 1) : xb;
-                if (nx.u != it.u) {
-                    if (half == 1) stage_x(nx, nb);
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                }
-                if (lane < 16) write_features(sX + (size_t)nb * a.maxn * 4, nx, wq, half * 16 + lane, sFeat);
-                tc::fence_proxy_async_smem();
-                tc::mbar_arrive(&bars[B_FEAT]);
-            }
             TRACE(role, 5);
             // ---- logits of this thread's 8 heads, segment softmax across the 32 lanes (rows) of the warp
             float al[8];
@@ -424,6 +429,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
                 tc::tmem_ld32_nowait(tmem + lane_base + C_OUT + 128 + half * 64, vu);
                 tc::tmem_ld32_nowait(tmem + lane_base + C_OUT + 128 + half * 64 + 32, vu + 32);
                 tc::tmem_ld_wait();
+                // the accumulators of this tile are in registers now: release TMEM so that the next tile's angle MMA (and its
+                // latency) overlaps the reduction below
+                tc::tc_fence_before();
+                tc::mbar_arrive(&bars[B_FREE]);
 #pragma unroll
                 for (int ch = 0; ch < 2; ch++) {
                     float v[32];
@@ -435,8 +444,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
                         a.hb[(size_t)sg.eji * 128 + c] += o + sB2[128 + c];     // sum(alpha) = 1; residual (uni_denoiser.py:285)
                     }
                 }
-                tc::tc_fence_before();
-                tc::mbar_arrive(&bars[B_FREE]);
             }
             TRACE(role, 7);
             it = nx; ph ^= 1; buf ^= 1; tcount++;
