@@ -33,7 +33,8 @@ enum { A_FULL = 0, A_EMPTY = 2, B_FULL = 4, B_EMPTY = 4 + NB, ACC_FULL = 4 + 2 *
 template <int PRO>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(GemmArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B tiles need 1024-byte alignment
+    // SWIZZLE_128B tiles need 1024-byte alignment; offset arithmetic keeps the shared address space (LDS/STS, not generic)
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA = smem;
     uint8_t* sB = smem + 2 * A_BUF;
     float* sEpi = (float*)(sB + NB * B_BUF);

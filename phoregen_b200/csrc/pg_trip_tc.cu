@@ -26,7 +26,7 @@
 #ifdef PG_TRIP_TRACE
 __device__ long long g_trip_trace[3 * 64 * 16];
 extern "C" int pg_debug_trip_trace(long long* h_out) { return cudaMemcpyFromSymbol(h_out, g_trip_trace, sizeof(g_trip_trace)) == cudaSuccess ? 0 : -2; }
-#define TRACE(role, slot) do { if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == 8) && tcount < 64) g_trip_trace[((role) * 64 + tcount) * 16 + (slot)] = clock64(); } while (0)
+#define TRACE(role, slot) do { if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == 16) && tcount < 64) g_trip_trace[((role) * 64 + tcount) * 16 + (slot)] = clock64(); } while (0)
 #else
 #define TRACE(role, slot) do {} while (0)
 #endif
@@ -41,7 +41,10 @@ constexpr int SM_QR = 2 * (4 * 128 + 4 * 256) * 4;   // double-buffered query ro
 constexpr int SM_ALPHA = 128 * 16 * 4;     // attention weights of the tile [row][head]
 constexpr int SM_FIXED = SM_W + SM_WA + SM_FEAT + SM_QR + SM_ALPHA + 6 * 128 * 4 /*ln + b2*/ + 128 /*barriers*/;
 constexpr float kInvSqrtD = 0.35355339059327373f;
-constexpr int NTHREADS = 384;              // warpgroups: 0 = key rows, 1 = value rows, 2 = MMA issue + q/R loader (warp 8; 9-11 idle)
+constexpr int ROW_WARPS = 16;               // 4 warps per TMEM lane quarter, each owning a 32-channel slice of the row
+constexpr int MMA_WARP = ROW_WARPS;         // MMA issue + q/R/P loaders; the 3 warps after it compute angular features
+constexpr int NTHREADS = (ROW_WARPS + 4) * 32;
+constexpr int ROW_THREADS = ROW_WARPS * 32;
 
 // mbarrier slots
 enum { B_FEAT = 0, B_PRE, B_HIDK, B_HIDV, B_OUTK, B_OUTV, B_PS, B_FREE, B_COUNT };
@@ -121,12 +124,13 @@ __device__ __forceinline__ void write_features(const float* xs, const TileIter& 
 
 __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // offset arithmetic on the __shared__ array (not a uintptr_t round trip) so the compiler keeps emitting LDS/STS
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sW = smem;
     uint8_t* sWa = sW + SM_W;
     uint8_t* sFeat = sWa + SM_WA;
     float* sQR = (float*)(sFeat + SM_FEAT);         // [2][ q: 4x128 | R: 4x256 ]
-    float* sStat = sQR + SM_QR / 4;                 // [2 mlp][128 rows][2 halves][2]  partial LayerNorm sums
+    float* sStat = sQR + SM_QR / 4;                 // [2 mlp][128 rows][4 quarters][2]  partial LayerNorm sums
     float* sLn = sStat + SM_ALPHA / 4;              // gk, bk, gv, bv
     float* sB2 = sLn + 4 * 128;                     // b2k, b2v
     uint64_t* bars = (uint64_t*)(sB2 + 2 * 128);
@@ -137,12 +141,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wq = warp & 3;
 
-    if (warp == 8) tc::tmem_alloc<512>(tmem_slot);
+    if (warp == MMA_WARP) tc::tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
         tc::mbar_init(&bars[B_FEAT], 96 + 32); tc::mbar_init(&bars[B_PRE], 1);
-        tc::mbar_init(&bars[B_HIDK], 256); tc::mbar_init(&bars[B_HIDV], 256);
+        tc::mbar_init(&bars[B_HIDK], ROW_THREADS); tc::mbar_init(&bars[B_HIDV], ROW_THREADS);
         tc::mbar_init(&bars[B_OUTK], 1); tc::mbar_init(&bars[B_OUTV], 1);
-        tc::mbar_init(&bars[B_PS], 1); tc::mbar_init(&bars[B_FREE], 256);
+        tc::mbar_init(&bars[B_PS], 1); tc::mbar_init(&bars[B_FREE], ROW_THREADS);
         tc::fence_barrier_init();
     }
     // ---- resident weights
@@ -177,14 +181,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
     iter_load_unit(d, it);
     if (!it.valid) {
         __syncthreads();
-        if (warp == 8) tc::tmem_dealloc<512>(tmem);
+        if (warp == MMA_WARP) tc::tmem_dealloc<512>(tmem);
         return;
     }
 
-    if (warp >= 8) {
-        // registers move from this (nearly idle) warpgroup to the two row warpgroups
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-      if (warp == 8) {
+    if (warp >= MMA_WARP) {
+        // registers move from this warpgroup to the four row warpgroups
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+      if (warp == MMA_WARP) {
         // ================= MMA issue + loaders (query / r_ji rows via cp.async, P rows via bulk copy) =================
         constexpr uint32_t idesc_feat = tc::umma_idesc_bf16(128, 256);
         constexpr uint32_t idesc_w2 = tc::umma_idesc_bf16(128, 128);
@@ -269,9 +273,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             it = nx; ph ^= 1; buf ^= 1; tcount++;
         }
       } else {
-        // ================= warps 9-11: angular features of the NEXT tile (off every critical path) =================
+        // ================= feature warps: angular features of the NEXT tile (off every critical path) =================
         // 96 threads cover the 128 rows of a tile in two passes; they also stage the next unit's coordinates.
-        const int ft = tid - 288;                       // 0..95
+        const int ft = tid - (MMA_WARP + 1) * 32;                       // 0..95
         auto stage_x = [&](const TileIter& t, int b) {
             for (int i = ft; i < t.n; i += 96) {
                 const float* src = a.x + (size_t)(t.ctx0 + i) * 3;
@@ -300,18 +304,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
         }
       }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
-        // ================= row warps: thread = (row, channel half) =================
-        // warp w: rows 32*(w&3)..+31, channels [64*(w>>2), +64) of the key MLP, then of the value MLP; heads 8*(w>>2)..+7
-        const int half = warp >> 2;
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        // ================= row warps: thread = (row, channel quarter) =================
+        // warp w: rows 32*(w&3)..+31, channels [32*(w>>2), +32) of the key MLP, then of the value MLP; heads 4*(w>>2)..+3
+        // (four row warps per scheduler: enough independent work to cover the TMEM / shared-memory latencies)
+        const int cq = warp >> 2;
         tc::mbar_arrive(&bars[B_FREE]);                 // TMEM starts free
         uint32_t ph = 0, psph = 0;
         int buf = 0, staged_u = -1;
         int tcount = 0;
-        const int role = half;
+        const int role = cq;
         while (it.valid) {
             TRACE(role, 0);
-            if (staged_u != it.u) {                     // P rows of this unit have landed (bulk copy issued by warp 8)
+            if (staged_u != it.u) {                     // P rows of this unit have landed (bulk copy issued by the MMA warp)
                 tc::mbar_wait(&bars[B_PS], psph);
                 psph ^= 1;
                 staged_u = it.u;
@@ -325,24 +330,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             tc::mbar_wait(&bars[B_PRE], ph);
             TRACE(role, 2);
             tc::tc_fence_after();
-            // ---- key MLP then value MLP: pre-activation half row -> LayerNorm + ReLU -> bf16 hi/lo A operand in TMEM
+            // ---- key MLP then value MLP: pre-activation quarter row -> LayerNorm + ReLU -> bf16 hi/lo A operand in TMEM
 #pragma unroll
             for (int mlp = 0; mlp < 2; mlp++) {
-                const int c0 = mlp * 128 + half * 64;    // first of this thread's 64 channels inside the 256-wide (k|v) row
-                float2 x2[32];
+                const int c0 = mlp * 128 + cq * 32;      // first of this thread's 32 channels inside the 256-wide (k|v) row
+                float2 x2[16];
                 {
-                    uint32_t xu[64];
+                    uint32_t xu[32];
                     tc::tmem_ld32_nowait(tmem + lane_base + C_PRE + c0, xu);
-                    tc::tmem_ld32_nowait(tmem + lane_base + C_PRE + c0 + 32, xu + 32);
                     tc::tmem_ld_wait();
+                    if (mlp == 0) TRACE(role, 8);
 #pragma unroll
-                    for (int i = 0; i < 32; i++) x2[i] = make_float2(__uint_as_float(xu[2 * i]), __uint_as_float(xu[2 * i + 1]));
+                    for (int i = 0; i < 16; i++) x2[i] = make_float2(__uint_as_float(xu[2 * i]), __uint_as_float(xu[2 * i + 1]));
                 }
                 float2 s1 = make_float2(0.f, 0.f), s2 = s1, s1b = s1, s2b = s1;
                 const float* prow = sPs + trow * PS_LD + c0;
                 const float* rrow = sR + wq * 256 + c0;
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
+                for (int i = 0; i < 16; i += 2) {
                     const float4 p = ld4(prow + 2 * i), rr = ld4(rrow + 2 * i);
                     x2[i] = tc::add2(x2[i], tc::add2(make_float2(p.x, p.y), make_float2(rr.x, rr.y)));
                     x2[i + 1] = tc::add2(x2[i + 1], tc::add2(make_float2(p.z, p.w), make_float2(rr.z, rr.w)));
@@ -350,19 +355,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
                     s2 = tc::fma2(x2[i], x2[i], s2); s2b = tc::fma2(x2[i + 1], x2[i + 1], s2b);
                 }
                 s1 = tc::add2(s1, s1b); s2 = tc::add2(s2, s2b);
-                // combine with the other channel half of the same row (warp w +- 4, same lane)
-                float* st = sStat + ((mlp * 128 + wq * 32 + lane) * 2) * 2;
-                *reinterpret_cast<float2*>(st + half * 2) = make_float2(s1.x + s1.y, s2.x + s2.y);
-                asm volatile("bar.sync %0, 64;" ::"r"(3 + wq) : "memory");
-                const float4 both = ld4(st);
-                const float mu = (both.x + both.z) * (1.0f / 128.0f);
-                const float rstd = rsqrtf(fmaxf(fmaf(-mu, mu, (both.y + both.w) * (1.0f / 128.0f)), 0.f) + 1e-5f);
+                // combine with the other three channel quarters of the same row (warps w +- 4k, same lane)
+                float* st = sStat + ((mlp * 128 + wq * 32 + lane) * 4) * 2;
+                *reinterpret_cast<float2*>(st + cq * 2) = make_float2(s1.x + s1.y, s2.x + s2.y);
+                if (mlp == 0) TRACE(role, 9);
+                asm volatile("bar.sync %0, 128;" ::"r"(3 + wq) : "memory");
+                if (mlp == 0) TRACE(role, 10);
+                const float4 sa4 = ld4(st), sb4 = ld4(st + 4);
+                const float mu = ((sa4.x + sa4.z) + (sb4.x + sb4.z)) * (1.0f / 128.0f);
+                const float rstd = rsqrtf(fmaxf(fmaf(-mu, mu, ((sa4.y + sa4.w) + (sb4.y + sb4.w)) * (1.0f / 128.0f)), 0.f) + 1e-5f);
                 const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mu * rstd, -mu * rstd);
-                const float* gam = sLn + mlp * 256 + half * 64;
+                const float* gam = sLn + mlp * 256 + cq * 32;
                 const float* bet = gam + 128;
-                uint32_t hi[32], lo[32];
+                uint32_t hi[16], lo[16];
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
+                for (int i = 0; i < 16; i += 2) {
                     const float4 g4 = ld4(gam + 2 * i), b4 = ld4(bet + 2 * i);
                     float2 y0 = tc::fma2(tc::fma2(x2[i], rs2, nm2), make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
                     float2 y1 = tc::fma2(tc::fma2(x2[i + 1], rs2, nm2), make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
@@ -370,8 +377,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
                     tc::split_pair_trunc(fmaxf(y1.x, 0.f), fmaxf(y1.y, 0.f), hi[i + 1], lo[i + 1]);
                 }
                 const uint32_t hid = tmem + lane_base + (mlp == 0 ? C_HIDK : C_HIDV);
-                tc::tmem_st32(hid + half * 32, hi);
-                tc::tmem_st32(hid + 64 + half * 32, lo);
+                if (mlp == 0) TRACE(role, 11);
+                tc::tmem_st16(hid + cq * 16, hi);
+                tc::tmem_st16(hid + 64 + cq * 16, lo);
                 tc::tmem_st_wait();
                 tc::tc_fence_before();
                 tc::mbar_arrive(&bars[mlp == 0 ? B_HIDK : B_HIDV]);
@@ -381,22 +389,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             TileIter nx = it;
             iter_next(d, nx);
             TRACE(role, 5);
-            // ---- logits of this thread's 8 heads, segment softmax across the 32 lanes (rows) of the warp
-            float al[8];
+            // ---- logits of this thread's 4 heads, segment softmax across the 32 lanes (rows) of the warp
+            float al[4];
             {
                 tc::mbar_wait(&bars[B_OUTK], ph);
                 tc::tc_fence_after();
-                uint32_t v0[32], v1[32];
-                tc::tmem_ld32_nowait(tmem + lane_base + C_OUT + half * 64, v0);
-                tc::tmem_ld32_nowait(tmem + lane_base + C_OUT + half * 64 + 32, v1);
+                uint32_t vv[32];
+                tc::tmem_ld32_nowait(tmem + lane_base + C_OUT + cq * 32, vv);
                 tc::tmem_ld_wait();
-                const float* qrow = sQ + wq * 128 + half * 64;
-                const float* b2 = sB2 + half * 64;
+                const float* qrow = sQ + wq * 128 + cq * 32;
+                const float* b2 = sB2 + cq * 32;
 #pragma unroll
-                for (int h = 0; h < 8; h++) {
+                for (int h = 0; h < 4; h++) {
                     float sa = 0.f, sb = 0.f;
-                    const uint32_t* vv = h < 4 ? v0 : v1;
-                    const int o = (h & 3) * 8;
+                    const int o = h * 8;
                     const float4 qa = ld4(qrow + h * 8), qb = ld4(qrow + h * 8 + 4), ba = ld4(b2 + h * 8), bb = ld4(b2 + h * 8 + 4);
                     sa = fmaf(qa.x, __uint_as_float(vv[o]) + ba.x, sa); sb = fmaf(qa.y, __uint_as_float(vv[o + 1]) + ba.y, sb);
                     sa = fmaf(qa.z, __uint_as_float(vv[o + 2]) + ba.z, sa); sb = fmaf(qa.w, __uint_as_float(vv[o + 3]) + ba.w, sb);
@@ -404,45 +410,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
                     sa = fmaf(qb.z, __uint_as_float(vv[o + 6]) + bb.z, sa); sb = fmaf(qb.w, __uint_as_float(vv[o + 7]) + bb.w, sb);
                     al[h] = rowvalid ? (sa + sb) * kInvSqrtD : -INFINITY;
                 }
-                float mx[8], sm[8];
+                float mx[4], sm[4];
 #pragma unroll
-                for (int h = 0; h < 8; h++) mx[h] = al[h];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                    for (int h = 0; h < 8; h++) mx[h] = fmaxf(mx[h], __shfl_xor_sync(PG_FULL, mx[h], o));
-#pragma unroll
-                for (int h = 0; h < 8; h++) { al[h] = rowvalid ? __expf(al[h] - mx[h]) : 0.f; sm[h] = al[h]; }
+                for (int h = 0; h < 4; h++) mx[h] = al[h];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-                    for (int h = 0; h < 8; h++) sm[h] += __shfl_xor_sync(PG_FULL, sm[h], o);
+                    for (int h = 0; h < 4; h++) mx[h] = fmaxf(mx[h], __shfl_xor_sync(PG_FULL, mx[h], o));
 #pragma unroll
-                for (int h = 0; h < 8; h++) al[h] *= __frcp_rn(sm[h]);
+                for (int h = 0; h < 4; h++) { al[h] = rowvalid ? __expf(al[h] - mx[h]) : 0.f; sm[h] = al[h]; }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int h = 0; h < 4; h++) sm[h] += __shfl_xor_sync(PG_FULL, sm[h], o);
+#pragma unroll
+                for (int h = 0; h < 4; h++) al[h] *= __frcp_rn(sm[h]);
             }
             TRACE(role, 6);
             // ---- alpha-weighted sum of the value rows over the segment (lanes), residual add into h_bond
             {
                 tc::mbar_wait(&bars[B_OUTV], ph);
                 tc::tc_fence_after();
-                uint32_t vu[64];
-                tc::tmem_ld32_nowait(tmem + lane_base + C_OUT + 128 + half * 64, vu);
-                tc::tmem_ld32_nowait(tmem + lane_base + C_OUT + 128 + half * 64 + 32, vu + 32);
+                uint32_t vu[32];
+                tc::tmem_ld32_nowait(tmem + lane_base + C_OUT + 128 + cq * 32, vu);
                 tc::tmem_ld_wait();
                 // the accumulators of this tile are in registers now: release TMEM so that the next tile's angle MMA (and its
                 // latency) overlaps the reduction below
                 tc::tc_fence_before();
                 tc::mbar_arrive(&bars[B_FREE]);
+                float v[32];
 #pragma unroll
-                for (int ch = 0; ch < 2; ch++) {
-                    float v[32];
-#pragma unroll
-                    for (int i = 0; i < 32; i++) v[i] = al[ch * 4 + (i >> 3)] * __uint_as_float(vu[ch * 32 + i]);   // alpha is 0 on padded rows
-                    const float o = transpose_reduce32(v, lane);
-                    if (sg.valid) {
-                        const int c = half * 64 + ch * 32 + lane;
-                        a.hb[(size_t)sg.eji * 128 + c] += o + sB2[128 + c];     // sum(alpha) = 1; residual (uni_denoiser.py:285)
-                    }
+                for (int i = 0; i < 32; i++) v[i] = al[i >> 3] * __uint_as_float(vu[i]);   // alpha is 0 on padded rows
+                const float o = transpose_reduce32(v, lane);
+                if (sg.valid) {
+                    const int c = cq * 32 + lane;
+                    a.hb[(size_t)sg.eji * 128 + c] += o + sB2[128 + c];     // sum(alpha) = 1; residual (uni_denoiser.py:285)
                 }
             }
             TRACE(role, 7);
@@ -451,7 +453,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 8) { tc::tc_fence_after(); tc::tmem_dealloc<512>(tmem); }
+    if (warp == MMA_WARP) { tc::tc_fence_after(); tc::tmem_dealloc<512>(tmem); }
 }
 
 // Per-edge partials of the triplet MLPs' first Linear, for every bond edge e = (src -> dst):
