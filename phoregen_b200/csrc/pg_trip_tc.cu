@@ -36,7 +36,8 @@ constexpr int PS_LD = 260;                 // padded row stride of the staged P 
 constexpr int W_TILE = 32768;              // one [128 x 128] bf16 matrix in two 128B-swizzled K blocks
 constexpr int SM_W = 4 * W_TILE;           // (k,v) x (hi,lo)
 constexpr int SM_WA = 2 * 8192;            // angle slice of the first Linear: (hi,lo) x [256 x 16] bf16, no swizzle
-constexpr int SM_FEAT = 2 * 4096;          // (hi,lo) x [128 x 16] bf16, no swizzle
+constexpr int SM_FEAT1 = 2 * 4096;         // (hi,lo) x [128 x 16] bf16, no swizzle
+constexpr int SM_FEAT = 2 * SM_FEAT1;      // double-buffered: the feature warps run up to two tiles ahead
 constexpr int SM_QR = 2 * (4 * 128 + 4 * 256) * 4;   // double-buffered query rows + r_ji rows of a tile's 4 segments
 constexpr int SM_ALPHA = 128 * 16 * 4;     // attention weights of the tile [row][head]
 constexpr int SM_FIXED = SM_W + SM_WA + SM_FEAT + SM_QR + SM_ALPHA + 6 * 128 * 4 /*ln + b2*/ + 128 /*barriers*/;
@@ -47,7 +48,7 @@ constexpr int NTHREADS = (ROW_WARPS + 4) * 32;
 constexpr int ROW_THREADS = ROW_WARPS * 32;
 
 // mbarrier slots
-enum { B_FEAT = 0, B_PRE, B_HIDK, B_HIDV, B_OUTK, B_OUTV, B_PS, B_FREE, B_COUNT };
+enum { B_FEAT0 = 0, B_FEAT1, B_PREK, B_PREV, B_HIDK, B_HIDV, B_OUTK, B_OUTV, B_PSK, B_PSV, B_COUNT };
 
 // the sequence of (unit, tile) a CTA walks; every role steps through it redundantly
 struct TileIter {
@@ -143,10 +144,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
 
     if (warp == MMA_WARP) tc::tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
-        tc::mbar_init(&bars[B_FEAT], 96 + 32); tc::mbar_init(&bars[B_PRE], 1);
+        tc::mbar_init(&bars[B_FEAT0], 96 + 32); tc::mbar_init(&bars[B_FEAT1], 96 + 32);
+        tc::mbar_init(&bars[B_PREK], 1); tc::mbar_init(&bars[B_PREV], 1);
         tc::mbar_init(&bars[B_HIDK], ROW_THREADS); tc::mbar_init(&bars[B_HIDV], ROW_THREADS);
         tc::mbar_init(&bars[B_OUTK], 1); tc::mbar_init(&bars[B_OUTV], 1);
-        tc::mbar_init(&bars[B_PS], 1); tc::mbar_init(&bars[B_FREE], ROW_THREADS);
+        tc::mbar_init(&bars[B_PSK], 1); tc::mbar_init(&bars[B_PSV], 1);
         tc::fence_barrier_init();
     }
     // ---- resident weights
@@ -173,8 +175,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-    // TMEM columns: pre_k [0,128) pre_v [128,256) (later out_k / out_v) ; hid_k [256,384) ; hid_v [384,512)
-    constexpr uint32_t C_PRE = 0, C_OUT = 0, C_HIDK = 256, C_HIDV = 384;
 
     TileIter it;
     it.u = blockIdx.x;
@@ -190,8 +190,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
       if (warp == MMA_WARP) {
         // ================= MMA issue + loaders (query / r_ji rows via cp.async, P rows via bulk copy) =================
-        constexpr uint32_t idesc_feat = tc::umma_idesc_bf16(128, 256);
-        constexpr uint32_t idesc_w2 = tc::umma_idesc_bf16(128, 128);
+        constexpr uint32_t idesc = tc::umma_idesc_bf16(128, 128);
         const uint32_t sW_u32 = tc::smem_u32(sW), sWa_u32 = tc::smem_u32(sWa), sFeat_u32 = tc::smem_u32(sFeat);
         auto load_qr = [&](const TileIter& t, int buf) {
             const uint32_t q = tc::smem_u32(sQR + buf * (SM_QR / 8));
@@ -207,75 +206,104 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        // P rows of the edges k -> j of a unit: n-1 contiguous 1 KB rows -> padded smem rows, one mbarrier transaction
-        auto load_ps = [&](const TileIter& t) {
-            if (lane == 0) tc::mbar_arrive_expect_tx(&bars[B_PS], (uint32_t)(t.n - 1) * 1024u);
+        // P rows of the edges k -> j of a unit (n-1 contiguous 1 KB rows) -> padded smem rows.  The key and value halves
+        // travel separately (one mbarrier transaction each): each half is dead as soon as its LayerNorm pass of the
+        // unit's last tile is done, so the next unit's half is requested a whole phase before it is needed.
+        auto load_ps = [&](const TileIter& t, int mlp) {
+            uint64_t* bar = &bars[mlp == 0 ? B_PSK : B_PSV];
+            if (lane == 0) tc::mbar_arrive_expect_tx(bar, (uint32_t)(t.n - 1) * 512u);
             __syncwarp();
-            const float* src = a.P + (size_t)(t.eoff + (long long)t.jl * (t.n - 1)) * 256;
-            for (int r = lane; r < t.n - 1; r += 32) tc::bulk_copy_g2s(sPs + (size_t)r * PS_LD, src + (size_t)r * 256, 1024u, &bars[B_PS]);
+            const float* src = a.P + (size_t)(t.eoff + (long long)t.jl * (t.n - 1)) * 256 + mlp * 128;
+            for (int r = lane; r < t.n - 1; r += 32) tc::bulk_copy_g2s(sPs + (size_t)r * PS_LD + mlp * 128, src + (size_t)r * 256, 512u, bar);
         };
-        load_ps(it);
+        // angle slice of the first Linear for one MLP of tile `tl` (operand buffer tl & 1) -> pre-activation columns `dcol`
+        auto feat_mma = [&](int tl, int mlp, uint32_t dcol, uint64_t* bar) {
+            if (lane == 0) {
+                const uint32_t fb = sFeat_u32 + (tl & 1) * SM_FEAT1;
+                const uint64_t fh = tc::umma_desc_k16_noswizzle(fb), fl = tc::umma_desc_k16_noswizzle(fb + 4096);
+                const uint64_t wh = tc::umma_desc_k16_noswizzle(sWa_u32 + mlp * 4096), wl = tc::umma_desc_k16_noswizzle(sWa_u32 + 8192 + mlp * 4096);
+                tc::umma_bf16(dcol, fh, wh, idesc, 0);
+                tc::umma_bf16(dcol, fh, wl, idesc, 1);
+                tc::umma_bf16(dcol, fl, wh, idesc, 1);
+                tc::umma_commit(bar);
+            }
+            __syncwarp();
+        };
+        // second Linear of one MLP: A = bf16 hi/lo activations in TMEM columns `hid`, D = `dcol`
+        auto w2_mma = [&](int mlp, uint32_t hid, uint32_t dcol, uint64_t* bar) {
+            if (lane == 0) {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int combo = 0; combo < 3; combo++) {       // hi*hi, hi*lo, lo*hi
+                    const uint32_t abase = hid + (combo == 2 ? 64 : 0);
+                    const uint32_t bbase = sW_u32 + (mlp * 2 + (combo == 1 ? 1 : 0)) * W_TILE;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ks++) {
+                        const uint64_t bd = tc::umma_desc_sw128(bbase + (ks >> 2) * 16384 + (ks & 3) * 32);
+                        tc::umma_bf16_ts(dcol, abase + ks * 8, bd, idesc, acc);
+                        acc = 1;
+                    }
+                }
+                tc::umma_commit(bar);
+            }
+            __syncwarp();
+        };
+        load_ps(it, 0);
+        load_ps(it, 1);
         load_qr(it, 0);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        tc::mbar_arrive(&bars[B_FEAT]);
-        uint32_t ph = 0;
-        int buf = 0;
+        tc::mbar_arrive(&bars[B_FEAT0]);
+        tc::mbar_wait(&bars[B_FEAT0], 0);
+        tc::tc_fence_after();
+        feat_mma(0, 0, tmem + 0, &bars[B_PREK]);
+        feat_mma(0, 1, tmem + 128, &bars[B_PREV]);
         int tcount = 0;
         while (it.valid) {
-            TRACE(2, 0);
-            tc::mbar_wait(&bars[B_FEAT], ph);          // features + q/R rows of this tile are in smem
-            TRACE(2, 1);
-            tc::mbar_wait(&bars[B_FREE], ph);          // previous tile's accumulators have been read
-            TRACE(2, 2);
-            tc::tc_fence_after();
-            if (lane == 0) {
-                const uint64_t fh = tc::umma_desc_k16_noswizzle(sFeat_u32), fl = tc::umma_desc_k16_noswizzle(sFeat_u32 + 4096);
-                const uint64_t wh = tc::umma_desc_k16_noswizzle(sWa_u32), wl = tc::umma_desc_k16_noswizzle(sWa_u32 + 8192);
-                tc::umma_bf16(tmem + C_PRE, fh, wh, idesc_feat, 0);
-                tc::umma_bf16(tmem + C_PRE, fh, wl, idesc_feat, 1);
-                tc::umma_bf16(tmem + C_PRE, fl, wh, idesc_feat, 1);
-                tc::umma_commit(&bars[B_PRE]);
-            }
-            __syncwarp();
-            TRACE(2, 3);
+            const uint32_t ph = tcount & 1;
+            // column roles alternate per tile: even tiles pre/out in [0,128)|[128,256), hid in [256,384)|[384,512); odd swapped
+            const uint32_t preK = tmem + (ph ? 256 : 0), hidK = tmem + (ph ? 0 : 256);
+            const uint32_t preV = tmem + (ph ? 384 : 128), hidV = tmem + (ph ? 128 : 384);
             TileIter nx = it;
             iter_next(d, nx);
-            if (nx.valid) load_qr(nx, buf ^ 1);
-            TRACE(2, 4);
-#pragma unroll
-            for (int mlp = 0; mlp < 2; mlp++) {
-                tc::mbar_wait(&bars[mlp == 0 ? B_HIDK : B_HIDV], ph);
-                TRACE(2, 5 + mlp * 2);
+            const bool newu = nx.valid && nx.u != it.u;
+            uint64_t* featbar = &bars[(tcount + 1) & 1 ? B_FEAT1 : B_FEAT0];
+            TRACE(2, 0);
+            tc::mbar_wait(&bars[B_HIDK], ph);          // key activations of tile t are in TMEM; logits of tile t-1 are done
+            TRACE(2, 1);
+            tc::tc_fence_after();
+            if (nx.valid) load_qr(nx, (tcount + 1) & 1);
+            if (newu) load_ps(nx, 0);
+            w2_mma(0, hidK, preK, &bars[B_OUTK]);
+            TRACE(2, 2);
+            if (nx.valid) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                tc::mbar_arrive(featbar);
+                tc::mbar_wait(&bars[B_OUTK], ph);      // hid_k(t) has been consumed: its columns take pre_k(t+1)
+                tc::mbar_wait(featbar, ((tcount + 1) >> 1) & 1);
                 tc::tc_fence_after();
-                // both LayerNorm passes of this tile are done: the P rows of the next unit may overwrite the current ones
-                if (mlp == 1 && nx.valid && nx.u != it.u) load_ps(nx);
-                if (lane == 0) {
-                    const uint32_t hid = tmem + (mlp == 0 ? C_HIDK : C_HIDV);
-                    const uint32_t dcol = tmem + C_OUT + mlp * 128;
-                    uint32_t acc = 0;
-#pragma unroll
-                    for (int combo = 0; combo < 3; combo++) {       // hi*hi, hi*lo, lo*hi
-                        const uint32_t abase = hid + (combo == 2 ? 64 : 0);
-                        const uint32_t bbase = sW_u32 + (mlp * 2 + (combo == 1 ? 1 : 0)) * W_TILE;
-#pragma unroll
-                        for (int ks = 0; ks < 8; ks++) {
-                            const uint64_t bd = tc::umma_desc_sw128(bbase + (ks >> 2) * 16384 + (ks & 3) * 32);
-                            tc::umma_bf16_ts(dcol, abase + ks * 8, bd, idesc_w2, acc);
-                            acc = 1;
-                        }
-                    }
-                    tc::umma_commit(&bars[mlp == 0 ? B_OUTK : B_OUTV]);
-                }
-                __syncwarp();
-                TRACE(2, 6 + mlp * 2);
+                TRACE(2, 3);
+                feat_mma(tcount + 1, 0, hidK, &bars[B_PREK]);
             }
-            if (nx.valid) { asm volatile("cp.async.wait_group 0;" ::: "memory"); tc::mbar_arrive(&bars[B_FEAT]); }
-            it = nx; ph ^= 1; buf ^= 1; tcount++;
+            TRACE(2, 4);
+            tc::mbar_wait(&bars[B_HIDV], ph);
+            TRACE(2, 5);
+            tc::tc_fence_after();
+            if (newu) load_ps(nx, 1);
+            w2_mma(1, hidV, preV, &bars[B_OUTV]);
+            TRACE(2, 6);
+            if (nx.valid) {
+                tc::mbar_wait(&bars[B_OUTV], ph);
+                tc::tc_fence_after();
+                TRACE(2, 7);
+                feat_mma(tcount + 1, 1, hidV, &bars[B_PREV]);
+            }
+            TRACE(2, 8);
+            it = nx; tcount++;
         }
       } else {
-        // ================= feature warps: angular features of the NEXT tile (off every critical path) =================
+        // ================= feature warps: angular features, up to two tiles ahead (double-buffered operand) =================
         // 96 threads cover the 128 rows of a tile in two passes; they also stage the next unit's coordinates.
-        const int ft = tid - (MMA_WARP + 1) * 32;                       // 0..95
+        const int ft = tid - (MMA_WARP + 1) * 32;       // 0..95
         auto stage_x = [&](const TileIter& t, int b) {
             for (int i = ft; i < t.n; i += 96) {
                 const float* src = a.x + (size_t)(t.ctx0 + i) * 3;
@@ -283,119 +311,140 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             }
             asm volatile("bar.sync 2, 96;" ::: "memory");
         };
-        auto features = [&](const TileIter& t, int b) {
-            for (int r = ft; r < 128; r += 96) write_features(sX + (size_t)b * a.maxn * 4, t, r >> 5, r & 31, sFeat);
+        auto features = [&](const TileIter& t, int b, int tl) {
+            for (int r = ft; r < 128; r += 96) write_features(sX + (size_t)b * a.maxn * 4, t, r >> 5, r & 31, sFeat + (tl & 1) * SM_FEAT1);
             tc::fence_proxy_async_smem();
-            tc::mbar_arrive(&bars[B_FEAT]);
+            tc::mbar_arrive(&bars[tl & 1 ? B_FEAT1 : B_FEAT0]);
         };
-        int xb = 0;
+        int xb = 0, s = 0;
         stage_x(it, 0);
-        features(it, 0);
-        uint32_t ph = 0;
+        features(it, 0, 0);
         while (it.valid) {
             TileIter nx = it;
             iter_next(d, nx);
-            tc::mbar_wait(&bars[B_PRE], ph);            // the tensor pipe has consumed this tile's feature operand
+            // operand buffer (s+1)&1 was last read by the value-side angle MMA of tile s-1
+            if (s >= 1) tc::mbar_wait(&bars[B_PREV], (s - 1) & 1);
             if (nx.valid) {
                 if (nx.u != it.u) { xb ^= 1; stage_x(nx, xb); }
-                features(nx, xb);
+                features(nx, xb, s + 1);
             }
-            it = nx; ph ^= 1;
+            it = nx; s++;
         }
       }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // ================= row warps: thread = (row, channel quarter) =================
-        // warp w: rows 32*(w&3)..+31, channels [32*(w>>2), +32) of the key MLP, then of the value MLP; heads 4*(w>>2)..+3
+        // warp w: rows 32*(w&3)..+31, channels [32*(w>>2), +32) of the key MLP and of the value MLP; heads 4*(w>>2)..+3
         // (four row warps per scheduler: enough independent work to cover the TMEM / shared-memory latencies)
+        // Software pipeline across tiles (no warp ever waits for the tensor pipe in steady state):
+        //   LN-k(t) | epilogue(t-1) | LN-v(t) | logits(t)      while the tensor pipe runs   W2k(t), angle-k(t+1) | W2v(t), angle-v(t+1)
         const int cq = warp >> 2;
-        tc::mbar_arrive(&bars[B_FREE]);                 // TMEM starts free
-        uint32_t ph = 0, psph = 0;
-        int buf = 0, staged_u = -1;
+        uint32_t psk = 0, psv = 0;
+        int staged_k = -1, staged_v = -1;
         int tcount = 0;
-        const int role = cq;
-        while (it.valid) {
-            TRACE(role, 0);
-            if (staged_u != it.u) {                     // P rows of this unit have landed (bulk copy issued by the MMA warp)
-                tc::mbar_wait(&bars[B_PS], psph);
-                psph ^= 1;
-                staged_u = it.u;
+        const int role = cq; (void)role;
+        float al[4] = {0.f, 0.f, 0.f, 0.f};
+        bool prev_valid = false;
+        long long prev_eji = 0;
+        // pre-activation slice -> LayerNorm + ReLU -> bf16 hi/lo A operand of the second Linear
+        auto layer_norm = [&](int mlp, uint32_t pre, uint32_t hid, int trow, const float* sR) {
+            const int c0 = mlp * 128 + cq * 32;          // first of this thread's 32 channels inside the 256-wide (k|v) row
+            float2 x2[16];
+            {
+                uint32_t xu[32];
+                tc::tmem_ld32_nowait(pre + lane_base + cq * 32, xu);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; i++) x2[i] = make_float2(__uint_as_float(xu[2 * i]), __uint_as_float(xu[2 * i + 1]));
             }
+            float2 s1 = make_float2(0.f, 0.f), s2 = s1, s1b = s1, s2b = s1;
+            const float* prow = sPs + trow * PS_LD + c0;
+            const float* rrow = sR + wq * 256 + c0;
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                const float4 p = ld4(prow + 2 * i), rr = ld4(rrow + 2 * i);
+                x2[i] = tc::add2(x2[i], tc::add2(make_float2(p.x, p.y), make_float2(rr.x, rr.y)));
+                x2[i + 1] = tc::add2(x2[i + 1], tc::add2(make_float2(p.z, p.w), make_float2(rr.z, rr.w)));
+                s1 = tc::add2(s1, x2[i]); s1b = tc::add2(s1b, x2[i + 1]);
+                s2 = tc::fma2(x2[i], x2[i], s2); s2b = tc::fma2(x2[i + 1], x2[i + 1], s2b);
+            }
+            s1 = tc::add2(s1, s1b); s2 = tc::add2(s2, s2b);
+            // combine with the other three channel quarters of the same row (warps w +- 4k, same lane).  The barrier also
+            // orders this lane quarter's reads of the previous tile's accumulators before the hid columns overwrite them.
+            float* st = sStat + ((mlp * 128 + wq * 32 + lane) * 4) * 2;
+            *reinterpret_cast<float2*>(st + cq * 2) = make_float2(s1.x + s1.y, s2.x + s2.y);
+            asm volatile("bar.sync %0, 128;" ::"r"(3 + wq) : "memory");
+            const float4 sa4 = ld4(st), sb4 = ld4(st + 4);
+            const float mu = ((sa4.x + sa4.z) + (sb4.x + sb4.z)) * (1.0f / 128.0f);
+            const float rstd = rsqrtf(fmaxf(fmaf(-mu, mu, ((sa4.y + sa4.w) + (sb4.y + sb4.w)) * (1.0f / 128.0f)), 0.f) + 1e-5f);
+            const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mu * rstd, -mu * rstd);
+            const float* gam = sLn + mlp * 256 + cq * 32;
+            const float* bet = gam + 128;
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                const float4 g4 = ld4(gam + 2 * i), b4 = ld4(bet + 2 * i);
+                float2 y0 = tc::fma2(tc::fma2(x2[i], rs2, nm2), make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
+                float2 y1 = tc::fma2(tc::fma2(x2[i + 1], rs2, nm2), make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
+                tc::split_pair_trunc(fmaxf(y0.x, 0.f), fmaxf(y0.y, 0.f), hi[i], lo[i]);
+                tc::split_pair_trunc(fmaxf(y1.x, 0.f), fmaxf(y1.y, 0.f), hi[i + 1], lo[i + 1]);
+            }
+            tc::tmem_st16(hid + lane_base + cq * 16, hi);
+            tc::tmem_st16(hid + lane_base + 64 + cq * 16, lo);
+            tc::tmem_st_wait();
+            tc::tc_fence_before();
+            tc::mbar_arrive(&bars[mlp == 0 ? B_HIDK : B_HIDV]);
+        };
+        // alpha-weighted sum of the value rows over the segment (lanes), residual add into h_bond
+        auto epilogue = [&](uint32_t outV, uint32_t parity) {
+            tc::mbar_wait(&bars[B_OUTV], parity);
+            tc::tc_fence_after();
+            uint32_t vu[32];
+            tc::tmem_ld32_nowait(outV + lane_base + cq * 32, vu);
+            tc::tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = al[i >> 3] * __uint_as_float(vu[i]);   // alpha is 0 on padded rows
+            const float o = transpose_reduce32(v, lane);
+            if (prev_valid) {
+                const int c = cq * 32 + lane;
+                a.hb[(size_t)prev_eji * 128 + c] += o + sB2[128 + c];     // sum(alpha) = 1; residual (uni_denoiser.py:285)
+            }
+        };
+        while (it.valid) {
+            const uint32_t ph = tcount & 1;
+            const uint32_t preK = tmem + (ph ? 256 : 0), hidK = tmem + (ph ? 0 : 256);
+            const uint32_t preV = tmem + (ph ? 384 : 128), hidV = tmem + (ph ? 128 : 384);
             const Seg sg = seg_of(it, wq);
             const bool rowvalid = sg.valid && lane < it.n - 2;
             const int trow = rowvalid ? lane + (lane >= sg.ti) : 0;
-            const float* sQ = sQR + buf * (SM_QR / 8);
+            const float* sQ = sQR + (tcount & 1) * (SM_QR / 8);
             const float* sR = sQ + 4 * 128;
-            TRACE(role, 1);
-            tc::mbar_wait(&bars[B_PRE], ph);
-            TRACE(role, 2);
+            TRACE(role, 0);
+            // ---- key MLP
+            if (staged_k != it.u) { tc::mbar_wait(&bars[B_PSK], psk); psk ^= 1; staged_k = it.u; }   // P rows (key half) landed
+            tc::mbar_wait(&bars[B_PREK], ph);
             tc::tc_fence_after();
-            // ---- key MLP then value MLP: pre-activation quarter row -> LayerNorm + ReLU -> bf16 hi/lo A operand in TMEM
-#pragma unroll
-            for (int mlp = 0; mlp < 2; mlp++) {
-                const int c0 = mlp * 128 + cq * 32;      // first of this thread's 32 channels inside the 256-wide (k|v) row
-                float2 x2[16];
-                {
-                    uint32_t xu[32];
-                    tc::tmem_ld32_nowait(tmem + lane_base + C_PRE + c0, xu);
-                    tc::tmem_ld_wait();
-                    if (mlp == 0) TRACE(role, 8);
-#pragma unroll
-                    for (int i = 0; i < 16; i++) x2[i] = make_float2(__uint_as_float(xu[2 * i]), __uint_as_float(xu[2 * i + 1]));
-                }
-                float2 s1 = make_float2(0.f, 0.f), s2 = s1, s1b = s1, s2b = s1;
-                const float* prow = sPs + trow * PS_LD + c0;
-                const float* rrow = sR + wq * 256 + c0;
-#pragma unroll
-                for (int i = 0; i < 16; i += 2) {
-                    const float4 p = ld4(prow + 2 * i), rr = ld4(rrow + 2 * i);
-                    x2[i] = tc::add2(x2[i], tc::add2(make_float2(p.x, p.y), make_float2(rr.x, rr.y)));
-                    x2[i + 1] = tc::add2(x2[i + 1], tc::add2(make_float2(p.z, p.w), make_float2(rr.z, rr.w)));
-                    s1 = tc::add2(s1, x2[i]); s1b = tc::add2(s1b, x2[i + 1]);
-                    s2 = tc::fma2(x2[i], x2[i], s2); s2b = tc::fma2(x2[i + 1], x2[i + 1], s2b);
-                }
-                s1 = tc::add2(s1, s1b); s2 = tc::add2(s2, s2b);
-                // combine with the other three channel quarters of the same row (warps w +- 4k, same lane)
-                float* st = sStat + ((mlp * 128 + wq * 32 + lane) * 4) * 2;
-                *reinterpret_cast<float2*>(st + cq * 2) = make_float2(s1.x + s1.y, s2.x + s2.y);
-                if (mlp == 0) TRACE(role, 9);
-                asm volatile("bar.sync %0, 128;" ::"r"(3 + wq) : "memory");
-                if (mlp == 0) TRACE(role, 10);
-                const float4 sa4 = ld4(st), sb4 = ld4(st + 4);
-                const float mu = ((sa4.x + sa4.z) + (sb4.x + sb4.z)) * (1.0f / 128.0f);
-                const float rstd = rsqrtf(fmaxf(fmaf(-mu, mu, ((sa4.y + sa4.w) + (sb4.y + sb4.w)) * (1.0f / 128.0f)), 0.f) + 1e-5f);
-                const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mu * rstd, -mu * rstd);
-                const float* gam = sLn + mlp * 256 + cq * 32;
-                const float* bet = gam + 128;
-                uint32_t hi[16], lo[16];
-#pragma unroll
-                for (int i = 0; i < 16; i += 2) {
-                    const float4 g4 = ld4(gam + 2 * i), b4 = ld4(bet + 2 * i);
-                    float2 y0 = tc::fma2(tc::fma2(x2[i], rs2, nm2), make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
-                    float2 y1 = tc::fma2(tc::fma2(x2[i + 1], rs2, nm2), make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
-                    tc::split_pair_trunc(fmaxf(y0.x, 0.f), fmaxf(y0.y, 0.f), hi[i], lo[i]);
-                    tc::split_pair_trunc(fmaxf(y1.x, 0.f), fmaxf(y1.y, 0.f), hi[i + 1], lo[i + 1]);
-                }
-                const uint32_t hid = tmem + lane_base + (mlp == 0 ? C_HIDK : C_HIDV);
-                if (mlp == 0) TRACE(role, 11);
-                tc::tmem_st16(hid + cq * 16, hi);
-                tc::tmem_st16(hid + 64 + cq * 16, lo);
-                tc::tmem_st_wait();
-                tc::tc_fence_before();
-                tc::mbar_arrive(&bars[mlp == 0 ? B_HIDK : B_HIDV]);
-                if (mlp == 0) TRACE(role, 3);
-            }
+            TRACE(role, 1);
+            layer_norm(0, preK, hidK, trow, sR);
+            TRACE(role, 2);
+            // ---- value epilogue of the previous tile (its W2v MMA ran during that tile's logits and the LayerNorm above)
+            if (tcount > 0) epilogue(ph ? 128 + tmem : 384 + tmem, ph ^ 1);
             TRACE(role, 4);
-            TileIter nx = it;
-            iter_next(d, nx);
+            // ---- value MLP
+            if (staged_v != it.u) { tc::mbar_wait(&bars[B_PSV], psv); psv ^= 1; staged_v = it.u; }
+            tc::mbar_wait(&bars[B_PREV], ph);
+            tc::tc_fence_after();
             TRACE(role, 5);
+            layer_norm(1, preV, hidV, trow, sR);
+            TRACE(role, 6);
             // ---- logits of this thread's 4 heads, segment softmax across the 32 lanes (rows) of the warp
-            float al[4];
             {
                 tc::mbar_wait(&bars[B_OUTK], ph);
                 tc::tc_fence_after();
+                TRACE(role, 7);
                 uint32_t vv[32];
-                tc::tmem_ld32_nowait(tmem + lane_base + C_OUT + cq * 32, vv);
+                tc::tmem_ld32_nowait(preK + lane_base + cq * 32, vv);
                 tc::tmem_ld_wait();
                 const float* qrow = sQ + wq * 128 + cq * 32;
                 const float* b2 = sB2 + cq * 32;
@@ -426,30 +475,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
 #pragma unroll
                 for (int h = 0; h < 4; h++) al[h] *= __frcp_rn(sm[h]);
             }
-            TRACE(role, 6);
-            // ---- alpha-weighted sum of the value rows over the segment (lanes), residual add into h_bond
-            {
-                tc::mbar_wait(&bars[B_OUTV], ph);
-                tc::tc_fence_after();
-                uint32_t vu[32];
-                tc::tmem_ld32_nowait(tmem + lane_base + C_OUT + 128 + cq * 32, vu);
-                tc::tmem_ld_wait();
-                // the accumulators of this tile are in registers now: release TMEM so that the next tile's angle MMA (and its
-                // latency) overlaps the reduction below
-                tc::tc_fence_before();
-                tc::mbar_arrive(&bars[B_FREE]);
-                float v[32];
-#pragma unroll
-                for (int i = 0; i < 32; i++) v[i] = al[i >> 3] * __uint_as_float(vu[i]);   // alpha is 0 on padded rows
-                const float o = transpose_reduce32(v, lane);
-                if (sg.valid) {
-                    const int c = cq * 32 + lane;
-                    a.hb[(size_t)sg.eji * 128 + c] += o + sB2[128 + c];     // sum(alpha) = 1; residual (uni_denoiser.py:285)
-                }
-            }
-            TRACE(role, 7);
-            it = nx; ph ^= 1; buf ^= 1; tcount++;
+            TRACE(role, 8);
+            prev_valid = sg.valid; prev_eji = sg.eji;
+            iter_next(d, it);
+            tcount++;
         }
+        // drain: value epilogue of the last tile
+        if (tcount > 0) epilogue(((tcount - 1) & 1) ? 384 + tmem : 128 + tmem, (tcount - 1) & 1);
     }
     tc::tc_fence_before();
     __syncthreads();
