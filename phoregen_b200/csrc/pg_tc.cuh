@@ -160,6 +160,21 @@ __device__ __forceinline__ void split_pair_trunc(float x0, float x1, uint32_t& h
     const float r0 = x0 - __uint_as_float(b0 & 0xFFFF0000u), r1 = x1 - __uint_as_float(b1 & 0xFFFF0000u);
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));   // upper half <- r1, lower half <- r0
 }
+// ReLU fused into the split: hi = bf16_rz(max(y, 0)) and lo = bf16_rn(max(y - hi, 0)), one packed cvt each.
+// For y < 0 both are 0; for y >= 0 truncation gives hi <= y, so the second ReLU is a no-op.  Same error bound as above.
+__device__ __forceinline__ void split_pair_relu(float2 y, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(y.y), "f"(y.x));
+    float2 hf = make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xFFFF0000u));
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&y)), "l"(*reinterpret_cast<unsigned long long*>(&hf)));
+    const float2 d = *reinterpret_cast<float2*>(&r);
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d.y), "f"(d.x));
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }

@@ -386,8 +386,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
                 const float4 g4 = ld4(gam + 2 * i), b4 = ld4(bet + 2 * i);
                 float2 y0 = tc::fma2(tc::fma2(x2[i], rs2, nm2), make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
                 float2 y1 = tc::fma2(tc::fma2(x2[i + 1], rs2, nm2), make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
-                tc::split_pair_trunc(fmaxf(y0.x, 0.f), fmaxf(y0.y, 0.f), hi[i], lo[i]);
-                tc::split_pair_trunc(fmaxf(y1.x, 0.f), fmaxf(y1.y, 0.f), hi[i + 1], lo[i + 1]);
+                tc::split_pair_relu(y0, hi[i], lo[i]);
+                tc::split_pair_relu(y1, hi[i + 1], lo[i + 1]);
             }
             tc::tmem_st16(hid + lane_base + cq * 16, hi);
             tc::tmem_st16(hid + lane_base + 64 + cq * 16, lo);
@@ -404,7 +404,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             tc::tmem_ld_wait();
             float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; i++) v[i] = al[i >> 3] * __uint_as_float(vu[i]);   // alpha is 0 on padded rows
+            for (int i = 0; i < 32; i += 2) {                                           // alpha is 0 on padded rows
+                const float2 pr = tc::mul2(make_float2(al[i >> 3], al[i >> 3]), make_float2(__uint_as_float(vu[i]), __uint_as_float(vu[i + 1])));
+                v[i] = pr.x; v[i + 1] = pr.y;
+            }
             const float o = transpose_reduce32(v, lane);
             if (prev_valid) {
                 const int c = cq * 32 + lane;
@@ -446,18 +449,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
                 uint32_t vv[32];
                 tc::tmem_ld32_nowait(preK + lane_base + cq * 32, vv);
                 tc::tmem_ld_wait();
+                // the key bias b2k shifts all logits of a (segment, head) by the same q . b: softmax-invariant, dropped
                 const float* qrow = sQ + wq * 128 + cq * 32;
-                const float* b2 = sB2 + cq * 32;
+                constexpr float kScale = kInvSqrtD * 1.4426950408889634f;      // logits in log2 units -> ex2 directly
 #pragma unroll
                 for (int h = 0; h < 4; h++) {
-                    float sa = 0.f, sb = 0.f;
                     const int o = h * 8;
-                    const float4 qa = ld4(qrow + h * 8), qb = ld4(qrow + h * 8 + 4), ba = ld4(b2 + h * 8), bb = ld4(b2 + h * 8 + 4);
-                    sa = fmaf(qa.x, __uint_as_float(vv[o]) + ba.x, sa); sb = fmaf(qa.y, __uint_as_float(vv[o + 1]) + ba.y, sb);
-                    sa = fmaf(qa.z, __uint_as_float(vv[o + 2]) + ba.z, sa); sb = fmaf(qa.w, __uint_as_float(vv[o + 3]) + ba.w, sb);
-                    sa = fmaf(qb.x, __uint_as_float(vv[o + 4]) + bb.x, sa); sb = fmaf(qb.y, __uint_as_float(vv[o + 5]) + bb.y, sb);
-                    sa = fmaf(qb.z, __uint_as_float(vv[o + 6]) + bb.z, sa); sb = fmaf(qb.w, __uint_as_float(vv[o + 7]) + bb.w, sb);
-                    al[h] = rowvalid ? (sa + sb) * kInvSqrtD : -INFINITY;
+                    const float4 qa = ld4(qrow + h * 8), qb = ld4(qrow + h * 8 + 4);
+                    float2 s0 = tc::mul2(make_float2(qa.x, qa.y), make_float2(__uint_as_float(vv[o]), __uint_as_float(vv[o + 1])));
+                    float2 s1 = tc::mul2(make_float2(qb.x, qb.y), make_float2(__uint_as_float(vv[o + 4]), __uint_as_float(vv[o + 5])));
+                    s0 = tc::fma2(make_float2(qa.z, qa.w), make_float2(__uint_as_float(vv[o + 2]), __uint_as_float(vv[o + 3])), s0);
+                    s1 = tc::fma2(make_float2(qb.z, qb.w), make_float2(__uint_as_float(vv[o + 6]), __uint_as_float(vv[o + 7])), s1);
+                    s0 = tc::add2(s0, s1);
+                    al[h] = rowvalid ? (s0.x + s0.y) * kScale : -INFINITY;
                 }
                 float mx[4], sm[4];
 #pragma unroll
@@ -467,7 +471,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
 #pragma unroll
                     for (int h = 0; h < 4; h++) mx[h] = fmaxf(mx[h], __shfl_xor_sync(PG_FULL, mx[h], o));
 #pragma unroll
-                for (int h = 0; h < 4; h++) { al[h] = rowvalid ? __expf(al[h] - mx[h]) : 0.f; sm[h] = al[h]; }
+                for (int h = 0; h < 4; h++) { al[h] = rowvalid ? tc::ex2_approx(al[h] - mx[h]) : 0.f; sm[h] = al[h]; }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
