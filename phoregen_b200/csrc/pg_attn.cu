@@ -318,6 +318,7 @@ __global__ void __launch_bounds__(128, 4) bond_attn_kernel(BondAttnArgs a) {
     const int ctx0 = d.ctx_off[g] + d.g_p[g];
     const int v = ctx0 + il;
     const int R = n - 1;
+    if (a.tc_max_rows > 0 && R >= 1 && R <= a.tc_max_rows) return;
     const long long e0 = d.eoff[g] + (long long)il * (n - 1);
     {
         float4 qt[16];

@@ -36,7 +36,22 @@ struct BondAttnArgs {
     AttnW w;
     float* out;              // node mode [N,128]; pos mode [N,3]
     int maxr;
+    int tc_max_rows;         // > 0: atoms with 1 <= n-1 <= tc_max_rows are skipped (they ran on the tcgen05 kernel)
 };
+
+// tcgen05 version of the bond-graph attention (pg_bond_tc.cu): same inputs plus the bf16 hi/lo second-Linear weights
+struct BondTcArgs {
+    PlanDev d;
+    const float* x;
+    NodeCols nc;
+    const float* B; long long ldb; int b_k, b_v;
+    const float* q;
+    AttnW w;
+    const uint16_t *w2k_bf, *w2v_bf;       // [hi|lo][128][128] and [hi|lo][128 | 16][128] bf16, K-major
+    float* out;
+};
+constexpr int PG_BOND_TC_MAX_ROWS = 32;    // one TMEM lane quarter per segment
+int pg_launch_bond_tc(const BondTcArgs& a, int pos, int num_sms, cudaStream_t s);
 
 struct TripArgs {
     PlanDev d;

@@ -1,0 +1,355 @@
+// NodeUpdateLayer / PosUpdateLayer over the complete ligand bond graph (uni_denoiser.py:284,294) on the 5th-gen
+// tensor cores.  Same tile shape and thread mapping as the triplet kernel (pg_trip_tc.cu):
+//
+//   tile   = 4 ligand atoms (segments) x 32 rows; TMEM lane = triplet row = incoming bond edge j -> i (n-1 <= 32 rows)
+//   thread = (row, 32-channel quarter): 16 row warps, warp w -> lane quarter w & 3 (segment), channel quarter w >> 2
+//
+//   1. pre-activation of the key / value MLP = dst-node partial + src-node partial + per-edge partial (three global
+//      rows, the first Linear was applied by the node / edge GEMMs), LayerNorm + ReLU thread-locally (statistics of
+//      the four channel quarters meet in shared memory), bf16 hi/lo split, tcgen05.st -> A operand in TMEM
+//   2. second Linear: 24 tcgen05.mma (M128 N128 K16; value MLP of the position layer: N16), B = W2 bf16 hi/lo resident
+//      in shared memory (128B swizzle), fp32 accumulators in TMEM
+//   3. logits = q . k per head (thread-local), segment softmax across the 32 lanes, then
+//        node layer: alpha-weighted sum of the value rows (butterfly transpose-reduce)          -> out[i, 128]
+//        pos  layer: sum_h alpha_h v_h per row, times rel_x, summed over the rows, mean over heads -> out[i, 3]
+//
+// Software pipeline across tiles, as in the triplet kernel:  LN-k(t) | epilogue(t-1) | LN-v(t) | logits(t)  on the row
+// warps while the tensor pipe runs W2k(t) | W2v(t).  TMEM: hid_k [0,128) out_k [128,256) hid_v [256,384) out_v [384,512).
+// Atoms whose segment does not fit a lane quarter (n-1 > 32) or has no rows are left to the fp32 kernel (pg_attn.cu).
+#include <algorithm>
+#include "pg_attn.h"
+#include "pg_tc.cuh"
+
+namespace {
+constexpr int W_TILE = 32768;               // one [128 x 128] bf16 matrix in two 128B-swizzled K blocks
+constexpr int SM_W = 4 * W_TILE;            // (k,v) x (hi,lo)
+constexpr int SM_STAT = 128 * 16 * 4;       // [2 mlp][128 rows][4 quarters][2] partial LayerNorm sums
+constexpr int SM_RED = 4 * 4 * 4 * 4;       // pos layer: [segment][quarter][4] partial coordinate updates
+constexpr int XP_LD = 36;                   // padded row stride (floats) of a warp's transpose tile [32 rows][32 channels]
+constexpr int SM_XP = 16 * 32 * XP_LD * 4;  // one tile per row warp
+constexpr int SM_TOTAL = SM_W + SM_XP + SM_STAT + SM_RED + 5 * 128 * 4 /*ln + b2v*/ + 128 /*barriers*/ + 1024 /*alignment*/;
+constexpr float kInvSqrtD = 0.35355339059327373f;
+constexpr int ROW_WARPS = 16;
+constexpr int MMA_WARP = ROW_WARPS;
+constexpr int NTHREADS = (ROW_WARPS + 4) * 32;
+constexpr int ROW_THREADS = ROW_WARPS * 32;
+enum { B_HIDK = 0, B_HIDV, B_OUTK, B_OUTV, B_COUNT };
+
+struct SegInfo {
+    bool valid;
+    int n, il, v, ctx0;
+    long long e0;
+};
+__device__ __forceinline__ SegInfo seg_info(const PlanDev& d, long long tile, int wq) {
+    SegInfo s;
+    const long long u = tile * 4 + wq;
+    s.valid = false; s.n = 2; s.il = 0; s.v = 0; s.ctx0 = 0; s.e0 = 0;
+    if (u < d.Nl) {
+        const int g = d.lig_graph[u];
+        s.n = d.g_n[g]; s.il = (int)(u - d.lig_off[g]);
+        s.ctx0 = d.ctx_off[g] + d.g_p[g];
+        s.v = s.ctx0 + s.il;
+        s.e0 = d.eoff[g] + (long long)s.il * (s.n - 1);
+        s.valid = s.n - 1 >= 1 && s.n - 1 <= PG_BOND_TC_MAX_ROWS;
+    }
+    return s;
+}
+
+template <int POS>
+__global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sW = smem;
+    float* sXp = (float*)(sW + SM_W);
+    float* sStat = sXp + SM_XP / 4;
+    float* sRed = sStat + SM_STAT / 4;
+    float* sLn = sRed + SM_RED / 4;                 // gk, bk, gv, bv
+    float* sB2 = sLn + 4 * 128;                     // b2v (128 or 16)
+    uint64_t* bars = (uint64_t*)(sB2 + 128);
+    uint32_t* tmem_slot = (uint32_t*)(bars + B_COUNT);
+    const PlanDev& d = a.d;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wq = warp & 3;
+    constexpr int NV = POS ? 16 : 128;              // outputs of the value MLP's second Linear
+
+    if (warp == MMA_WARP) tc::tmem_alloc<512>(tmem_slot);
+    if (tid == 0) {
+        tc::mbar_init(&bars[B_HIDK], ROW_THREADS); tc::mbar_init(&bars[B_HIDV], ROW_THREADS);
+        tc::mbar_init(&bars[B_OUTK], 1); tc::mbar_init(&bars[B_OUTV], 1);
+        tc::fence_barrier_init();
+    }
+    // ---- resident weights: 16-byte chunks [mat 4][n][chunk 16] -> 128B-swizzled K-major tiles
+    for (int idx = tid; idx < 4 * 128 * 16; idx += NTHREADS) {
+        const int mat = idx >> 11, n = (idx >> 4) & 127, c = idx & 15;
+        const bool isv = mat >> 1;
+        if (isv && n >= NV) continue;
+        const uint16_t* src = (isv ? a.w2v_bf : a.w2k_bf) + ((size_t)(mat & 1) * (isv ? NV : 128) + n) * 128 + c * 8;
+        const uint32_t dst = tc::smem_u32(sW) + mat * W_TILE + (c >> 3) * 16384 + tc::sw128_chunk(n, c & 7);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    if (tid < 128) {
+        sLn[tid] = a.w.lnk_g[tid]; sLn[128 + tid] = a.w.lnk_b[tid]; sLn[256 + tid] = a.w.lnv_g[tid]; sLn[384 + tid] = a.w.lnv_b[tid];
+        if (tid < NV) sB2[tid] = a.w.b2v[tid];
+    }
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+    constexpr uint32_t C_HIDK = 0, C_OUTK = 128, C_HIDV = 256, C_OUTV = 384;
+    const long long ntiles = (d.Nl + 3) / 4;
+
+    if (warp >= MMA_WARP) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (warp == MMA_WARP) {
+            // ================= MMA issue =================
+            constexpr uint32_t idesc_k = tc::umma_idesc_bf16(128, 128);
+            constexpr uint32_t idesc_v = tc::umma_idesc_bf16(128, NV);
+            const uint32_t sW_u32 = tc::smem_u32(sW);
+            uint32_t ph = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
+#pragma unroll
+                for (int mlp = 0; mlp < 2; mlp++) {
+                    tc::mbar_wait(&bars[mlp == 0 ? B_HIDK : B_HIDV], ph);
+                    tc::tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t hid = tmem + (mlp == 0 ? C_HIDK : C_HIDV);
+                        const uint32_t dcol = tmem + (mlp == 0 ? C_OUTK : C_OUTV);
+                        uint32_t acc = 0;
+#pragma unroll
+                        for (int combo = 0; combo < 3; combo++) {       // hi*hi, hi*lo, lo*hi
+                            const uint32_t abase = hid + (combo == 2 ? 64 : 0);
+                            const uint32_t bbase = sW_u32 + (mlp * 2 + (combo == 1 ? 1 : 0)) * W_TILE;
+#pragma unroll
+                            for (int ks = 0; ks < 8; ks++) {
+                                const uint64_t bd = tc::umma_desc_sw128(bbase + (ks >> 2) * 16384 + (ks & 3) * 32);
+                                tc::umma_bf16_ts(dcol, abase + ks * 8, bd, mlp == 0 ? idesc_k : idesc_v, acc);
+                                acc = 1;
+                            }
+                        }
+                        tc::umma_commit(&bars[mlp == 0 ? B_OUTK : B_OUTV]);
+                    }
+                    __syncwarp();
+                }
+            }
+        } else {
+            // ================= idle warps: pull the next tile's per-edge rows (the only HBM stream) into L2 =================
+            const int pt = tid - (MMA_WARP + 1) * 32;      // 0..95
+            uint32_t ph = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
+                const long long nt = tile + gridDim.x;
+                if (nt < ntiles) {
+                    for (int s4 = 0; s4 < 4; s4++) {
+                        const SegInfo sg = seg_info(d, nt, s4);
+                        if (!sg.valid) continue;
+                        for (int r = pt; r < sg.n - 1; r += 96) {
+                            const float* row = a.B + (size_t)(sg.e0 + r) * a.ldb + a.b_k;
+                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row), "r"((a.b_v - a.b_k + 128) * 4) : "memory");
+                        }
+                    }
+                }
+                tc::mbar_wait(&bars[B_HIDV], ph);          // pace: one tile ahead of the row warps
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        // ================= row warps: thread = (row, channel quarter) =================
+        const int cq = warp >> 2;
+        float al[4] = {0.f, 0.f, 0.f, 0.f};
+        bool prev_valid = false;
+        int prev_v = 0;
+        float rel0 = 0.f, rel1 = 0.f, rel2 = 0.f;   // pos layer: x[dst] - x[src] of the previous tile's row
+        // pre-activation slice (dst node + src node + bond edge partials) -> LayerNorm + ReLU -> bf16 hi/lo A operand
+        auto layer_norm = [&](int mlp, const SegInfo& sg, uint32_t hid) {
+            // Coalesced gather: 8 lanes read the 128-byte slice of one row (4 rows per instruction), the three partial rows
+            // are summed in that layout and transposed through a per-warp shared tile to the row-per-lane layout of TMEM.
+            // (A row-per-lane global read would cost 32 L1 wavefronts per instruction instead of 4.)
+            {
+                const int sr = lane >> 3, ch = (lane & 7) * 4, c0 = cq * 32 + ch;
+                const int nrow = sg.valid ? sg.n - 1 : 0;
+                const float4 d4 = ldg4(a.nc.A + (size_t)sg.v * a.nc.lda + (mlp == 0 ? a.nc.dst_k : a.nc.dst_v) + c0);
+                const float* ps = a.nc.A + (mlp == 0 ? a.nc.src_k : a.nc.src_v) + c0;
+                const float* pb = a.B + (mlp == 0 ? a.b_k : a.b_v) + c0;
+                // unconditional loads (padded rows re-read row 0 and are masked by alpha = 0): all 16 requests of the phase
+                // are in flight together instead of one round trip per row group
+                float4 t[8], u[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int row = (i * 4 + sr) < nrow ? (i * 4 + sr) : 0;
+                    t[i] = ld4(pb + (size_t)(sg.e0 + row) * a.ldb);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int row = (i * 4 + sr) < nrow ? (i * 4 + sr) : 0;
+                    u[i] = ldg4(ps + (size_t)(sg.ctx0 + row + (row >= sg.il)) * a.nc.lda);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) t[i] = f4add(t[i], u[i]);
+                float* xp = sXp + warp * (32 * XP_LD);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; i++) st4(xp + (i * 4 + sr) * XP_LD + ch, f4add(t[i], d4));
+                __syncwarp();
+            }
+            const float* xrow = sXp + warp * (32 * XP_LD) + lane * XP_LD;
+            float2 x2[16];
+            float2 s1 = make_float2(0.f, 0.f), s2 = s1, s1b = s1, s2b = s1;
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                const float4 e4 = ld4(xrow + 2 * i);
+                x2[i] = make_float2(e4.x, e4.y);
+                x2[i + 1] = make_float2(e4.z, e4.w);
+                s1 = tc::add2(s1, x2[i]); s1b = tc::add2(s1b, x2[i + 1]);
+                s2 = tc::fma2(x2[i], x2[i], s2); s2b = tc::fma2(x2[i + 1], x2[i + 1], s2b);
+            }
+            s1 = tc::add2(s1, s1b); s2 = tc::add2(s2, s2b);
+            // combine with the other three channel quarters of the same row (warps w +- 4k, same lane).  The barrier also
+            // orders this lane quarter's reads of the previous tile's accumulators before the hid columns are rewritten.
+            float* st = sStat + ((mlp * 128 + wq * 32 + lane) * 4) * 2;
+            *reinterpret_cast<float2*>(st + cq * 2) = make_float2(s1.x + s1.y, s2.x + s2.y);
+            asm volatile("bar.sync %0, 128;" ::"r"(3 + wq) : "memory");
+            const float4 sa4 = ld4(st), sb4 = ld4(st + 4);
+            const float mu = ((sa4.x + sa4.z) + (sb4.x + sb4.z)) * (1.0f / 128.0f);
+            const float rstd = rsqrtf(fmaxf(fmaf(-mu, mu, ((sa4.y + sa4.w) + (sb4.y + sb4.w)) * (1.0f / 128.0f)), 0.f) + 1e-5f);
+            const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mu * rstd, -mu * rstd);
+            const float* gam = sLn + mlp * 256 + cq * 32;
+            const float* bet = gam + 128;
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                const float4 g4 = ld4(gam + 2 * i), b4 = ld4(bet + 2 * i);
+                float2 y0 = tc::fma2(tc::fma2(x2[i], rs2, nm2), make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
+                float2 y1 = tc::fma2(tc::fma2(x2[i + 1], rs2, nm2), make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
+                tc::split_pair_relu(y0, hi[i], lo[i]);
+                tc::split_pair_relu(y1, hi[i + 1], lo[i + 1]);
+            }
+            tc::tmem_st16(hid + lane_base + cq * 16, hi);
+            tc::tmem_st16(hid + lane_base + 64 + cq * 16, lo);
+            tc::tmem_st_wait();
+            tc::tc_fence_before();
+            tc::mbar_arrive(&bars[mlp == 0 ? B_HIDK : B_HIDV]);
+        };
+        auto epilogue = [&](uint32_t parity) {
+            tc::mbar_wait(&bars[B_OUTV], parity);
+            tc::tc_fence_after();
+            if (POS == 0) {
+                uint32_t vu[32];
+                tc::tmem_ld32_nowait(tmem + C_OUTV + lane_base + cq * 32, vu);
+                tc::tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {                                           // alpha is 0 on padded rows
+                    const float2 pr = tc::mul2(make_float2(al[i >> 3], al[i >> 3]), make_float2(__uint_as_float(vu[i]), __uint_as_float(vu[i + 1])));
+                    v[i] = pr.x; v[i + 1] = pr.y;
+                }
+                const float o = transpose_reduce32(v, lane);
+                if (prev_valid) {
+                    const int c = cq * 32 + lane;
+                    a.out[(size_t)prev_v * 128 + c] = o + sB2[c];                          // sum(alpha) = 1
+                }
+            } else {
+                float vh[4];
+                tc::tmem_ld4(tmem + C_OUTV + lane_base + cq * 4, vh);
+                float c = 0.f;
+#pragma unroll
+                for (int h = 0; h < 4; h++) c = fmaf(al[h], vh[h] + sB2[cq * 4 + h], c);     // alpha is 0 on padded rows
+                float p0 = c * rel0, p1 = c * rel1, p2 = c * rel2;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    p0 += __shfl_xor_sync(PG_FULL, p0, o); p1 += __shfl_xor_sync(PG_FULL, p1, o); p2 += __shfl_xor_sync(PG_FULL, p2, o);
+                }
+                float* rd = sRed + (wq * 4 + cq) * 4;
+                if (lane == 0) { rd[0] = p0; rd[1] = p1; rd[2] = p2; }
+                asm volatile("bar.sync %0, 128;" ::"r"(3 + wq) : "memory");
+                if (cq == 0 && lane < 3 && prev_valid) {
+                    const float* r4 = sRed + wq * 16 + lane;
+                    a.out[(size_t)prev_v * 3 + lane] = ((r4[0] + r4[4]) + (r4[8] + r4[12])) * (1.0f / 16.0f);
+                }
+            }
+        };
+        uint32_t ph = 0;
+        bool any = false;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
+            const SegInfo sg = seg_info(d, tile, wq);
+            const bool rowvalid = sg.valid && lane < sg.n - 1;
+            const int r = rowvalid ? lane : 0;
+            // ---- key MLP
+            layer_norm(0, sg, tmem + C_HIDK);
+            // ---- value epilogue of the previous tile (its W2v MMA ran during that tile's logits and the LayerNorm above)
+            if (any) epilogue(ph ^ 1);
+            // ---- value MLP
+            layer_norm(1, sg, tmem + C_HIDV);
+            // ---- logits of this thread's 4 heads, segment softmax across the 32 lanes (rows) of the warp
+            {
+                // the key bias b2k shifts all logits of a (segment, head) by the same q . b: softmax-invariant, dropped
+                const float* qrow = a.q + (size_t)sg.v * 128 + cq * 32;
+                float4 qv[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) qv[i] = ldg4(qrow + i * 4);
+                tc::mbar_wait(&bars[B_OUTK], ph);
+                tc::tc_fence_after();
+                uint32_t vv[32];
+                tc::tmem_ld32_nowait(tmem + C_OUTK + lane_base + cq * 32, vv);
+                tc::tmem_ld_wait();
+                constexpr float kScale = kInvSqrtD * 1.4426950408889634f;      // logits in log2 units -> ex2 directly
+#pragma unroll
+                for (int h = 0; h < 4; h++) {
+                    const int o = h * 8;
+                    const float4 qa = qv[2 * h], qb = qv[2 * h + 1];
+                    float2 s0 = tc::mul2(make_float2(qa.x, qa.y), make_float2(__uint_as_float(vv[o]), __uint_as_float(vv[o + 1])));
+                    float2 s1 = tc::mul2(make_float2(qb.x, qb.y), make_float2(__uint_as_float(vv[o + 4]), __uint_as_float(vv[o + 5])));
+                    s0 = tc::fma2(make_float2(qa.z, qa.w), make_float2(__uint_as_float(vv[o + 2]), __uint_as_float(vv[o + 3])), s0);
+                    s1 = tc::fma2(make_float2(qb.z, qb.w), make_float2(__uint_as_float(vv[o + 6]), __uint_as_float(vv[o + 7])), s1);
+                    s0 = tc::add2(s0, s1);
+                    al[h] = rowvalid ? (s0.x + s0.y) * kScale : -INFINITY;
+                }
+                float mx[4], sm[4];
+#pragma unroll
+                for (int h = 0; h < 4; h++) mx[h] = al[h];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int h = 0; h < 4; h++) mx[h] = fmaxf(mx[h], __shfl_xor_sync(PG_FULL, mx[h], o));
+#pragma unroll
+                for (int h = 0; h < 4; h++) { al[h] = rowvalid ? tc::ex2_approx(al[h] - mx[h]) : 0.f; sm[h] = al[h]; }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int h = 0; h < 4; h++) sm[h] += __shfl_xor_sync(PG_FULL, sm[h], o);
+#pragma unroll
+                for (int h = 0; h < 4; h++) al[h] = rowvalid ? al[h] * __frcp_rn(sm[h]) : 0.f;
+            }
+            prev_valid = sg.valid; prev_v = sg.v;
+            if (POS) {
+                const int sj = sg.ctx0 + r + (r >= sg.il);
+                rel0 = a.x[(size_t)sg.v * 3] - a.x[(size_t)sj * 3];                        // rel_x = x[dst] - x[src]
+                rel1 = a.x[(size_t)sg.v * 3 + 1] - a.x[(size_t)sj * 3 + 1];
+                rel2 = a.x[(size_t)sg.v * 3 + 2] - a.x[(size_t)sj * 3 + 2];
+            }
+            any = true;
+        }
+        if (any) epilogue(ph ^ 1);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) { tc::tc_fence_after(); tc::tmem_dealloc<512>(tmem); }
+}
+}  // namespace
+
+int pg_launch_bond_tc(const BondTcArgs& a, int pos, int num_sms, cudaStream_t s) {
+    if (a.d.Nl <= 0) return PG_OK;
+    static bool init = false;
+    if (!init) {
+        PG_CUDA_CHECK(cudaFuncSetAttribute(bond_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        PG_CUDA_CHECK(cudaFuncSetAttribute(bond_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        init = true;
+    }
+    const long long ntiles = (a.d.Nl + 3) / 4;
+    const unsigned grid = (unsigned)std::min<long long>(ntiles, num_sms);
+    if (pos == 0) bond_tc_kernel<0><<<grid, NTHREADS, SM_TOTAL, s>>>(a);
+    else bond_tc_kernel<1><<<grid, NTHREADS, SM_TOTAL, s>>>(a);
+    PG_LAUNCH_CHECK();
+    return PG_OK;
+}

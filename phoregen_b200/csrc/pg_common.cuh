@@ -25,7 +25,7 @@ void pg_set_error(const char* fmt, ...);
 struct PlanDev {
     int G, N, Nl, P;
     long long Eb, Ek, E3;
-    int max_n, max_p, max_ng;
+    int max_n, max_p, max_ng, min_n;
     const int* ctx_off;     // [G+1] context node offsets
     const int* lig_off;     // [G+1]
     const int* ph_off;      // [G+1]

@@ -33,11 +33,11 @@ struct Carver {
 
 struct Sizes {
     long long N, Nl, P, Eb, Ek, E3;
-    int max_n, max_p, max_ng;
+    int max_n, max_p, max_ng, min_n;
 };
 
 Sizes plan_sizes(int G, const int32_t* na, const int32_t* np) {
-    Sizes s{0, 0, 0, 0, 0, 0, 0, 0, 0};
+    Sizes s{0, 0, 0, 0, 0, 0, 0, 0, 0, 1 << 30};
     for (int g = 0; g < G; g++) {
         long long n = na[g], p = np[g], ng = n + p;
         s.Nl += n; s.P += p; s.N += ng;
@@ -45,6 +45,7 @@ Sizes plan_sizes(int G, const int32_t* na, const int32_t* np) {
         s.Ek += ng * std::min<long long>(PG_KNN, ng - 1);
         s.E3 += n * (n - 1) * std::max<long long>(n - 2, 0);
         s.max_n = std::max<int>(s.max_n, (int)n);
+        s.min_n = std::min<int>(s.min_n, (int)n);
         s.max_p = std::max<int>(s.max_p, (int)p);
         s.max_ng = std::max<int>(s.max_ng, (int)ng);
     }
@@ -141,7 +142,7 @@ extern "C" int pg_plan_create(PgPlan** out, int G, const int32_t* na, const int3
     carve(c, s, G, pl);
     PlanDev& d = pl->d;
     d.G = G; d.N = (int)s.N; d.Nl = (int)s.Nl; d.P = (int)s.P; d.Eb = s.Eb; d.Ek = s.Ek; d.E3 = s.E3;
-    d.max_n = s.max_n; d.max_p = s.max_p; d.max_ng = s.max_ng;
+    d.max_n = s.max_n; d.max_p = s.max_p; d.max_ng = s.max_ng; d.min_n = G > 0 ? s.min_n : 0;
 
     pl->n.assign(na, na + G); pl->p.assign(np, np + G);
     pl->ctx_off.assign(G + 1, 0); pl->lig_off.assign(G + 1, 0); pl->ph_off.assign(G + 1, 0);

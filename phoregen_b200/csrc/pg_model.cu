@@ -51,6 +51,7 @@ std::vector<PgSlotDesc> build_slots() {
             const bool pos = s >= 3;
             add(S + "w2v", (pos ? 16 : 128) * 128); add(S + "b2v", pos ? 16 : 128);
             if (s == 0 || s == 3) { add(S + "tab_k", 4 * 24 * 128); add(S + "tab_v", 4 * 24 * 128); }
+            if (s == 1 || s == 4) { add(S + "w2k.bf", 128 * 128); add(S + "w2v.bf", (pos ? 16 : 128) * 128); }   // bond_tc
             if (s == 2) {
                 add(S + "wrkj", 20 * 256); add(S + "wrji", 20 * 256); add(S + "wa", 13 * 256);
                 add(S + "w2k.bf", 128 * 128); add(S + "w2v.bf", 128 * 128); add(S + "wa.bf", 2 * 256 * 16 / 2);
@@ -261,6 +262,31 @@ bool use_tc_trip(const PlanDev& d) {
     return v == 1 && d.max_n >= 3;
 }
 
+// tcgen05 bond-graph attention unless PG_BOND=fp32; atoms outside its segment range take the fp32 kernel
+bool use_tc_bond() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PG_BOND"); v = (e && !strcmp(e, "fp32")) ? 0 : 1; }
+    return v == 1;
+}
+template <class W>
+int launch_bond(PgPlan* p, const BondAttnArgs& a0, const W& w, const std::string& S, int pos, cudaStream_t s) {
+    BondAttnArgs a = a0;
+    a.tc_max_rows = 0;
+    PgTimed timed(p, KC_BOND_ATTN, s);
+    if (use_tc_bond()) {
+        BondTcArgs t;
+        t.d = a.d; t.x = a.x; t.nc = a.nc; t.B = a.B; t.ldb = a.ldb; t.b_k = a.b_k; t.b_v = a.b_v; t.q = a.q; t.w = a.w;
+        t.w2k_bf = (const uint16_t*)w(S + "w2k.bf"); t.w2v_bf = (const uint16_t*)w(S + "w2v.bf"); t.out = a.out;
+        PG_TRY(pg_launch_bond_tc(t, pos, num_sms(), s));
+        p->launches++;
+        a.tc_max_rows = PG_BOND_TC_MAX_ROWS;
+        if (a.d.max_n - 1 <= PG_BOND_TC_MAX_ROWS && a.d.min_n >= 2) return PG_OK;
+    }
+    PG_TRY(pg_launch_bond_attn(a, pos, s));
+    p->launches++;
+    return PG_OK;
+}
+
 bool use_simt_gemm() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("PG_GEMM"); v = (e && !strcmp(e, "simt")) ? 1 : 0; }
@@ -340,7 +366,7 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
             a.nc = NodeCols{p->nbuf, N1_COLS, N1_NB_DK, N1_NB_SK, N1_NB_DV, N1_NB_SV};
             a.B = p->ebuf; a.ldb = E1_COLS; a.b_k = E1_NB_K; a.b_v = E1_NB_V;
             a.q = p->qn2; a.w = attn_w(w, L + "nb.", false); a.out = p->o2; a.maxr = maxr_bond;
-            { PgTimed timed(p, KC_BOND_ATTN, s); PG_TRY(pg_launch_bond_attn(a, 0, s)); } p->launches++;
+            PG_TRY(launch_bond(p, a, w, L + "nb.", 0, s));
         }
         {   // bond update over triplets (uses the old h, x); h_bond updated in place
             TripArgs a;
@@ -387,7 +413,7 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
             a.nc = NodeCols{p->nbuf, N2_COLS, N2_PB_DK, N2_PB_SK, N2_PB_DV, N2_PB_SV};
             a.B = p->ebuf; a.ldb = 256; a.b_k = 0; a.b_v = 128;
             a.q = p->qn2; a.w = attn_w(w, L + "pb.", false); a.out = p->dx2; a.maxr = maxr_bond;
-            { PgTimed timed(p, KC_BOND_ATTN, s); PG_TRY(pg_launch_bond_attn(a, 1, s)); } p->launches++;
+            PG_TRY(launch_bond(p, a, w, L + "pb.", 1, s));
         }
         pos_update_kernel<<<(unsigned)((N * 3 + 255) / 256), 256, 0, s>>>(d, p->x, p->dx1, p->dx2);
         PG_LAUNCH_CHECK(); p->launches++;
