@@ -162,38 +162,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
         int prev_v = 0;
         float rel0 = 0.f, rel1 = 0.f, rel2 = 0.f;   // pos layer: x[dst] - x[src] of the previous tile's row
         // pre-activation slice (dst node + src node + bond edge partials) -> LayerNorm + ReLU -> bf16 hi/lo A operand
-        auto layer_norm = [&](int mlp, const SegInfo& sg, uint32_t hid) {
-            // Coalesced gather: 8 lanes read the 128-byte slice of one row (4 rows per instruction), the three partial rows
-            // are summed in that layout and transposed through a per-warp shared tile to the row-per-lane layout of TMEM.
-            // (A row-per-lane global read would cost 32 L1 wavefronts per instruction instead of 4.)
+        // Coalesced gather: 8 lanes cover the 128-byte slice of one row (4 rows per instruction); the rows meet in a per-warp
+        // shared tile and are read back row-per-lane, the layout of TMEM.  (A row-per-lane global read would cost 32 L1
+        // wavefronts per instruction instead of 4.)  The per-edge rows - the only HBM stream - are requested one phase
+        // ahead with cp.async straight into the tile; padded rows re-read row 0 and are masked by alpha = 0.
+        const int sr = lane >> 3, ch = (lane & 7) * 4;
+        float* xp = sXp + warp * (32 * XP_LD);
+        auto request_edge_rows = [&](int mlp, const SegInfo& sg) {
+            const int nrow = sg.valid ? sg.n - 1 : 0;
+            const float* pb = a.B + (mlp == 0 ? a.b_k : a.b_v) + cq * 32 + ch;
+            const uint32_t dst = tc::smem_u32(xp + sr * XP_LD + ch);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int row = (i * 4 + sr) < nrow ? (i * 4 + sr) : 0;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 4 * XP_LD * 4), "l"(pb + (size_t)(sg.e0 + row) * a.ldb) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        // pre-activation slice (dst node + src node + bond edge partials) -> LayerNorm + ReLU -> bf16 hi/lo A operand;
+        // `nsg` / `nmlp`: the phase whose edge rows are requested as soon as this one has left the shared tile
+        auto layer_norm = [&](int mlp, const SegInfo& sg, uint32_t hid, bool has_next, int nmlp, const SegInfo& nsg) {
             {
-                const int sr = lane >> 3, ch = (lane & 7) * 4, c0 = cq * 32 + ch;
+                const int c0 = cq * 32 + ch;
                 const int nrow = sg.valid ? sg.n - 1 : 0;
                 const float4 d4 = ldg4(a.nc.A + (size_t)sg.v * a.nc.lda + (mlp == 0 ? a.nc.dst_k : a.nc.dst_v) + c0);
                 const float* ps = a.nc.A + (mlp == 0 ? a.nc.src_k : a.nc.src_v) + c0;
-                const float* pb = a.B + (mlp == 0 ? a.b_k : a.b_v) + c0;
-                // unconditional loads (padded rows re-read row 0 and are masked by alpha = 0): all 16 requests of the phase
-                // are in flight together instead of one round trip per row group
-                float4 t[8], u[8];
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int row = (i * 4 + sr) < nrow ? (i * 4 + sr) : 0;
-                    t[i] = ld4(pb + (size_t)(sg.e0 + row) * a.ldb);
-                }
+                float4 u[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const int row = (i * 4 + sr) < nrow ? (i * 4 + sr) : 0;
                     u[i] = ldg4(ps + (size_t)(sg.ctx0 + row + (row >= sg.il)) * a.nc.lda);
                 }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
-                for (int i = 0; i < 8; i++) t[i] = f4add(t[i], u[i]);
-                float* xp = sXp + warp * (32 * XP_LD);
-                __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 8; i++) st4(xp + (i * 4 + sr) * XP_LD + ch, f4add(t[i], d4));
+                for (int i = 0; i < 8; i++) {
+                    float* pxy = xp + (i * 4 + sr) * XP_LD + ch;
+                    st4(pxy, f4add(f4add(ld4(pxy), u[i]), d4));
+                }
                 __syncwarp();
             }
-            const float* xrow = sXp + warp * (32 * XP_LD) + lane * XP_LD;
+            const float* xrow = xp + lane * XP_LD;
             float2 x2[16];
             float2 s1 = make_float2(0.f, 0.f), s2 = s1, s1b = s1, s2b = s1;
 #pragma unroll
@@ -204,6 +212,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
                 s1 = tc::add2(s1, x2[i]); s1b = tc::add2(s1b, x2[i + 1]);
                 s2 = tc::fma2(x2[i], x2[i], s2); s2b = tc::fma2(x2[i + 1], x2[i + 1], s2b);
             }
+            __syncwarp();
+            if (has_next) request_edge_rows(nmlp, nsg);
             s1 = tc::add2(s1, s1b); s2 = tc::add2(s2, s2b);
             // combine with the other three channel quarters of the same row (warps w +- 4k, same lane).  The barrier also
             // orders this lane quarter's reads of the previous tile's accumulators before the hid columns are rewritten.
@@ -271,16 +281,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
         };
         uint32_t ph = 0;
         bool any = false;
+        SegInfo sg = seg_info(d, blockIdx.x, wq);
+        request_edge_rows(0, sg);
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
-            const SegInfo sg = seg_info(d, tile, wq);
             const bool rowvalid = sg.valid && lane < sg.n - 1;
             const int r = rowvalid ? lane : 0;
+            const bool more = tile + gridDim.x < ntiles;
+            const SegInfo nsg = seg_info(d, more ? tile + gridDim.x : tile, wq);
             // ---- key MLP
-            layer_norm(0, sg, tmem + C_HIDK);
+            layer_norm(0, sg, tmem + C_HIDK, true, 1, sg);
             // ---- value epilogue of the previous tile (its W2v MMA ran during that tile's logits and the LayerNorm above)
             if (any) epilogue(ph ^ 1);
             // ---- value MLP
-            layer_norm(1, sg, tmem + C_HIDV);
+            layer_norm(1, sg, tmem + C_HIDV, more, 0, nsg);
             // ---- logits of this thread's 4 heads, segment softmax across the 32 lanes (rows) of the warp
             {
                 // the key bias b2k shifts all logits of a (segment, head) by the same q . b: softmax-invariant, dropped
@@ -329,6 +342,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
                 rel2 = a.x[(size_t)sg.v * 3 + 2] - a.x[(size_t)sj * 3 + 2];
             }
             any = true;
+            sg = nsg;
         }
         if (any) epilogue(ph ^ 1);
     }
