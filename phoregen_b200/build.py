@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libphoregen_b200.so")
-SOURCES = ["pg_graph.cu", "pg_gemm.cu", "pg_gemm_tc.cu", "pg_attn.cu", "pg_trip_tc.cu", "pg_bond_tc.cu", "pg_model.cu", "pg_transition.cu"]
+SOURCES = ["pg_graph.cu", "pg_gemm.cu", "pg_gemm_tc.cu", "pg_attn.cu", "pg_trip_tc.cu", "pg_bond_tc.cu", "pg_knn_tc.cu", "pg_model.cu", "pg_transition.cu"]
 EXTRA = os.environ.get("PG_NVCC_EXTRA", "").split()     # e.g. PG_NVCC_EXTRA=-DPG_TRIP_TRACE for the phase tracer
 NVCC_FLAGS = [*EXTRA, 
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -50,6 +50,23 @@ struct BondTcArgs {
     const uint16_t *w2k_bf, *w2v_bf;       // [hi|lo][128][128] and [hi|lo][128 | 16][128] bf16, K-major
     float* out;
 };
+// tcgen05 version of the kNN-graph attention (pg_knn_tc.cu): key pass + value pass
+struct KnnTcArgs {
+    PlanDev d;
+    const float* x;          // [N,3]
+    const float* comb;       // [N,3]
+    const int* knn_src;      // [Ek]
+    const float* ew;         // [Ek]
+    NodeCols nc;
+    const float* q;          // [N,128]
+    AttnW w;
+    const uint16_t *w2k_bf, *w2v_bf;       // [hi|lo][128][128] and [hi|lo][128 | 16][128] bf16, K-major
+    const uint16_t *tabk_bf, *tabv_bf;     // [hi|lo][128][96] bf16: first-Linear slices of the 4 edge types x 24 features
+    float* alpha;            // scratch [Ek,16]: softmax weights times e_w
+    float* alpha_sum;        // scratch [N,16]: their per-head sums
+    float* out;              // node mode [N,128]; pos mode [N,3]
+};
+int pg_launch_knn_tc(const KnnTcArgs& a, int pos, int num_sms, cudaStream_t s);
 constexpr int PG_BOND_TC_MAX_ROWS = 32;    // one TMEM lane quarter per segment
 int pg_launch_bond_tc(const BondTcArgs& a, int pos, int num_sms, cudaStream_t s);
 

@@ -71,7 +71,7 @@ void carve(Carver& c, const Sizes& s, int G, PgPlan* pl) {
     float* dx1 = F(s.N * 3 + 4); float* dx2 = F(s.N * 3 + 4);
     float* ebuf = F(s.Eb * 640);
     float* qt = F(s.Eb * 128);
-    float* rbuf = F(s.Eb * 256); float* pbuf2 = F(s.Eb * 256);
+    float* rbuf = F(s.Eb * 256); float* pbuf2 = F(s.Eb * 256); float* abuf = F(s.Ek * 16 + s.N * 16);
     float* ew = F(s.Ek); float* comb = F(s.N * 3 + 4);
     int* knn_src = I(s.Ek);
     float* pbuf = F(s.P * 640); float* pq = F(s.P * 128); float* pemb = F(s.P * 128);
@@ -83,7 +83,7 @@ void carve(Carver& c, const Sizes& s, int G, PgPlan* pl) {
         d.perm = perm; d.edge_graph = edge_graph; d.esrc_node = esrc; d.edst_node = edst;
         pl->inv_perm = inv_perm; pl->flag = flag;
         pl->h = h; pl->x = x; pl->hb = hb; pl->nbuf = nbuf; pl->qn1 = qn1; pl->qn2 = qn2; pl->o1 = o1; pl->o2 = o2;
-        pl->dx1 = dx1; pl->dx2 = dx2; pl->ebuf = ebuf; pl->qt = qt; pl->rbuf = rbuf; pl->pbuf2 = pbuf2; pl->ew = ew;
+        pl->dx1 = dx1; pl->dx2 = dx2; pl->ebuf = ebuf; pl->qt = qt; pl->rbuf = rbuf; pl->pbuf2 = pbuf2; pl->abuf = abuf; pl->ew = ew;
         pl->comb = comb; pl->knn_src = knn_src; pl->pbuf = pbuf; pl->pq = pq; pl->pemb = pemb; pl->gcnt = gcnt;
     }
 }

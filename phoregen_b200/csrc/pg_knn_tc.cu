@@ -1,0 +1,452 @@
+// NodeUpdateLayer / PosUpdateLayer over the joint ligand + pharmacophore kNN graph (uni_denoiser.py:264-281,291) on the
+// 5th-gen tensor cores.  Tile = 4 destination nodes (segments) x 32 neighbour rows; thread = (row, 32-channel quarter)
+// exactly as in pg_trip_tc.cu / pg_bond_tc.cu.
+//
+// The key and the value MLP run as two passes of the same kernel (PASS 0 / 1): shared memory holds one second-Linear
+// weight (bf16 hi/lo, 64 KB), one edge-feature table (48 KB) and the edge-feature operand (48 KB) at a time.
+//   pre-activation = dst-node partial + src-node partial (gathered) + Table[edge type] . feat(edge)
+//     feat = 20 Gaussian smearings of the distance, 1, 3 direction dot products (uni_denoiser.py:373-387); the one-hot
+//     edge type (x) feat outer product is a K = 96 operand, so the table product is 18 tcgen05.mma (M128 N128 K16, bf16x3)
+//     into TMEM; three otherwise idle warps compute the features of the next tile while the row warps work.
+//   LayerNorm + ReLU thread-locally -> bf16 hi/lo A operand in TMEM -> second Linear (24 tcgen05.mma).
+//   PASS 0: logits = q . k per head, segment softmax over the 32 lanes, alpha * e_w -> global scratch [Ek,16] (+ its
+//           per-head sums [N,16]).
+//   PASS 1: node layer  out[i] = sum_r alpha'_r v_r + b2v * sum_r alpha'_r           (butterfly transpose-reduce)
+//           pos  layer  out[i] = mean_h sum_r alpha'_rh (v_rh + b2v_h) rel_x_r
+// Row-warp order per tile: LayerNorm(t) | logits or epilogue (t-1), so the W2 MMA of tile t and the table MMA of tile
+// t+1 run under the previous tile's post-processing.  TMEM: pre [0,128) hid [128,256) out [256,384) | [384,512).
+#include <algorithm>
+#include "pg_attn.h"
+#include "pg_tc.cuh"
+
+namespace {
+constexpr int W_TILE = 32768;               // one [128 x 128] bf16 matrix in two 128B-swizzled K blocks
+constexpr int SM_W = 2 * W_TILE;            // hi, lo
+constexpr int KF = 96;                      // 4 edge types x 24 features
+constexpr int TAB_PART = KF * 128 * 2;      // 24 KB: [k-step 6][n/8][kc 2][n%8][8 bf16]
+constexpr int SM_TAB = 2 * TAB_PART;
+constexpr int FEAT_PART = 128 * KF * 2;     // 24 KB: [k-step 6][row/8][kc 2][row%8][8 bf16]
+constexpr int SM_FEAT = 2 * FEAT_PART;
+constexpr int XP_LD = 36;
+constexpr int SM_XP = 16 * 16 * XP_LD * 4;  // per row warp: transpose tile of 16 rows x 32 channels (two rounds per tile)
+constexpr int SM_STAT = 128 * 4 * 2 * 4;    // [128 rows][4 quarters][2] partial LayerNorm sums
+constexpr int SM_RED = 4 * 4 * 4 * 4;
+constexpr int SM_TOTAL = SM_W + SM_TAB + SM_FEAT + SM_XP + SM_STAT + SM_RED + 3 * 128 * 4 + 128 + 1024;
+constexpr float kInvSqrtD = 0.35355339059327373f;
+constexpr int ROW_WARPS = 16;
+constexpr int MMA_WARP = ROW_WARPS;
+constexpr int NTHREADS = (ROW_WARPS + 4) * 32;
+constexpr int ROW_THREADS = ROW_WARPS * 32;
+enum { B_FEAT = 0, B_PRE, B_HID, B_OUT, B_COUNT };
+
+struct KSeg {
+    bool valid, dl, inr;
+    int v, R, ctx0, gp;
+    long long e0;
+};
+__device__ __forceinline__ KSeg kseg(const PlanDev& d, long long tile, int wq) {
+    KSeg s;
+    const long long v = tile * 4 + wq;
+    s.valid = false; s.dl = false; s.inr = v < d.N; s.v = 0; s.R = 0; s.ctx0 = 0; s.gp = 0; s.e0 = 0;
+    if (v < d.N) {
+        const int g = d.node_graph[v];
+        const int ng = d.g_n[g] + d.g_p[g];
+        s.v = (int)v; s.ctx0 = d.ctx_off[g]; s.gp = d.g_p[g];
+        s.R = min(PG_KNN, ng - 1);
+        s.e0 = d.koff[g] + (long long)(s.v - s.ctx0) * s.R;
+        s.dl = (s.v - s.ctx0) >= s.gp;
+        s.valid = s.R >= 1;
+    }
+    return s;
+}
+
+template <int PASS, int POS>
+__global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sW = smem;
+    uint8_t* sTab = sW + SM_W;
+    uint8_t* sFeat = sTab + SM_TAB;
+    float* sXp = (float*)(sFeat + SM_FEAT);
+    float* sStat = sXp + SM_XP / 4;
+    float* sRed = sStat + SM_STAT / 4;
+    float* sLn = sRed + SM_RED / 4;                 // gamma, beta of this pass's LayerNorm
+    float* sB2 = sLn + 2 * 128;                     // b2v (128 or 16), value pass only
+    uint64_t* bars = (uint64_t*)(sB2 + 128);
+    uint32_t* tmem_slot = (uint32_t*)(bars + B_COUNT);
+    const PlanDev& d = a.d;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wq = warp & 3;
+    constexpr int NOUT = (PASS == 1 && POS) ? 16 : 128;     // outputs of this pass's second Linear
+
+    if (warp == MMA_WARP) tc::tmem_alloc<512>(tmem_slot);
+    if (tid == 0) {
+        tc::mbar_init(&bars[B_FEAT], 96); tc::mbar_init(&bars[B_PRE], 1);
+        tc::mbar_init(&bars[B_HID], ROW_THREADS); tc::mbar_init(&bars[B_OUT], 1);
+        tc::fence_barrier_init();
+    }
+    // ---- resident operands of this pass
+    {
+        const uint16_t* w2 = PASS == 0 ? a.w2k_bf : a.w2v_bf;
+        for (int idx = tid; idx < 2 * 128 * 16; idx += NTHREADS) {        // [part 2][n][chunk 16] -> 128B-swizzled K-major
+            const int part = idx >> 11, n = (idx >> 4) & 127, c = idx & 15;
+            if (n >= NOUT) continue;
+            const uint16_t* src = w2 + ((size_t)part * NOUT + n) * 128 + c * 8;
+            const uint32_t dst = tc::smem_u32(sW) + part * W_TILE + (c >> 3) * 16384 + tc::sw128_chunk(n, c & 7);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        }
+        const uint16_t* tb = PASS == 0 ? a.tabk_bf : a.tabv_bf;
+        for (int idx = tid; idx < 2 * 128 * 12; idx += NTHREADS) {        // [part 2][n 128][chunk 12] -> no-swizzle K-major
+            const int part = idx / (128 * 12), rem = idx - part * (128 * 12), n = rem / 12, c = rem - n * 12;
+            const uint16_t* src = tb + ((size_t)part * 128 + n) * KF + c * 8;
+            const uint32_t dst = tc::smem_u32(sTab) + part * TAB_PART + (c >> 1) * 4096 + (n >> 3) * 256 + (c & 1) * 128 + (n & 7) * 16;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+        for (int i = tid; i < SM_FEAT / 16; i += NTHREADS) reinterpret_cast<uint4*>(sFeat)[i] = make_uint4(0, 0, 0, 0);
+        if (tid < 128) {
+            sLn[tid] = (PASS == 0 ? a.w.lnk_g : a.w.lnv_g)[tid]; sLn[128 + tid] = (PASS == 0 ? a.w.lnk_b : a.w.lnv_b)[tid];
+            if (PASS == 1 && tid < NOUT) sB2[tid] = a.w.b2v[tid];
+        }
+    }
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+    constexpr uint32_t C_PRE = 0, C_HID = 128, C_OUT = 256;     // out: two buffers of 128 columns
+    const long long ntiles = (d.N + 3) / 4;
+
+    if (warp >= MMA_WARP) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (warp == MMA_WARP) {
+            // ================= MMA issue =================
+            constexpr uint32_t idesc_t = tc::umma_idesc_bf16(128, 128);
+            constexpr uint32_t idesc_w = tc::umma_idesc_bf16(128, NOUT);
+            const uint32_t sW_u32 = tc::smem_u32(sW), sTab_u32 = tc::smem_u32(sTab), sFeat_u32 = tc::smem_u32(sFeat);
+            auto table_mma = [&]() {
+                if (lane == 0) {
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int combo = 0; combo < 3; combo++) {       // hi*hi, hi*lo, lo*hi
+                        const uint32_t fb = sFeat_u32 + (combo == 2 ? FEAT_PART : 0), wb = sTab_u32 + (combo == 1 ? TAB_PART : 0);
+#pragma unroll
+                        for (int ks = 0; ks < KF / 16; ks++) {
+                            tc::umma_bf16(tmem + C_PRE, tc::umma_desc_k16_noswizzle(fb + ks * 4096), tc::umma_desc_k16_noswizzle(wb + ks * 4096), idesc_t, acc);
+                            acc = 1;
+                        }
+                    }
+                    tc::umma_commit(&bars[B_PRE]);
+                }
+                __syncwarp();
+            };
+            tc::mbar_wait(&bars[B_FEAT], 0);
+            tc::tc_fence_after();
+            table_mma();
+            uint32_t ph = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
+                tc::mbar_wait(&bars[B_HID], ph);
+                tc::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t dcol = tmem + C_OUT + ph * 128;
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int combo = 0; combo < 3; combo++) {
+                        const uint32_t abase = tmem + C_HID + (combo == 2 ? 64 : 0);
+                        const uint32_t bbase = sW_u32 + (combo == 1 ? W_TILE : 0);
+#pragma unroll
+                        for (int ks = 0; ks < 8; ks++) {
+                            const uint64_t bd = tc::umma_desc_sw128(bbase + (ks >> 2) * 16384 + (ks & 3) * 32);
+                            tc::umma_bf16_ts(dcol, abase + ks * 8, bd, idesc_w, acc);
+                            acc = 1;
+                        }
+                    }
+                    tc::umma_commit(&bars[B_OUT]);
+                }
+                __syncwarp();
+                if (tile + gridDim.x < ntiles) {
+                    tc::mbar_wait(&bars[B_FEAT], ph ^ 1);   // features of the next tile (pre columns are free: HID(t) has fired)
+                    tc::tc_fence_after();
+                    table_mma();
+                }
+            }
+        } else {
+            // ================= feature warps: edge features of the next tile -> bf16 hi/lo one-hot-typed operand =================
+            const int ft = tid - (MMA_WARP + 1) * 32;       // 0..95; row slots ft and ft + 96
+            int prev_type[2] = {-1, -1};
+            auto features = [&](long long tile) {
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    const int r = ft + k * 96;
+                    if (r >= 128) break;
+                    const KSeg sg = kseg(d, tile, r >> 5);
+                    const int row = r & 31;
+                    int type = -1;
+                    uint32_t hi[12], lo[12];
+                    if (sg.valid && row < sg.R) {
+                        const int s = a.knn_src[sg.e0 + row];
+                        const float x0 = a.x[(size_t)sg.v * 3], x1 = a.x[(size_t)sg.v * 3 + 1], x2 = a.x[(size_t)sg.v * 3 + 2];
+                        const float r0 = x0 - a.x[(size_t)s * 3], r1 = x1 - a.x[(size_t)s * 3 + 1], r2 = x2 - a.x[(size_t)s * 3 + 2];
+                        const float dist = sqrtf(r0 * r0 + r1 * r1 + r2 * r2);
+                        const bool sl = (s - sg.ctx0) >= sg.gp;
+                        type = sl ? (sg.dl ? 0 : 1) : (sg.dl ? 2 : 3);                      // uni_denoiser.py:373-378
+                        float f[24];
+#pragma unroll
+                        for (int gg = 0; gg < 20; gg++) f[gg] = smear_val(dist, gg);
+                        f[20] = 1.0f;
+                        const float* c1 = a.comb + (size_t)s * 3;                             // vec_1 = comb[src]
+                        const float* c2 = a.comb + (size_t)sg.v * 3;                          // vec_2 = comb[dst]
+                        f[21] = c1[0] * c2[0] + c1[1] * c2[1] + c1[2] * c2[2];
+                        f[22] = -(c1[0] * r0 + c1[1] * r1 + c1[2] * r2);                      // vec_3 = x[src] - x[dst]
+                        f[23] = -(c2[0] * r0 + c2[1] * r1 + c2[2] * r2);
+#pragma unroll
+                        for (int i = 0; i < 12; i++) tc::split_pair_trunc(f[2 * i], f[2 * i + 1], hi[i], lo[i]);
+                    }
+                    uint8_t* base = sFeat + (r >> 3) * 256 + (r & 7) * 16;
+                    auto chunk = [&](int c) { return base + (c >> 1) * 4096 + (c & 1) * 128; };
+                    if (prev_type[k] >= 0 && prev_type[k] != type) {
+#pragma unroll
+                        for (int j = 0; j < 3; j++) {
+                            uint8_t* p = chunk(prev_type[k] * 3 + j);
+                            *reinterpret_cast<uint4*>(p) = make_uint4(0, 0, 0, 0);
+                            *reinterpret_cast<uint4*>(p + FEAT_PART) = make_uint4(0, 0, 0, 0);
+                        }
+                    }
+                    if (type >= 0) {
+#pragma unroll
+                        for (int j = 0; j < 3; j++) {
+                            uint8_t* p = chunk(type * 3 + j);
+                            *reinterpret_cast<uint4*>(p) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                            *reinterpret_cast<uint4*>(p + FEAT_PART) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        }
+                    }
+                    prev_type[k] = type;
+                }
+                tc::fence_proxy_async_smem();
+                tc::mbar_arrive(&bars[B_FEAT]);
+            };
+            features(blockIdx.x);
+            uint32_t ph = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
+                tc::mbar_wait(&bars[B_PRE], ph);            // the table MMA of this tile has consumed the operand
+                if (tile + gridDim.x < ntiles) features(tile + gridDim.x);
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        // ================= row warps: thread = (row, channel quarter) =================
+        const int cq = warp >> 2;
+        const int sr = lane >> 3, ch = (lane & 7) * 4;
+        float* xp = sXp + warp * (16 * XP_LD);
+        float al[4] = {0.f, 0.f, 0.f, 0.f};
+        KSeg psg = kseg(d, blockIdx.x, wq);                 // segment of the tile whose post-processing is pending
+        bool prow = false;
+        float rel0 = 0.f, rel1 = 0.f, rel2 = 0.f;
+
+        // ---- post-processing of a finished tile (its out columns: buffer `ob`)
+        auto post = [&](uint32_t parity, uint32_t ob) {
+            const uint32_t out = tmem + C_OUT + ob * 128 + lane_base;
+            if (PASS == 0) {
+                // logits of this thread's 4 heads (key bias dropped: softmax-invariant), softmax over the lanes, times e_w
+                const float* qrow = a.q + (size_t)psg.v * 128 + cq * 32;
+                float4 qv[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) qv[i] = ldg4(qrow + i * 4);
+                const float ew = prow ? a.ew[psg.e0 + lane] : 0.f;
+                tc::mbar_wait(&bars[B_OUT], parity);
+                tc::tc_fence_after();
+                uint32_t vv[32];
+                tc::tmem_ld32_nowait(out + cq * 32, vv);
+                tc::tmem_ld_wait();
+                constexpr float kScale = kInvSqrtD * 1.4426950408889634f;
+#pragma unroll
+                for (int h = 0; h < 4; h++) {
+                    const int o = h * 8;
+                    const float4 qa = qv[2 * h], qb = qv[2 * h + 1];
+                    float2 s0 = tc::mul2(make_float2(qa.x, qa.y), make_float2(__uint_as_float(vv[o]), __uint_as_float(vv[o + 1])));
+                    float2 s1 = tc::mul2(make_float2(qb.x, qb.y), make_float2(__uint_as_float(vv[o + 4]), __uint_as_float(vv[o + 5])));
+                    s0 = tc::fma2(make_float2(qa.z, qa.w), make_float2(__uint_as_float(vv[o + 2]), __uint_as_float(vv[o + 3])), s0);
+                    s1 = tc::fma2(make_float2(qb.z, qb.w), make_float2(__uint_as_float(vv[o + 6]), __uint_as_float(vv[o + 7])), s1);
+                    s0 = tc::add2(s0, s1);
+                    al[h] = prow ? (s0.x + s0.y) * kScale : -INFINITY;
+                }
+                float mx[4], sm[4];
+#pragma unroll
+                for (int h = 0; h < 4; h++) mx[h] = al[h];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int h = 0; h < 4; h++) mx[h] = fmaxf(mx[h], __shfl_xor_sync(PG_FULL, mx[h], o));
+#pragma unroll
+                for (int h = 0; h < 4; h++) { al[h] = prow ? tc::ex2_approx(al[h] - mx[h]) : 0.f; sm[h] = al[h]; }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int h = 0; h < 4; h++) sm[h] += __shfl_xor_sync(PG_FULL, sm[h], o);
+                float sw[4];
+#pragma unroll
+                for (int h = 0; h < 4; h++) { al[h] = prow ? al[h] * __frcp_rn(sm[h]) * ew : 0.f; sw[h] = al[h]; }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int h = 0; h < 4; h++) sw[h] += __shfl_xor_sync(PG_FULL, sw[h], o);
+                if (prow) st4(a.alpha + (size_t)(psg.e0 + lane) * 16 + cq * 4, make_float4(al[0], al[1], al[2], al[3]));
+                if (psg.valid && lane == 0) st4(a.alpha_sum + (size_t)psg.v * 16 + cq * 4, make_float4(sw[0], sw[1], sw[2], sw[3]));
+            } else {
+                float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (prow) a4 = ld4(a.alpha + (size_t)(psg.e0 + lane) * 16 + cq * 4);
+                tc::mbar_wait(&bars[B_OUT], parity);
+                tc::tc_fence_after();
+                if (POS == 0) {
+                    const float swc = psg.valid ? a.alpha_sum[(size_t)psg.v * 16 + cq * 4 + (lane >> 3)] : 0.f;
+                    uint32_t vu[32];
+                    tc::tmem_ld32_nowait(out + cq * 32, vu);
+                    tc::tmem_ld_wait();
+                    const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float2 pr = tc::mul2(make_float2(aa[i >> 3], aa[i >> 3]), make_float2(__uint_as_float(vu[i]), __uint_as_float(vu[i + 1])));
+                        v[i] = pr.x; v[i + 1] = pr.y;
+                    }
+                    const float o = transpose_reduce32(v, lane);
+                    if (psg.inr) {                                                          // isolated node: no messages
+                        const int c = cq * 32 + lane;
+                        a.out[(size_t)psg.v * 128 + c] = psg.valid ? fmaf(sB2[c], swc, o) : 0.f;
+                    }
+                } else {
+                    float vh[4];
+                    tc::tmem_ld4(out + cq * 4, vh);
+                    float c = a4.x * (vh[0] + sB2[cq * 4]) + a4.y * (vh[1] + sB2[cq * 4 + 1]) + a4.z * (vh[2] + sB2[cq * 4 + 2]) + a4.w * (vh[3] + sB2[cq * 4 + 3]);
+                    float p0 = c * rel0, p1 = c * rel1, p2 = c * rel2;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        p0 += __shfl_xor_sync(PG_FULL, p0, o); p1 += __shfl_xor_sync(PG_FULL, p1, o); p2 += __shfl_xor_sync(PG_FULL, p2, o);
+                    }
+                    float* rd = sRed + (wq * 4 + cq) * 4;
+                    if (lane == 0) { rd[0] = p0; rd[1] = p1; rd[2] = p2; }
+                    asm volatile("bar.sync %0, 128;" ::"r"(3 + wq) : "memory");
+                    if (cq == 0 && lane < 3 && psg.inr) {
+                        const float* r4 = sRed + wq * 16 + lane;
+                        a.out[(size_t)psg.v * 3 + lane] = psg.valid ? ((r4[0] + r4[4]) + (r4[8] + r4[12])) * (1.0f / 16.0f) : 0.f;
+                    }
+                }
+            }
+        };
+
+        uint32_t ph = 0;
+        bool any = false;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
+            const KSeg sg = kseg(d, tile, wq);
+            const bool rowvalid = sg.valid && lane < sg.R;
+            const int nrow = sg.valid ? sg.R : 0;
+            // ---- gather the src-node partial rows: 8 lanes cover the 128-byte slice of one row (coalesced), the rows are
+            //      transposed to row-per-lane through the warp's shared tile (two rounds of 16 rows)
+            const int c0 = cq * 32;
+            const float* ps = a.nc.A + (PASS == 0 ? a.nc.src_k : a.nc.src_v) + c0 + ch;
+            float4 u[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int row = (i * 4 + sr) < nrow ? (i * 4 + sr) : 0;
+                const int s = nrow > 0 ? a.knn_src[sg.e0 + row] : 0;
+                u[i] = ldg4(ps + (size_t)s * a.nc.lda);
+            }
+            const float* pd = a.nc.A + (size_t)sg.v * a.nc.lda + (PASS == 0 ? a.nc.dst_k : a.nc.dst_v) + c0;
+            float2 x2[16];
+#pragma unroll
+            for (int round = 0; round < 2; round++) {
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; i++) st4(xp + (i * 4 + sr) * XP_LD + ch, u[round * 4 + i]);
+                __syncwarp();
+                if ((lane >> 4) == round) {
+                    const float* xrow = xp + (lane & 15) * XP_LD;
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const float4 e4 = ld4(xrow + 2 * i), d4 = ldg4(pd + 2 * i);
+                        x2[i] = make_float2(e4.x + d4.x, e4.y + d4.y);
+                        x2[i + 1] = make_float2(e4.z + d4.z, e4.w + d4.w);
+                    }
+                }
+            }
+            // ---- table product from TMEM, LayerNorm + ReLU, bf16 hi/lo A operand
+            tc::mbar_wait(&bars[B_PRE], ph);
+            tc::tc_fence_after();
+            {
+                uint32_t xu[32];
+                tc::tmem_ld32_nowait(tmem + C_PRE + lane_base + cq * 32, xu);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; i++) x2[i] = tc::add2(x2[i], make_float2(__uint_as_float(xu[2 * i]), __uint_as_float(xu[2 * i + 1])));
+            }
+            float2 s1 = make_float2(0.f, 0.f), s2 = s1, s1b = s1, s2b = s1;
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                s1 = tc::add2(s1, x2[i]); s1b = tc::add2(s1b, x2[i + 1]);
+                s2 = tc::fma2(x2[i], x2[i], s2); s2b = tc::fma2(x2[i + 1], x2[i + 1], s2b);
+            }
+            s1 = tc::add2(s1, s1b); s2 = tc::add2(s2, s2b);
+            float* st = sStat + ((wq * 32 + lane) * 4) * 2;
+            *reinterpret_cast<float2*>(st + cq * 2) = make_float2(s1.x + s1.y, s2.x + s2.y);
+            asm volatile("bar.sync %0, 128;" ::"r"(3 + wq) : "memory");
+            const float4 sa4 = ld4(st), sb4 = ld4(st + 4);
+            const float mu = ((sa4.x + sa4.z) + (sb4.x + sb4.z)) * (1.0f / 128.0f);
+            const float rstd = rsqrtf(fmaxf(fmaf(-mu, mu, ((sa4.y + sa4.w) + (sb4.y + sb4.w)) * (1.0f / 128.0f)), 0.f) + 1e-5f);
+            const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mu * rstd, -mu * rstd);
+            const float* gam = sLn + cq * 32;
+            const float* bet = gam + 128;
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                const float4 g4 = ld4(gam + 2 * i), b4 = ld4(bet + 2 * i);
+                float2 y0 = tc::fma2(tc::fma2(x2[i], rs2, nm2), make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
+                float2 y1 = tc::fma2(tc::fma2(x2[i + 1], rs2, nm2), make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
+                tc::split_pair_relu(y0, hi[i], lo[i]);
+                tc::split_pair_relu(y1, hi[i + 1], lo[i + 1]);
+            }
+            // the W2 MMA of the previous tile must be done with the hid columns before they are rewritten
+            if (any) tc::mbar_wait(&bars[B_OUT], ph ^ 1);
+            tc::tc_fence_after();
+            tc::tmem_st16(tmem + C_HID + lane_base + cq * 16, hi);
+            tc::tmem_st16(tmem + C_HID + lane_base + 64 + cq * 16, lo);
+            tc::tmem_st_wait();
+            tc::tc_fence_before();
+            tc::mbar_arrive(&bars[B_HID]);
+            // ---- post-processing of the previous tile while the tensor pipe works on this one
+            if (any) post(ph ^ 1, ph ^ 1);
+            psg = sg; prow = rowvalid;
+            if (PASS == 1 && POS) {
+                const int s = rowvalid ? a.knn_src[sg.e0 + lane] : sg.v;
+                rel0 = a.x[(size_t)sg.v * 3] - a.x[(size_t)s * 3];                          // rel_x = x[dst] - x[src]
+                rel1 = a.x[(size_t)sg.v * 3 + 1] - a.x[(size_t)s * 3 + 1];
+                rel2 = a.x[(size_t)sg.v * 3 + 2] - a.x[(size_t)s * 3 + 2];
+            }
+            any = true;
+        }
+        if (any) post(ph ^ 1, ph ^ 1);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) { tc::tc_fence_after(); tc::tmem_dealloc<512>(tmem); }
+}
+}  // namespace
+
+int pg_launch_knn_tc(const KnnTcArgs& a, int pos, int num_sms, cudaStream_t s) {
+    if (a.d.N <= 0) return PG_OK;
+    static bool init = false;
+    if (!init) {
+        PG_CUDA_CHECK(cudaFuncSetAttribute(knn_tc_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        PG_CUDA_CHECK(cudaFuncSetAttribute(knn_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        PG_CUDA_CHECK(cudaFuncSetAttribute(knn_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        init = true;
+    }
+    const long long ntiles = (a.d.N + 3) / 4;
+    const unsigned grid = (unsigned)std::min<long long>(ntiles, num_sms);
+    knn_tc_kernel<0, 0><<<grid, NTHREADS, SM_TOTAL, s>>>(a);          // key pass: alpha * e_w -> scratch
+    PG_LAUNCH_CHECK();
+    if (pos == 0) knn_tc_kernel<1, 0><<<grid, NTHREADS, SM_TOTAL, s>>>(a);
+    else knn_tc_kernel<1, 1><<<grid, NTHREADS, SM_TOTAL, s>>>(a);
+    PG_LAUNCH_CHECK();
+    return PG_OK;
+}

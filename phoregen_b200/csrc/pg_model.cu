@@ -51,7 +51,8 @@ std::vector<PgSlotDesc> build_slots() {
             const bool pos = s >= 3;
             add(S + "w2v", (pos ? 16 : 128) * 128); add(S + "b2v", pos ? 16 : 128);
             if (s == 0 || s == 3) { add(S + "tab_k", 4 * 24 * 128); add(S + "tab_v", 4 * 24 * 128); }
-            if (s == 1 || s == 4) { add(S + "w2k.bf", 128 * 128); add(S + "w2v.bf", (pos ? 16 : 128) * 128); }   // bond_tc
+            if (s != 2) { add(S + "w2k.bf", 128 * 128); add(S + "w2v.bf", (pos ? 16 : 128) * 128); }   // bond_tc / knn_tc
+            if (s == 0 || s == 3) { add(S + "tab_k.bf", 96 * 128); add(S + "tab_v.bf", 96 * 128); }
             if (s == 2) {
                 add(S + "wrkj", 20 * 256); add(S + "wrji", 20 * 256); add(S + "wa", 13 * 256);
                 add(S + "w2k.bf", 128 * 128); add(S + "w2v.bf", 128 * 128); add(S + "wa.bf", 2 * 256 * 16 / 2);
@@ -287,6 +288,30 @@ int launch_bond(PgPlan* p, const BondAttnArgs& a0, const W& w, const std::string
     return PG_OK;
 }
 
+// tcgen05 kNN-graph attention unless PG_KNN_ATTN=fp32
+bool use_tc_knn() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PG_KNN_ATTN"); v = (e && !strcmp(e, "fp32")) ? 0 : 1; }
+    return v == 1;
+}
+template <class W>
+int launch_knn_attn(PgPlan* p, const KnnAttnArgs& a, const W& w, const std::string& S, int pos, cudaStream_t s) {
+    PgTimed timed(p, KC_KNN_ATTN, s);
+    if (use_tc_knn()) {
+        KnnTcArgs t;
+        t.d = a.d; t.x = a.x; t.comb = a.comb; t.knn_src = a.knn_src; t.ew = a.ew; t.nc = a.nc; t.q = a.q; t.w = a.w;
+        t.w2k_bf = (const uint16_t*)w(S + "w2k.bf"); t.w2v_bf = (const uint16_t*)w(S + "w2v.bf");
+        t.tabk_bf = (const uint16_t*)w(S + "tab_k.bf"); t.tabv_bf = (const uint16_t*)w(S + "tab_v.bf");
+        t.alpha = p->abuf; t.alpha_sum = p->abuf + (size_t)a.d.Ek * 16; t.out = a.out;
+        PG_TRY(pg_launch_knn_tc(t, pos, num_sms(), s));
+        p->launches += 2;
+        return PG_OK;
+    }
+    PG_TRY(pg_launch_knn_attn(a, 0, pos, s));
+    p->launches++;
+    return PG_OK;
+}
+
 bool use_simt_gemm() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("PG_GEMM"); v = (e && !strcmp(e, "simt")) ? 1 : 0; }
@@ -358,7 +383,7 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
             a.d = d; a.x = p->x; a.comb = p->comb; a.knn_src = p->knn_src; a.ew = p->ew;
             a.nc = NodeCols{p->nbuf, N1_COLS, N1_NK_DK, N1_NK_SK, N1_NK_DV, N1_NK_SV};
             a.q = p->qn1; a.w = attn_w(w, L + "nk.", true); a.out = p->o1; a.maxr = maxr_knn;
-            { PgTimed timed(p, KC_KNN_ATTN, s); PG_TRY(pg_launch_knn_attn(a, 0, 0, s)); } p->launches++;
+            PG_TRY(launch_knn_attn(p, a, w, L + "nk.", 0, s));
         }
         {   // node update over the bond graph
             BondAttnArgs a;
@@ -405,7 +430,7 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
             a.d = d; a.x = p->x; a.comb = p->comb; a.knn_src = p->knn_src; a.ew = p->ew;
             a.nc = NodeCols{p->nbuf, N2_COLS, N2_PK_DK, N2_PK_SK, N2_PK_DV, N2_PK_SV};
             a.q = p->qn1; a.w = attn_w(w, L + "pk.", true); a.out = p->dx1; a.maxr = maxr_knn;
-            { PgTimed timed(p, KC_KNN_ATTN, s); PG_TRY(pg_launch_knn_attn(a, 0, 1, s)); } p->launches++;
+            PG_TRY(launch_knn_attn(p, a, w, L + "pk.", 1, s));
         }
         {
             BondAttnArgs a;

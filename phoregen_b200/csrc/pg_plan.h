@@ -17,6 +17,7 @@ struct PgPlan {
     float *dx1, *dx2;             // [N,3]
     float* ebuf;                  // [Eb,640] edge GEMM outputs
     float* qt;                    // [Eb,128] per-edge triplet queries / head hidden
+    float* abuf;                  // [Ek,16] + [N,16] attention weights of the tcgen05 kNN attention (key pass -> value pass)
     float* rbuf;                  // [Eb,256] r_ji slice of the triplet MLPs (tcgen05 triplet kernel)
     float* pbuf2;                 // [Eb,256] per-edge first-Linear partials P[k->j] (tcgen05 triplet kernel)
     float *ew, *comb;             // [Ek], [N,3]

@@ -164,8 +164,10 @@ def build_blob(sd):
         packed[name + ".bf"] = bf16_tiles64(packed[name])
     for name in [k for k in packed if k.endswith(".tr.w2k") or k.endswith(".tr.w2v")]:
         packed[name + ".bf"] = bf16_split(np.asarray(packed[name]).T)          # already [out][in] = [N][K]
-    for name in [k for k in packed if k.endswith((".nb.w2k", ".nb.w2v", ".pb.w2k", ".pb.w2v"))]:
+    for name in [k for k in packed if k.endswith((".nb.w2k", ".nb.w2v", ".pb.w2k", ".pb.w2v", ".nk.w2k", ".nk.w2v", ".pk.w2k", ".pk.w2v"))]:
         packed[name + ".bf"] = bf16_split(np.asarray(packed[name]).T)          # [out][in]; pos value head: 16 outputs
+    for name in [k for k in packed if k.endswith((".nk.tab_k", ".nk.tab_v", ".pk.tab_k", ".pk.tab_v"))]:
+        packed[name + ".bf"] = bf16_split(np.asarray(packed[name]).reshape(96, 128))   # [type*24 + feat][128] -> [hi|lo][128][96]
     for name in [k for k in packed if k.endswith(".tr.wa")]:
         wa = np.zeros((16, 256))
         wa[:13] = packed[name]                                                  # [13][256] -> pad K to 16
