@@ -31,7 +31,8 @@ constexpr int XP_LD = 36;
 constexpr int SM_XP = 16 * 16 * XP_LD * 4;  // per row warp: transpose tile of 16 rows x 32 channels (two rounds per tile)
 constexpr int SM_STAT = 128 * 4 * 2 * 4;    // [128 rows][4 quarters][2] partial LayerNorm sums
 constexpr int SM_RED = 4 * 4 * 4 * 4;
-constexpr int SM_TOTAL = SM_W + SM_TAB + SM_FEAT + SM_XP + SM_STAT + SM_RED + 3 * 128 * 4 + 128 + 1024;
+constexpr int SM_Q = 16 * 2 * 32 * 4;       // per row warp: two 128-byte slots for the query slice of the pending / current tile
+constexpr int SM_TOTAL = SM_W + SM_TAB + SM_FEAT + SM_XP + SM_STAT + SM_RED + SM_Q + 3 * 128 * 4 + 128 + 1024;
 constexpr float kInvSqrtD = 0.35355339059327373f;
 constexpr int ROW_WARPS = 16;
 constexpr int MMA_WARP = ROW_WARPS;
@@ -70,7 +71,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
     float* sXp = (float*)(sFeat + SM_FEAT);
     float* sStat = sXp + SM_XP / 4;
     float* sRed = sStat + SM_STAT / 4;
-    float* sLn = sRed + SM_RED / 4;                 // gamma, beta of this pass's LayerNorm
+    float* sQ = sRed + SM_RED / 4;
+    float* sLn = sQ + SM_Q / 4;                 // gamma, beta of this pass's LayerNorm
     float* sB2 = sLn + 2 * 128;                     // b2v (128 or 16), value pass only
     uint64_t* bars = (uint64_t*)(sB2 + 128);
     uint32_t* tmem_slot = (uint32_t*)(bars + B_COUNT);
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
 
     if (warp == MMA_WARP) tc::tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
-        tc::mbar_init(&bars[B_FEAT], 96); tc::mbar_init(&bars[B_PRE], 1);
+        tc::mbar_init(&bars[B_FEAT], 128); tc::mbar_init(&bars[B_PRE], 1);
         tc::mbar_init(&bars[B_HID], ROW_THREADS); tc::mbar_init(&bars[B_OUT], 1);
         tc::fence_barrier_init();
     }
@@ -120,32 +122,100 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
 
     if (warp >= MMA_WARP) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        if (warp == MMA_WARP) {
-            // ================= MMA issue =================
-            constexpr uint32_t idesc_t = tc::umma_idesc_bf16(128, 128);
-            constexpr uint32_t idesc_w = tc::umma_idesc_bf16(128, NOUT);
-            const uint32_t sW_u32 = tc::smem_u32(sW), sTab_u32 = tc::smem_u32(sTab), sFeat_u32 = tc::smem_u32(sFeat);
-            auto table_mma = [&]() {
-                if (lane == 0) {
-                    uint32_t acc = 0;
+        // ================= auxiliary warpgroup: edge features of the next tile (one row per thread) + MMA issue (warp 16) =======
+        // feature row r = tid - 512: segment r / 32, neighbour row r % 32 -> bf16 hi/lo one-hot-typed operand row
+        const int r = tid - MMA_WARP * 32, frow = r & 31;
+        int prev_type = -1;
+        // neighbour index of this thread's row in `tile` (-1: padded row); fetched one tile ahead of its use
+        auto row_src = [&](long long tile) -> int {
+            if (tile >= ntiles) return -1;
+            const KSeg sg = kseg(d, tile, r >> 5);
+            return (sg.valid && frow < sg.R) ? a.knn_src[sg.e0 + frow] : -1;
+        };
+        auto features = [&](long long tile, int s) {
+            int type = -1;
+            uint32_t hi[12], lo[12];
+            if (s >= 0) {
+                const KSeg sg = kseg(d, tile, r >> 5);
+                const float x0 = a.x[(size_t)sg.v * 3], x1 = a.x[(size_t)sg.v * 3 + 1], x2 = a.x[(size_t)sg.v * 3 + 2];
+                const float r0 = x0 - a.x[(size_t)s * 3], r1 = x1 - a.x[(size_t)s * 3 + 1], r2 = x2 - a.x[(size_t)s * 3 + 2];
+                const float* c1 = a.comb + (size_t)s * 3;                             // vec_1 = comb[src]
+                const float* c2 = a.comb + (size_t)sg.v * 3;                          // vec_2 = comb[dst]
+                const float c10 = c1[0], c11 = c1[1], c12 = c1[2], c20 = c2[0], c21 = c2[1], c22 = c2[2];
+                const float dist = sqrtf(r0 * r0 + r1 * r1 + r2 * r2);
+                const bool sl = (s - sg.ctx0) >= sg.gp;
+                type = sl ? (sg.dl ? 0 : 1) : (sg.dl ? 2 : 3);                        // uni_denoiser.py:373-378
+                float f[24];
 #pragma unroll
-                    for (int combo = 0; combo < 3; combo++) {       // hi*hi, hi*lo, lo*hi
-                        const uint32_t fb = sFeat_u32 + (combo == 2 ? FEAT_PART : 0), wb = sTab_u32 + (combo == 1 ? TAB_PART : 0);
+                for (int gg = 0; gg < 20; gg++) { const float dd = dist - c_smear_off[gg]; f[gg] = __expf(-0.5f * dd * dd); }
+                f[20] = 1.0f;
+                f[21] = c10 * c20 + c11 * c21 + c12 * c22;
+                f[22] = -(c10 * r0 + c11 * r1 + c12 * r2);                            // vec_3 = x[src] - x[dst]
+                f[23] = -(c20 * r0 + c21 * r1 + c22 * r2);
 #pragma unroll
-                        for (int ks = 0; ks < KF / 16; ks++) {
-                            tc::umma_bf16(tmem + C_PRE, tc::umma_desc_k16_noswizzle(fb + ks * 4096), tc::umma_desc_k16_noswizzle(wb + ks * 4096), idesc_t, acc);
-                            acc = 1;
-                        }
-                    }
-                    tc::umma_commit(&bars[B_PRE]);
+                for (int i = 0; i < 12; i++) tc::split_pair_trunc(f[2 * i], f[2 * i + 1], hi[i], lo[i]);
+            }
+            uint8_t* base = sFeat + (r >> 3) * 256 + (r & 7) * 16;
+            auto chunk = [&](int c) { return base + (c >> 1) * 4096 + (c & 1) * 128; };
+            if (prev_type >= 0 && prev_type != type) {
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    uint8_t* p = chunk(prev_type * 3 + j);
+                    *reinterpret_cast<uint4*>(p) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4*>(p + FEAT_PART) = make_uint4(0, 0, 0, 0);
                 }
-                __syncwarp();
-            };
+            }
+            if (type >= 0) {
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    uint8_t* p = chunk(type * 3 + j);
+                    *reinterpret_cast<uint4*>(p) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                    *reinterpret_cast<uint4*>(p + FEAT_PART) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                }
+            }
+            prev_type = type;
+            tc::fence_proxy_async_smem();
+            tc::mbar_arrive(&bars[B_FEAT]);
+        };
+        constexpr uint32_t idesc_t = tc::umma_idesc_bf16(128, 128);
+        constexpr uint32_t idesc_w = tc::umma_idesc_bf16(128, NOUT);
+        const uint32_t sW_u32 = tc::smem_u32(sW), sTab_u32 = tc::smem_u32(sTab), sFeat_u32 = tc::smem_u32(sFeat);
+        auto table_mma = [&]() {                                // MMA warp only
+            if (lane == 0) {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int combo = 0; combo < 3; combo++) {       // hi*hi, hi*lo, lo*hi
+                    const uint32_t fb = sFeat_u32 + (combo == 2 ? FEAT_PART : 0), wb = sTab_u32 + (combo == 1 ? TAB_PART : 0);
+#pragma unroll
+                    for (int ks = 0; ks < KF / 16; ks++) {
+                        tc::umma_bf16(tmem + C_PRE, tc::umma_desc_k16_noswizzle(fb + ks * 4096), tc::umma_desc_k16_noswizzle(wb + ks * 4096), idesc_t, acc);
+                        acc = 1;
+                    }
+                }
+                tc::umma_commit(&bars[B_PRE]);
+            }
+            __syncwarp();
+        };
+        int s_cur = row_src(blockIdx.x);
+        int s_nxt = row_src(blockIdx.x + gridDim.x);
+        features(blockIdx.x, s_cur);
+        if (warp == MMA_WARP) {
             tc::mbar_wait(&bars[B_FEAT], 0);
             tc::tc_fence_after();
             table_mma();
-            uint32_t ph = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
+        }
+        uint32_t ph = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
+            const long long nt = tile + gridDim.x;
+            const bool more = nt < ntiles;
+            // features of the next tile as soon as the table MMA of this one has consumed the operand
+            tc::mbar_wait(&bars[B_PRE], ph);
+            if (more) {
+                s_cur = s_nxt;
+                s_nxt = row_src(nt + gridDim.x);
+                features(nt, s_cur);
+            }
+            if (warp == MMA_WARP) {
                 tc::mbar_wait(&bars[B_HID], ph);
                 tc::tc_fence_after();
                 if (lane == 0) {
@@ -165,72 +235,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
                     tc::umma_commit(&bars[B_OUT]);
                 }
                 __syncwarp();
-                if (tile + gridDim.x < ntiles) {
+                if (more) {
                     tc::mbar_wait(&bars[B_FEAT], ph ^ 1);   // features of the next tile (pre columns are free: HID(t) has fired)
                     tc::tc_fence_after();
                     table_mma();
                 }
-            }
-        } else {
-            // ================= feature warps: edge features of the next tile -> bf16 hi/lo one-hot-typed operand =================
-            const int ft = tid - (MMA_WARP + 1) * 32;       // 0..95; row slots ft and ft + 96
-            int prev_type[2] = {-1, -1};
-            auto features = [&](long long tile) {
-#pragma unroll
-                for (int k = 0; k < 2; k++) {
-                    const int r = ft + k * 96;
-                    if (r >= 128) break;
-                    const KSeg sg = kseg(d, tile, r >> 5);
-                    const int row = r & 31;
-                    int type = -1;
-                    uint32_t hi[12], lo[12];
-                    if (sg.valid && row < sg.R) {
-                        const int s = a.knn_src[sg.e0 + row];
-                        const float x0 = a.x[(size_t)sg.v * 3], x1 = a.x[(size_t)sg.v * 3 + 1], x2 = a.x[(size_t)sg.v * 3 + 2];
-                        const float r0 = x0 - a.x[(size_t)s * 3], r1 = x1 - a.x[(size_t)s * 3 + 1], r2 = x2 - a.x[(size_t)s * 3 + 2];
-                        const float dist = sqrtf(r0 * r0 + r1 * r1 + r2 * r2);
-                        const bool sl = (s - sg.ctx0) >= sg.gp;
-                        type = sl ? (sg.dl ? 0 : 1) : (sg.dl ? 2 : 3);                      // uni_denoiser.py:373-378
-                        float f[24];
-#pragma unroll
-                        for (int gg = 0; gg < 20; gg++) f[gg] = smear_val(dist, gg);
-                        f[20] = 1.0f;
-                        const float* c1 = a.comb + (size_t)s * 3;                             // vec_1 = comb[src]
-                        const float* c2 = a.comb + (size_t)sg.v * 3;                          // vec_2 = comb[dst]
-                        f[21] = c1[0] * c2[0] + c1[1] * c2[1] + c1[2] * c2[2];
-                        f[22] = -(c1[0] * r0 + c1[1] * r1 + c1[2] * r2);                      // vec_3 = x[src] - x[dst]
-                        f[23] = -(c2[0] * r0 + c2[1] * r1 + c2[2] * r2);
-#pragma unroll
-                        for (int i = 0; i < 12; i++) tc::split_pair_trunc(f[2 * i], f[2 * i + 1], hi[i], lo[i]);
-                    }
-                    uint8_t* base = sFeat + (r >> 3) * 256 + (r & 7) * 16;
-                    auto chunk = [&](int c) { return base + (c >> 1) * 4096 + (c & 1) * 128; };
-                    if (prev_type[k] >= 0 && prev_type[k] != type) {
-#pragma unroll
-                        for (int j = 0; j < 3; j++) {
-                            uint8_t* p = chunk(prev_type[k] * 3 + j);
-                            *reinterpret_cast<uint4*>(p) = make_uint4(0, 0, 0, 0);
-                            *reinterpret_cast<uint4*>(p + FEAT_PART) = make_uint4(0, 0, 0, 0);
-                        }
-                    }
-                    if (type >= 0) {
-#pragma unroll
-                        for (int j = 0; j < 3; j++) {
-                            uint8_t* p = chunk(type * 3 + j);
-                            *reinterpret_cast<uint4*>(p) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                            *reinterpret_cast<uint4*>(p + FEAT_PART) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-                        }
-                    }
-                    prev_type[k] = type;
-                }
-                tc::fence_proxy_async_smem();
-                tc::mbar_arrive(&bars[B_FEAT]);
-            };
-            features(blockIdx.x);
-            uint32_t ph = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
-                tc::mbar_wait(&bars[B_PRE], ph);            // the table MMA of this tile has consumed the operand
-                if (tile + gridDim.x < ntiles) features(tile + gridDim.x);
             }
         }
     } else {
@@ -243,17 +252,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
         KSeg psg = kseg(d, blockIdx.x, wq);                 // segment of the tile whose post-processing is pending
         bool prow = false;
         float rel0 = 0.f, rel1 = 0.f, rel2 = 0.f;
+        float4 pf = make_float4(0.f, 0.f, 0.f, 0.f);       // per-row inputs of the pending tile's post-processing, fetched a tile ahead:
+        float pfs = 0.f;                                    //   key pass: e_w (pf.x); value pass: alpha' of the 4 heads, per-head alpha' sum
 
         // ---- post-processing of a finished tile (its out columns: buffer `ob`)
         auto post = [&](uint32_t parity, uint32_t ob) {
             const uint32_t out = tmem + C_OUT + ob * 128 + lane_base;
             if (PASS == 0) {
                 // logits of this thread's 4 heads (key bias dropped: softmax-invariant), softmax over the lanes, times e_w
-                const float* qrow = a.q + (size_t)psg.v * 128 + cq * 32;
+                const float* qrow = sQ + (warp * 2 + ob) * 32;          // staged by this warp one tile ago (cp.async)
                 float4 qv[8];
 #pragma unroll
-                for (int i = 0; i < 8; i++) qv[i] = ldg4(qrow + i * 4);
-                const float ew = prow ? a.ew[psg.e0 + lane] : 0.f;
+                for (int i = 0; i < 8; i++) qv[i] = ld4(qrow + i * 4);
+                const float ew = pf.x;
                 tc::mbar_wait(&bars[B_OUT], parity);
                 tc::tc_fence_after();
                 uint32_t vv[32];
@@ -294,12 +305,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
                 if (prow) st4(a.alpha + (size_t)(psg.e0 + lane) * 16 + cq * 4, make_float4(al[0], al[1], al[2], al[3]));
                 if (psg.valid && lane == 0) st4(a.alpha_sum + (size_t)psg.v * 16 + cq * 4, make_float4(sw[0], sw[1], sw[2], sw[3]));
             } else {
-                float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (prow) a4 = ld4(a.alpha + (size_t)(psg.e0 + lane) * 16 + cq * 4);
+                const float4 a4 = pf;
                 tc::mbar_wait(&bars[B_OUT], parity);
                 tc::tc_fence_after();
                 if (POS == 0) {
-                    const float swc = psg.valid ? a.alpha_sum[(size_t)psg.v * 16 + cq * 4 + (lane >> 3)] : 0.f;
+                    const float swc = pfs;
                     uint32_t vu[32];
                     tc::tmem_ld32_nowait(out + cq * 32, vu);
                     tc::tmem_ld_wait();
@@ -337,36 +347,64 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
 
         uint32_t ph = 0;
         bool any = false;
+        KSeg sg = kseg(d, blockIdx.x, wq);
+        int idx[8];
+        {
+            const int nn = sg.valid ? sg.R : 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int row = (i * 4 + sr) < nn ? (i * 4 + sr) : 0;
+                idx[i] = nn > 0 ? a.knn_src[sg.e0 + row] : 0;
+            }
+        }
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
-            const KSeg sg = kseg(d, tile, wq);
             const bool rowvalid = sg.valid && lane < sg.R;
-            const int nrow = sg.valid ? sg.R : 0;
-            // ---- gather the src-node partial rows: 8 lanes cover the 128-byte slice of one row (coalesced), the rows are
-            //      transposed to row-per-lane through the warp's shared tile (two rounds of 16 rows)
+            // ---- gather the src-node partial rows: 8 lanes cover the 128-byte slice of one row (coalesced), the dst-node
+            //      partial is added in that layout, and the rows are transposed to row-per-lane through the warp's shared
+            //      tile (two rounds of 16 rows).  Neighbour indices were fetched one tile ahead.
             const int c0 = cq * 32;
             const float* ps = a.nc.A + (PASS == 0 ? a.nc.src_k : a.nc.src_v) + c0 + ch;
             float4 u[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int row = (i * 4 + sr) < nrow ? (i * 4 + sr) : 0;
-                const int s = nrow > 0 ? a.knn_src[sg.e0 + row] : 0;
-                u[i] = ldg4(ps + (size_t)s * a.nc.lda);
+            for (int i = 0; i < 8; i++) u[i] = ldg4(ps + (size_t)idx[i] * a.nc.lda);
+            const float4 d4 = ldg4(a.nc.A + (size_t)sg.v * a.nc.lda + (PASS == 0 ? a.nc.dst_k : a.nc.dst_v) + c0 + ch);
+            // this tile's post-processing inputs (consumed one iteration later) and the next tile's neighbour indices
+            float4 nf = make_float4(0.f, 0.f, 0.f, 0.f);
+            float nfs = 0.f;
+            if (PASS == 0) { if (rowvalid) nf.x = a.ew[sg.e0 + lane]; }
+            else {
+                if (rowvalid) nf = ld4(a.alpha + (size_t)(sg.e0 + lane) * 16 + cq * 4);
+                if (POS == 0 && sg.valid) nfs = a.alpha_sum[(size_t)sg.v * 16 + cq * 4 + (lane >> 3)];
             }
-            const float* pd = a.nc.A + (size_t)sg.v * a.nc.lda + (PASS == 0 ? a.nc.dst_k : a.nc.dst_v) + c0;
+            if (PASS == 0 && lane < 8)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(sQ + (warp * 2 + ph) * 32 + lane * 4)),
+                             "l"(a.q + (size_t)sg.v * 128 + c0 + lane * 4) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            const bool more = tile + gridDim.x < ntiles;
+            const KSeg nsg = kseg(d, more ? tile + gridDim.x : tile, wq);
+            int nidx[8];
+            {
+                const int nn = nsg.valid ? nsg.R : 0;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int row = (i * 4 + sr) < nn ? (i * 4 + sr) : 0;
+                    nidx[i] = nn > 0 ? a.knn_src[nsg.e0 + row] : 0;
+                }
+            }
             float2 x2[16];
 #pragma unroll
             for (int round = 0; round < 2; round++) {
                 __syncwarp();
 #pragma unroll
-                for (int i = 0; i < 4; i++) st4(xp + (i * 4 + sr) * XP_LD + ch, u[round * 4 + i]);
+                for (int i = 0; i < 4; i++) st4(xp + (i * 4 + sr) * XP_LD + ch, f4add(u[round * 4 + i], d4));
                 __syncwarp();
                 if ((lane >> 4) == round) {
                     const float* xrow = xp + (lane & 15) * XP_LD;
 #pragma unroll
                     for (int i = 0; i < 16; i += 2) {
-                        const float4 e4 = ld4(xrow + 2 * i), d4 = ldg4(pd + 2 * i);
-                        x2[i] = make_float2(e4.x + d4.x, e4.y + d4.y);
-                        x2[i + 1] = make_float2(e4.z + d4.z, e4.w + d4.w);
+                        const float4 e4 = ld4(xrow + 2 * i);
+                        x2[i] = make_float2(e4.x, e4.y);
+                        x2[i + 1] = make_float2(e4.z, e4.w);
                     }
                 }
             }
@@ -414,8 +452,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
             tc::tc_fence_before();
             tc::mbar_arrive(&bars[B_HID]);
             // ---- post-processing of the previous tile while the tensor pipe works on this one
-            if (any) post(ph ^ 1, ph ^ 1);
-            psg = sg; prow = rowvalid;
+            if (any) { asm volatile("cp.async.wait_group 1;" ::: "memory"); __syncwarp(); post(ph ^ 1, ph ^ 1); }
+            psg = sg; prow = rowvalid; pf = nf; pfs = nfs;
             if (PASS == 1 && POS) {
                 const int s = rowvalid ? a.knn_src[sg.e0 + lane] : sg.v;
                 rel0 = a.x[(size_t)sg.v * 3] - a.x[(size_t)s * 3];                          // rel_x = x[dst] - x[src]
@@ -423,8 +461,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
                 rel2 = a.x[(size_t)sg.v * 3 + 2] - a.x[(size_t)s * 3 + 2];
             }
             any = true;
+            sg = nsg;
+#pragma unroll
+            for (int i = 0; i < 8; i++) idx[i] = nidx[i];
         }
-        if (any) post(ph ^ 1, ph ^ 1);
+        if (any) { asm volatile("cp.async.wait_group 0;" ::: "memory"); __syncwarp(); post(ph ^ 1, ph ^ 1); }
     }
     tc::tc_fence_before();
     __syncthreads();
