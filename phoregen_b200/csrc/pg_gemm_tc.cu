@@ -6,12 +6,13 @@
 // (2^-9) does not meet through six residual layers.
 //
 // Persistent, warp-specialised CTA (one per SM) walking 128-row tiles:
-//   warps 0-3  epilogue      : accumulator (TMEM, double buffered) -> registers -> bias / residual / ReLU -> global
-//   warps 4-7  A producer    : fused prologue (sum of two inputs, or gather-add + LayerNorm + ReLU), bf16 hi/lo split,
+//   warps 0-7  epilogue      : accumulator (TMEM, double buffered) -> registers -> bias / residual / ReLU -> global;
+//                              warp w owns lane quarter w & 3 and column half w >> 2 of every 64-column block
+//   warps 8-11 A producer    : fused prologue (sum of two inputs, or gather-add + LayerNorm + ReLU), bf16 hi/lo split,
 //                              canonical K-major 128B-swizzled UMMA layout, double buffered (next tile while MMAs run)
-//   warp  8    B loader      : weights are stored pre-swizzled, one 32 KB image per 64-column block -> a single
+//   warp  12   B loader      : weights are stored pre-swizzled, one 32 KB image per 64-column block -> a single
 //                              cp.async.bulk (TMA unit) per block into a 2-stage ring, mbarrier transaction counts
-//   warp  9    MMA issuer    : 24 tcgen05.mma (M=128, N=64, K=16) per block, tcgen05.commit releases smem / signals epilogue
+//   warp  13   MMA issuer    : 24 tcgen05.mma (M=128, N=64, K=16) per block, tcgen05.commit releases smem / signals epilogue
 #include <algorithm>
 #include "pg_gemm.h"
 #include "pg_tc.cuh"
@@ -23,10 +24,11 @@ constexpr int A_BUF = 4 * A_KBLK;            // (hi,lo) x 2 K blocks = 64 KB
 constexpr int B_KBLK = TN * 128;             // 8 KB
 constexpr int B_BUF = 4 * B_KBLK;            // (hi,lo) x 2 K blocks = 32 KB  (== one pre-swizzled weight image)
 constexpr int NB = 2;                        // B ring stages
-constexpr int EPI_LD = 36;                     // padded row stride (floats) of the per-warp epilogue staging tile [32 rows x 32 cols]
-constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;   // four epilogue warps
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;   // per epilogue warp: staging tile [32 rows x 32 cols], 16-byte chunks XOR-swizzled by row
 constexpr int SMEM_TOTAL = 2 * A_BUF + NB * B_BUF + EPI_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-constexpr int NTHREADS = 320;
+constexpr int NTHREADS = (EPI_WARPS + 6) * 32;
+constexpr int PROD_WARP0 = EPI_WARPS, LOAD_WARP = EPI_WARPS + 4, MMA_WARP = EPI_WARPS + 5;
 
 enum { A_FULL = 0, A_EMPTY = 2, B_FULL = 4, B_EMPTY = 4 + NB, ACC_FULL = 4 + 2 * NB, ACC_EMPTY = 6 + 2 * NB, NBARS = 8 + 2 * NB };
 
@@ -43,11 +45,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(GemmArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long n_mtiles = (a.M + TM - 1) / TM;
 
-    if (warp == 9) tc::tmem_alloc<2 * TN>(tmem_slot);
+    if (warp == MMA_WARP) tc::tmem_alloc<2 * TN>(tmem_slot);
     if (tid == 0) {
         for (int i = 0; i < 2; i++) {
             tc::mbar_init(&bars[A_FULL + i], 128); tc::mbar_init(&bars[A_EMPTY + i], 1);
-            tc::mbar_init(&bars[ACC_FULL + i], 1); tc::mbar_init(&bars[ACC_EMPTY + i], 128);
+            tc::mbar_init(&bars[ACC_FULL + i], 1); tc::mbar_init(&bars[ACC_EMPTY + i], EPI_WARPS * 32);
         }
         for (int i = 0; i < NB; i++) { tc::mbar_init(&bars[B_FULL + i], 1); tc::mbar_init(&bars[B_EMPTY + i], 1); }
         tc::fence_barrier_init();
@@ -57,52 +59,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(GemmArgs a) {
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < EPI_WARPS) {
         // ================= epilogue =================
         // TMEM row (thread = row) -> per-warp smem tile -> row-contiguous global stores (4 rows x 128 B per instruction)
         long long cnt = 0;
-        float* stg = sEpi + warp * 32 * EPI_LD;
-        const int rsub = lane >> 3, csub = (lane & 7) * 4;
+        float* stg = sEpi + warp * 32 * 32;
+        const int wq = warp & 3, hh = warp >> 2;
+        const int rsub = lane >> 3, cj = lane & 7, csub = cj * 4;
         for (long long mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
-            const long long mw = mt * TM + warp * 32;               // first row of this warp
+            const long long mw = mt * TM + wq * 32;                 // first row of this warp
             for (int nt = 0; nt < a.ntiles; nt++, cnt++) {
                 const int ab = cnt & 1;
                 tc::mbar_wait(&bars[ACC_FULL + ab], (cnt >> 1) & 1);
                 tc::tc_fence_after();
-                uint32_t v[64];
-                tc::tmem_ld32_nowait(tmem_base + ((uint32_t)(warp * 32) << 16) + ab * TN, v);
-                tc::tmem_ld32_nowait(tmem_base + ((uint32_t)(warp * 32) << 16) + ab * TN + 32, v + 32);
+                uint32_t v[32];
+                tc::tmem_ld32_nowait(tmem_base + ((uint32_t)(wq * 32) << 16) + ab * TN + hh * 32, v);
                 tc::tmem_ld_wait();
                 tc::tc_fence_before();
                 tc::mbar_arrive(&bars[ACC_EMPTY + ab]);            // accumulator is in registers: the MMA warp may reuse it
+                const int c0 = nt * TN + hh * 32 + csub;
 #pragma unroll
-                for (int hh = 0; hh < 2; hh++) {
-                    const int c0 = nt * TN + hh * 32 + csub;
+                for (int q = 0; q < 8; q++)
+                    st4(stg + lane * 32 + ((q ^ (lane & 7)) << 2), make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
+                                                                             __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3])));
+                __syncwarp();
+                float4 bb = make_float4(0, 0, 0, 0);
+                if (a.bias) bb = ldg4(a.bias + c0);
 #pragma unroll
-                    for (int q = 0; q < 8; q++)
-                        st4(stg + lane * EPI_LD + q * 4, make_float4(__uint_as_float(v[hh * 32 + q * 4]), __uint_as_float(v[hh * 32 + q * 4 + 1]),
-                                                                     __uint_as_float(v[hh * 32 + q * 4 + 2]), __uint_as_float(v[hh * 32 + q * 4 + 3])));
-                    __syncwarp();
-                    float4 bb = make_float4(0, 0, 0, 0);
-                    if (a.bias) bb = ldg4(a.bias + c0);
-#pragma unroll
-                    for (int rr = 0; rr < 8; rr++) {
-                        const int r = rr * 4 + rsub;
-                        const long long m = mw + r;
-                        if (m < a.M) {
-                            float4 o = f4add(ld4(stg + r * EPI_LD + csub), bb);
-                            if (a.resid) o = f4add(o, ld4(a.resid + m * a.ldr + c0));
-                            if (a.relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
-                            st4(a.C + m * a.ldc + c0, o);
-                        }
+                for (int rr = 0; rr < 8; rr++) {
+                    const int r = rr * 4 + rsub;
+                    const long long m = mw + r;
+                    if (m < a.M) {
+                        float4 o = f4add(ld4(stg + r * 32 + ((cj ^ (r & 7)) << 2)), bb);
+                        if (a.resid) o = f4add(o, ld4(a.resid + m * a.ldr + c0));
+                        if (a.relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+                        st4(a.C + m * a.ldc + c0, o);
                     }
-                    __syncwarp();
                 }
+                __syncwarp();
             }
         }
-    } else if (warp < 8) {
+    } else if (warp < LOAD_WARP) {
         // ================= A producer: fused prologue, bf16 hi/lo split, swizzled K-major layout =================
-        const int pw = warp - 4;
+        const int pw = warp - PROD_WARP0;
         float4 g4 = make_float4(1, 1, 1, 1), b4 = make_float4(0, 0, 0, 0);
         if (PRO == PRO_LNRELU) { g4 = ldg4(a.ln_g + lane * 4); b4 = ldg4(a.ln_b + lane * 4); }
         long long it = 0;
@@ -177,7 +176,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(GemmArgs a) {
             tc::fence_proxy_async_smem();                               // generic-proxy writes -> async proxy (tensor core reads)
             tc::mbar_arrive(&bars[A_FULL + buf]);
         }
-    } else if (warp == 8) {
+    } else if (warp == LOAD_WARP) {
         // ================= B loader: one bulk copy of a pre-swizzled 32 KB weight image per 64-column block =================
         long long cnt = 0;
         for (long long mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
@@ -231,7 +230,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(GemmArgs a) {
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 9) { tc::tc_fence_after(); tc::tmem_dealloc<2 * TN>(tmem_base); }
+    if (warp == MMA_WARP) { tc::tc_fence_after(); tc::tmem_dealloc<2 * TN>(tmem_base); }
 }
 }  // namespace
 

@@ -134,7 +134,8 @@ def test_phore_encoder_and_denoiser_layers_match_reference_golden(model, dev):
 
 
 # ---------------------------------------------------------------- forward: oracle on fresh inputs, ragged sizes
-@pytest.mark.parametrize("seed,n_graphs,n_atoms,n_ex", [(101, 3, (2, 6), 0), (102, 2, (33, 41), 0), (103, 1, 17, 80)])
+@pytest.mark.parametrize("seed,n_graphs,n_atoms,n_ex", [(101, 3, (2, 6), 0), (102, 2, (33, 41), 0), (103, 1, 17, 80),
+                                                          (104, 5, (2, 3), 0), (105, 4, (28, 37), 6)])
 def test_forward_matches_oracle(model, dev, seed, n_graphs, n_atoms, n_ex):
     m, sd = model
     # the kNN graphs are discontinuous in the coordinates: take the first seed whose forward pass stays away from a
