@@ -8,11 +8,11 @@
 // Persistent, warp-specialised CTA (one per SM) walking 128-row tiles:
 //   warps 0-7  epilogue      : accumulator (TMEM, double buffered) -> registers -> bias / residual / ReLU -> global;
 //                              warp w owns lane quarter w & 3 and column half w >> 2 of every 64-column block
-//   warps 8-11 A producer    : fused prologue (sum of two inputs, or gather-add + LayerNorm + ReLU), bf16 hi/lo split,
+//   warps 8-15 A producer    : fused prologue (sum of two inputs, or gather-add + LayerNorm + ReLU), bf16 hi/lo split,
 //                              canonical K-major 128B-swizzled UMMA layout, double buffered (next tile while MMAs run)
-//   warp  12   B loader      : weights are stored pre-swizzled, one 32 KB image per 64-column block -> a single
+//   warp  16   B loader      : weights are stored pre-swizzled, one 32 KB image per 64-column block -> a single
 //                              cp.async.bulk (TMA unit) per block into a 2-stage ring, mbarrier transaction counts
-//   warp  13   MMA issuer    : 24 tcgen05.mma (M=128, N=64, K=16) per block, tcgen05.commit releases smem / signals epilogue
+//   warp  17   MMA issuer    : 24 tcgen05.mma (M=128, N=64, K=16) per block, tcgen05.commit releases smem / signals epilogue
 #include <algorithm>
 #include "pg_gemm.h"
 #include "pg_tc.cuh"
@@ -27,8 +27,9 @@ constexpr int NB = 2;                        // B ring stages
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;   // per epilogue warp: staging tile [32 rows x 32 cols], 16-byte chunks XOR-swizzled by row
 constexpr int SMEM_TOTAL = 2 * A_BUF + NB * B_BUF + EPI_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-constexpr int NTHREADS = (EPI_WARPS + 6) * 32;
-constexpr int PROD_WARP0 = EPI_WARPS, LOAD_WARP = EPI_WARPS + 4, MMA_WARP = EPI_WARPS + 5;
+constexpr int PROD_WARPS = 8;
+constexpr int NTHREADS = (EPI_WARPS + PROD_WARPS + 2) * 32;
+constexpr int PROD_WARP0 = EPI_WARPS, LOAD_WARP = EPI_WARPS + PROD_WARPS, MMA_WARP = LOAD_WARP + 1;
 
 enum { A_FULL = 0, A_EMPTY = 2, B_FULL = 4, B_EMPTY = 4 + NB, ACC_FULL = 4 + 2 * NB, ACC_EMPTY = 6 + 2 * NB, NBARS = 8 + 2 * NB };
 
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(GemmArgs a) {
     if (warp == MMA_WARP) tc::tmem_alloc<2 * TN>(tmem_slot);
     if (tid == 0) {
         for (int i = 0; i < 2; i++) {
-            tc::mbar_init(&bars[A_FULL + i], 128); tc::mbar_init(&bars[A_EMPTY + i], 1);
+            tc::mbar_init(&bars[A_FULL + i], PROD_WARPS * 32); tc::mbar_init(&bars[A_EMPTY + i], 1);
             tc::mbar_init(&bars[ACC_FULL + i], 1); tc::mbar_init(&bars[ACC_EMPTY + i], EPI_WARPS * 32);
         }
         for (int i = 0; i < NB; i++) { tc::mbar_init(&bars[B_FULL + i], 1); tc::mbar_init(&bars[B_EMPTY + i], 1); }
@@ -110,14 +111,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(GemmArgs a) {
             tc::mbar_wait(&bars[A_EMPTY + buf], ((it >> 1) & 1) ^ 1);   // MMAs that read this buffer two tiles ago are done
             uint8_t* dstA = sA + buf * A_BUF;
             const long long m0 = mt * TM;
-            // rows pw, pw+4, ...: loads of a whole batch are issued before any is consumed (enough bytes in flight per SM
+            // rows pw, pw+PROD_WARPS, ...: loads of a whole batch are issued before any is consumed (enough bytes in flight per SM
             // to cover HBM latency: Little's law needs ~28 KB at 23 B/clk/SM)
             constexpr int BATCH = (PRO == PRO_PLAIN) ? 16 : 8;
-            for (int rb = 0; rb < TM / 4; rb += BATCH) {
+            for (int rb = 0; rb < TM / PROD_WARPS; rb += BATCH) {
                 float4 v[BATCH], w[BATCH];
 #pragma unroll
                 for (int i = 0; i < BATCH; i++) {
-                    const long long m = m0 + pw + (rb + i) * 4;
+                    const long long m = m0 + pw + (rb + i) * PROD_WARPS;
                     v[i] = make_float4(0, 0, 0, 0); w[i] = v[i];
                     if (m < a.M) {
                         v[i] = ld4(a.A + m * a.lda + lane * 4);
@@ -156,12 +157,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(GemmArgs a) {
                         const float rstd = rsqrtf(s2[i] * (1.0f / 128.0f) + 1e-5f);
                         v[i] = make_float4(fmaxf(fmaf(v[i].x * rstd, g4.x, b4.x), 0.f), fmaxf(fmaf(v[i].y * rstd, g4.y, b4.y), 0.f),
                                            fmaxf(fmaf(v[i].z * rstd, g4.z, b4.z), 0.f), fmaxf(fmaf(v[i].w * rstd, g4.w, b4.w), 0.f));
-                        if (m0 + pw + (rb + i) * 4 >= a.M) v[i] = make_float4(0, 0, 0, 0);
+                        if (m0 + pw + (rb + i) * PROD_WARPS >= a.M) v[i] = make_float4(0, 0, 0, 0);
                     }
                 }
 #pragma unroll
                 for (int i = 0; i < BATCH; i++) {
-                    const int r = pw + (rb + i) * 4;
+                    const int r = pw + (rb + i) * PROD_WARPS;
                     const float4 x = v[i];
                     uint32_t h0, l0, h1, l1;
                     tc::split_pair_trunc(x.x, x.y, h0, l0);
