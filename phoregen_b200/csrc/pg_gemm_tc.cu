@@ -116,18 +116,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(GemmArgs a) {
             constexpr int BATCH = (PRO == PRO_PLAIN) ? 16 : 8;
             for (int rb = 0; rb < TM / PROD_WARPS; rb += BATCH) {
                 float4 v[BATCH], w[BATCH];
+                // gather indices of the whole batch first: one round trip instead of one per row (the warp issues in order)
+                long long gi[BATCH];
+                if (PRO == PRO_LNRELU) {
+#pragma unroll
+                    for (int i = 0; i < BATCH; i++) {
+                        const long long m = min(m0 + pw + (long long)(rb + i) * PROD_WARPS, a.M - 1);
+                        gi[i] = (a.A2 && a.gidx) ? (long long)__ldg(a.gidx + m) : m;
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < BATCH; i++) {
                     const long long m = m0 + pw + (rb + i) * PROD_WARPS;
-                    v[i] = make_float4(0, 0, 0, 0); w[i] = v[i];
-                    if (m < a.M) {
-                        v[i] = ld4(a.A + m * a.lda + lane * 4);
-                        if (PRO == PRO_SUM2) w[i] = ld4(a.A2 + m * a.lda2 + lane * 4);
-                        if (PRO == PRO_LNRELU && a.A2) {
-                            const long long idx = a.gidx ? (long long)a.gidx[m] : m;
-                            w[i] = ld4(a.A2 + idx * a.lda2 + lane * 4);
-                        }
-                    }
+                    const long long mc = min(m, a.M - 1);           // rows past the end re-read the last row and are zeroed below
+                    v[i] = ld4(a.A + mc * a.lda + lane * 4);
+                    w[i] = make_float4(0, 0, 0, 0);
+                    if (PRO == PRO_SUM2) w[i] = ld4(a.A2 + mc * a.lda2 + lane * 4);
+                    if (PRO == PRO_LNRELU && a.A2) w[i] = ld4(a.A2 + gi[i] * a.lda2 + lane * 4);
+                    if (m >= a.M) { v[i] = make_float4(0, 0, 0, 0); w[i] = v[i]; }
                 }
                 if (PRO != PRO_PLAIN) {
 #pragma unroll
