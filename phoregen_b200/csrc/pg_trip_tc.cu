@@ -504,18 +504,36 @@ __global__ void __launch_bounds__(256, 2) trip_pr_kernel(TripTcArgs a) {
     if (e0 >= d.Eb) return;
     float mine[PR_EDGES];
     unsigned long long acc[PR_EDGES][8];
+    // the warp issues in order: every dependent load level (indices -> coordinates / partial rows) is requested for all
+    // edges of the warp before the first use, so the warp pays one memory round trip per level instead of one per edge
+    long long ee[PR_EDGES];
+    int sn[PR_EDGES], tn[PR_EDGES];
 #pragma unroll
     for (int k = 0; k < PR_EDGES; k++) {
-        const long long e = min(e0 + k, d.Eb - 1);
-        const int s = d.esrc_node[e], t = d.edst_node[e];
-        const float d0 = a.x[(size_t)t * 3] - a.x[(size_t)s * 3], d1 = a.x[(size_t)t * 3 + 1] - a.x[(size_t)s * 3 + 1],
-                    d2 = a.x[(size_t)t * 3 + 2] - a.x[(size_t)s * 3 + 2];
+        ee[k] = min(e0 + k, d.Eb - 1);
+        sn[k] = d.esrc_node[ee[k]]; tn[k] = d.edst_node[ee[k]];
+    }
+    float4 tk[PR_EDGES], tv[PR_EDGES];
+#pragma unroll
+    for (int k = 0; k < PR_EDGES; k++) {
+        tk[k] = ldg4(a.T + (size_t)ee[k] * a.ldt + a.t_k + lane * 4);
+        tv[k] = ldg4(a.T + (size_t)ee[k] * a.ldt + a.t_v + lane * 4);
+    }
+    float xs[PR_EDGES][3], xt[PR_EDGES][3];
+#pragma unroll
+    for (int k = 0; k < PR_EDGES; k++) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { xs[k][c] = a.x[(size_t)sn[k] * 3 + c]; xt[k][c] = a.x[(size_t)tn[k] * 3 + c]; }
+    }
+#pragma unroll
+    for (int k = 0; k < PR_EDGES; k++) {
+        const float4 hs0 = ldg4(a.H + (size_t)sn[k] * a.ldh + a.hk_k + lane * 4), ht0 = ldg4(a.H + (size_t)tn[k] * a.ldh + a.hj_k + lane * 4);
+        const float4 hs1 = ldg4(a.H + (size_t)sn[k] * a.ldh + a.hk_v + lane * 4), ht1 = ldg4(a.H + (size_t)tn[k] * a.ldh + a.hj_v + lane * 4);
+        const float d0 = xt[k][0] - xs[k][0], d1 = xt[k][1] - xs[k][1], d2 = xt[k][2] - xs[k][2];
         const float dist = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
         mine[k] = lane < 20 ? smear_val(dist, lane) : 0.f;
-        const float4 p0 = f4add(f4add(ldg4(a.T + (size_t)e * a.ldt + a.t_k + lane * 4), ldg4(a.H + (size_t)s * a.ldh + a.hk_k + lane * 4)),
-                                ldg4(a.H + (size_t)t * a.ldh + a.hj_k + lane * 4));
-        const float4 p1 = f4add(f4add(ldg4(a.T + (size_t)e * a.ldt + a.t_v + lane * 4), ldg4(a.H + (size_t)s * a.ldh + a.hk_v + lane * 4)),
-                                ldg4(a.H + (size_t)t * a.ldh + a.hj_v + lane * 4));
+        const float4 p0 = f4add(f4add(tk[k], hs0), ht0);
+        const float4 p1 = f4add(f4add(tv[k], hs1), ht1);
         acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0ull;
         acc[k][4] = pk2(p0.x, p0.y); acc[k][5] = pk2(p0.z, p0.w); acc[k][6] = pk2(p1.x, p1.y); acc[k][7] = pk2(p1.z, p1.w);
     }
