@@ -19,6 +19,15 @@
 #include "pg_attn.h"
 #include "pg_tc.cuh"
 
+// Optional phase tracing (debug builds only, -DPG_TRIP_TRACE): cycle stamps of CTA 0, key pass
+#ifdef PG_TRIP_TRACE
+__device__ long long g_knn_trace[2 * 64 * 16];
+extern "C" int pg_debug_knn_trace(long long* h_out) { return cudaMemcpyFromSymbol(h_out, g_knn_trace, sizeof(g_knn_trace)) == cudaSuccess ? 0 : -2; }
+#define KTRACE(role, slot) do { if (PASS == 0 && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 16) && tcount < 64) g_knn_trace[((role) * 64 + tcount) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define KTRACE(role, slot) do {} while (0)
+#endif
+
 namespace {
 constexpr int W_TILE = 32768;               // one [128 x 128] bf16 matrix in two 128B-swizzled K blocks
 constexpr int SM_W = 2 * W_TILE;            // hi, lo
@@ -205,18 +214,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
             table_mma();
         }
         uint32_t ph = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
+        int tcount = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1, tcount++) {
             const long long nt = tile + gridDim.x;
             const bool more = nt < ntiles;
+            KTRACE(1, 0);
             // features of the next tile as soon as the table MMA of this one has consumed the operand
             tc::mbar_wait(&bars[B_PRE], ph);
+            KTRACE(1, 1);
             if (more) {
                 s_cur = s_nxt;
                 s_nxt = row_src(nt + gridDim.x);
                 features(nt, s_cur);
             }
+            KTRACE(1, 2);
             if (warp == MMA_WARP) {
                 tc::mbar_wait(&bars[B_HID], ph);
+                KTRACE(1, 3);
                 tc::tc_fence_after();
                 if (lane == 0) {
                     const uint32_t dcol = tmem + C_OUT + ph * 128;
@@ -235,10 +249,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
                     tc::umma_commit(&bars[B_OUT]);
                 }
                 __syncwarp();
+                KTRACE(1, 4);
                 if (more) {
                     tc::mbar_wait(&bars[B_FEAT], ph ^ 1);   // features of the next tile (pre columns are free: HID(t) has fired)
                     tc::tc_fence_after();
+                    KTRACE(1, 5);
                     table_mma();
+                    KTRACE(1, 6);
                 }
             }
         }
@@ -255,6 +272,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
         float4 pf = make_float4(0.f, 0.f, 0.f, 0.f);       // per-row inputs of the pending tile's post-processing, fetched a tile ahead:
         float pfs = 0.f;                                    //   key pass: e_w (pf.x); value pass: alpha' of the 4 heads, per-head alpha' sum
 
+        int tcount = 0;
         // ---- post-processing of a finished tile (its out columns: buffer `ob`)
         auto post = [&](uint32_t parity, uint32_t ob) {
             const uint32_t out = tmem + C_OUT + ob * 128 + lane_base;
@@ -265,11 +283,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
 #pragma unroll
                 for (int i = 0; i < 8; i++) qv[i] = ld4(qrow + i * 4);
                 const float ew = pf.x;
+                KTRACE(0, 8);
                 tc::mbar_wait(&bars[B_OUT], parity);
                 tc::tc_fence_after();
+                KTRACE(0, 9);
                 uint32_t vv[32];
                 tc::tmem_ld32_nowait(out + cq * 32, vv);
                 tc::tmem_ld_wait();
+                KTRACE(0, 10);
                 constexpr float kScale = kInvSqrtD * 1.4426950408889634f;
 #pragma unroll
                 for (int h = 0; h < 4; h++) {
@@ -283,6 +304,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
                     al[h] = prow ? (s0.x + s0.y) * kScale : -INFINITY;
                 }
                 float mx[4], sm[4];
+                KTRACE(0, 11);
 #pragma unroll
                 for (int h = 0; h < 4; h++) mx[h] = al[h];
 #pragma unroll
@@ -302,6 +324,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
                 for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
                     for (int h = 0; h < 4; h++) sw[h] += __shfl_xor_sync(PG_FULL, sw[h], o);
+                KTRACE(0, 12);
                 if (prow) st4(a.alpha + (size_t)(psg.e0 + lane) * 16 + cq * 4, make_float4(al[0], al[1], al[2], al[3]));
                 if (psg.valid && lane == 0) st4(a.alpha_sum + (size_t)psg.v * 16 + cq * 4, make_float4(sw[0], sw[1], sw[2], sw[3]));
             } else {
@@ -357,8 +380,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
                 idx[i] = nn > 0 ? a.knn_src[sg.e0 + row] : 0;
             }
         }
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1, tcount++) {
             const bool rowvalid = sg.valid && lane < sg.R;
+            KTRACE(0, 0);
             // ---- gather the src-node partial rows: 8 lanes cover the 128-byte slice of one row (coalesced), the dst-node
             //      partial is added in that layout, and the rows are transposed to row-per-lane through the warp's shared
             //      tile (two rounds of 16 rows).  Neighbour indices were fetched one tile ahead.
@@ -380,8 +404,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(sQ + (warp * 2 + ph) * 32 + lane * 4)),
                              "l"(a.q + (size_t)sg.v * 128 + c0 + lane * 4) : "memory");
             asm volatile("cp.async.commit_group;" ::: "memory");
+            KTRACE(0, 13);
             const bool more = tile + gridDim.x < ntiles;
             const KSeg nsg = kseg(d, more ? tile + gridDim.x : tile, wq);
+            KTRACE(0, 14);
             int nidx[8];
             {
                 const int nn = nsg.valid ? nsg.R : 0;
@@ -392,6 +418,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
                 }
             }
             float2 x2[16];
+            KTRACE(0, 1);
 #pragma unroll
             for (int round = 0; round < 2; round++) {
                 __syncwarp();
@@ -409,8 +436,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
                 }
             }
             // ---- table product from TMEM, LayerNorm + ReLU, bf16 hi/lo A operand
+            KTRACE(0, 2);
             tc::mbar_wait(&bars[B_PRE], ph);
             tc::tc_fence_after();
+            KTRACE(0, 3);
             {
                 uint32_t xu[32];
                 tc::tmem_ld32_nowait(tmem + C_PRE + lane_base + cq * 32, xu);
@@ -428,6 +457,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
             float* st = sStat + ((wq * 32 + lane) * 4) * 2;
             *reinterpret_cast<float2*>(st + cq * 2) = make_float2(s1.x + s1.y, s2.x + s2.y);
             asm volatile("bar.sync %0, 128;" ::"r"(3 + wq) : "memory");
+            KTRACE(0, 4);
             const float4 sa4 = ld4(st), sb4 = ld4(st + 4);
             const float mu = ((sa4.x + sa4.z) + (sb4.x + sb4.z)) * (1.0f / 128.0f);
             const float rstd = rsqrtf(fmaxf(fmaf(-mu, mu, ((sa4.y + sa4.w) + (sb4.y + sb4.w)) * (1.0f / 128.0f)), 0.f) + 1e-5f);
@@ -451,8 +481,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
             tc::tmem_st_wait();
             tc::tc_fence_before();
             tc::mbar_arrive(&bars[B_HID]);
+            KTRACE(0, 5);
             // ---- post-processing of the previous tile while the tensor pipe works on this one
             if (any) { asm volatile("cp.async.wait_group 1;" ::: "memory"); __syncwarp(); post(ph ^ 1, ph ^ 1); }
+            KTRACE(0, 6);
             psg = sg; prow = rowvalid; pf = nf; pfs = nfs;
             if (PASS == 1 && POS) {
                 const int s = rowvalid ? a.knn_src[sg.e0 + lane] : sg.v;
