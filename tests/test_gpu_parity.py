@@ -420,3 +420,36 @@ def test_tcgen05_gemm_matches_fp32_kernel_and_fp64(dev):
                                    P(Wt_d), P(Wbf), P(bias), None, 0, P(C), N, nt, st), "pg_gemm_k128")
             err = float((C.double() - want).abs().max())
             assert err < tol, f"impl {impl} M={M} N={N} pro={pro}: max err {err:.2e}"
+
+
+# ---------------------------------------------------------------- tcgen05 kernels vs the fp32 FFMA kernels of the same library
+_AB_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+from helpers import build_model, load_golden
+from oracle import phoregen_oracle as O
+dev = torch.device("cuda:0")
+m, _ = build_model(dev)
+f = load_golden("forward_n30.pt")
+b = O.synthetic_batch(f["seed"], f["n_graphs"], n_atoms=f["n_atoms"], n_ex=f["n_ex"])
+ph = b["phore"]; to = lambda t: t.to(dev)
+out = m(to(b["h_node"]), to(b["pos"]), to(b["batch_node"]), to(b["h_edge"]), to(b["edge_index"]), to(b["batch_edge"]),
+        torch.tensor(f["times"], dtype=torch.long, device=dev), to(ph["x"]), to(ph["pos"]), to(ph["norm"]), to(ph["batch"]))
+torch.save([o.cpu() for o in out[:3]], sys.argv[2])
+"""
+
+
+def test_tensor_core_kernels_match_fp32_kernels(tmp_path):
+    """The same forward pass with every tcgen05 kernel switched off (PG_GEMM=simt, PG_TRIP / PG_BOND / PG_KNN_ATTN=fp32: the
+    fp32 FFMA kernels that also serve out-of-range shapes) must agree with the default path and with the reference golden."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for name, env in (("tc", {}), ("fp32", {"PG_GEMM": "simt", "PG_TRIP": "fp32", "PG_BOND": "fp32", "PG_KNN_ATTN": "fp32"})):
+        path = str(tmp_path / f"{name}.pt")
+        subprocess.run([sys.executable, "-c", _AB_SCRIPT, root, path], check=True, env={**os.environ, **env}, timeout=600)
+        outs[name] = torch.load(path)
+    f = load_golden("forward_n30.pt")
+    for k, what in enumerate(("pred_node", "pred_pos", "pred_edge")):
+        assert_close(outs["tc"][k], outs["fp32"][k], f"tcgen05 vs fp32 kernels: {what}")
+        assert_close(outs["fp32"][k], f[what], f"fp32 kernels vs reference golden: {what}")
