@@ -95,6 +95,7 @@ struct TripTcArgs {
     const float *wrkj, *wrji;              // [20][256] fp32
     const uint16_t *w2k_bf, *w2v_bf;       // [hi|lo][128][128] bf16, K-major
     const uint16_t* wa_bf;                 // [hi|lo][256][16] bf16 (angle slice, 13 used)
+    int flags;                             // experiment switches (PG_TRIP_FLAGS): bit 0 = shuffle-butterfly softmax instead of REDUX
     const float *lnk_g, *lnk_b, *lnv_g, *lnv_b, *b2k, *b2v;
     float* hb;
     int maxn;

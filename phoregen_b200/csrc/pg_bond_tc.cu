@@ -318,21 +318,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
                     s0 = tc::add2(s0, s1);
                     al[h] = rowvalid ? (s0.x + s0.y) * kScale : -INFINITY;
                 }
-                float mx[4], sm[4];
+                // segment softmax across the 32 lanes: max and sum on the REDUX unit
 #pragma unroll
-                for (int h = 0; h < 4; h++) mx[h] = al[h];
+                for (int h = 0; h < 4; h++) {
+                    const float mx = tc::warp_max_redux(al[h]);
+                    al[h] = rowvalid ? tc::ex2_approx(al[h] - mx) : 0.f;
+                }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                    for (int h = 0; h < 4; h++) mx[h] = fmaxf(mx[h], __shfl_xor_sync(PG_FULL, mx[h], o));
-#pragma unroll
-                for (int h = 0; h < 4; h++) { al[h] = rowvalid ? tc::ex2_approx(al[h] - mx[h]) : 0.f; sm[h] = al[h]; }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                    for (int h = 0; h < 4; h++) sm[h] += __shfl_xor_sync(PG_FULL, sm[h], o);
-#pragma unroll
-                for (int h = 0; h < 4; h++) al[h] = rowvalid ? al[h] * __frcp_rn(sm[h]) : 0.f;
+                for (int h = 0; h < 4; h++) {
+                    const float ssum = tc::warp_sum01_redux(al[h]);      // every lane takes part in the reduction (not under the ?:)
+                    al[h] = rowvalid ? al[h] * __frcp_rn(ssum) : 0.f;
+                }
             }
             prev_valid = sg.valid; prev_v = sg.v;
             if (POS) {

@@ -407,6 +407,7 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
                 t.wrkj = a.wrkj; t.wrji = a.wrji;
                 t.w2k_bf = (const uint16_t*)w(L + "tr.w2k.bf"); t.w2v_bf = (const uint16_t*)w(L + "tr.w2v.bf");
                 t.wa_bf = (const uint16_t*)w(L + "tr.wa.bf");
+                { static int fl = -1; if (fl < 0) { const char* e = getenv("PG_TRIP_FLAGS"); fl = e ? atoi(e) : 0; } t.flags = fl; }
                 t.lnk_g = a.w.lnk_g; t.lnk_b = a.w.lnk_b; t.lnv_g = a.w.lnv_g; t.lnv_b = a.w.lnv_b; t.b2k = a.w.b2k; t.b2v = a.w.b2v;
                 t.hb = p->hb; t.maxn = std::min(d.max_n, PG_TRIP_TC_MAX_ATOMS);
                 { PgTimed timed(p, KC_OTHER, s); PG_TRY(pg_launch_trip_pr(t, s)); }

@@ -177,6 +177,20 @@ __device__ __forceinline__ void split_pair_relu(float2 y, uint32_t& hi, uint32_t
     const float2 d = *reinterpret_cast<float2*>(&r);
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d.y), "f"(d.x));
 }
+// Warp-wide reductions on the REDUX unit (one instruction instead of a 5-round shuffle butterfly).
+__device__ __forceinline__ float warp_max_redux(float x) {        // sm_100a: redux.sync on f32
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(x));
+    return r;
+}
+// Sum of 32 values in [0, 1]: fixed point with 23 fractional bits (sum <= 2^28), every term rounded to nearest, so the
+// result is within 32 * 2^-24 of the exact sum and independent of the lane order.
+__device__ __forceinline__ float warp_sum01_redux(float x) {
+    const uint32_t q = __float2uint_rn(x * 8388608.0f);
+    uint32_t r;
+    asm volatile("redux.sync.add.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(q));
+    return (float)r * (1.0f / 8388608.0f);
+}
 __device__ __forceinline__ float ex2_approx(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
