@@ -524,32 +524,45 @@ __global__ void __launch_bounds__(TRIP_WARPS * 32) trip_kernel(TripArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------ global edge weight
-// e_w = sigmoid(MLP(20->128->LN->ReLU->1)(smear(|x_dst - x_src|)))  (uni_denoiser.py:410-415); warp per edge.
+// e_w = sigmoid(MLP(20->128->LN->ReLU->1)(smear(|x_dst - x_src|)))  (uni_denoiser.py:410-415).
+// Warp per destination node: its <= 32 kNN edges are contiguous, so the neighbour indices and distances are fetched by
+// the lanes in one round trip, and the first-Linear rows stay in registers across the edges.
 __global__ void __launch_bounds__(256) edge_weight_kernel(PlanDev d, const float* __restrict__ x,
                                                           const int* __restrict__ knn_src, const float* __restrict__ w1t,
                                                           const float* __restrict__ b1, const float* __restrict__ g,
                                                           const float* __restrict__ b, const float* __restrict__ w2,
                                                           const float* __restrict__ b2, float* __restrict__ ew) {
     const int lane = threadIdx.x & 31;
-    const long long e = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (e >= d.Ek) return;
-    // dst of kNN edge e: binary search over graphs, then division by the per-node degree
-    int lo = 0, hi = d.G - 1;
-    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (d.koff[mid] <= e) lo = mid; else hi = mid - 1; }
-    const int gph = lo;
+    const int v = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (v >= d.N) return;
+    const int gph = d.node_graph[v];
     const int ng = d.g_n[gph] + d.g_p[gph];
-    const int kk = min(PG_KNN, ng - 1);
-    const int v = d.ctx_off[gph] + (int)((e - d.koff[gph]) / kk);
-    const int s = knn_src[e];
-    const float r0 = x[(size_t)v * 3] - x[(size_t)s * 3], r1 = x[(size_t)v * 3 + 1] - x[(size_t)s * 3 + 1], r2 = x[(size_t)v * 3 + 2] - x[(size_t)s * 3 + 2];
-    const float dist = sqrtf(r0 * r0 + r1 * r1 + r2 * r2);
-    float4 pre = ldg4(b1 + lane * 4);
-    const float mine = lane < 20 ? smear_val(dist, lane) : 0.f;
+    const int R = min(PG_KNN, ng - 1);
+    if (R <= 0) return;
+    const long long e0 = d.koff[gph] + (long long)(v - d.ctx_off[gph]) * R;
+    float dist = 0.f;
+    if (lane < R) {
+        const int s = knn_src[e0 + lane];
+        const float r0 = x[(size_t)v * 3] - x[(size_t)s * 3], r1 = x[(size_t)v * 3 + 1] - x[(size_t)s * 3 + 1], r2 = x[(size_t)v * 3 + 2] - x[(size_t)s * 3 + 2];
+        dist = sqrtf(r0 * r0 + r1 * r1 + r2 * r2);
+    }
+    float4 w[20];
 #pragma unroll
-    for (int gg = 0; gg < 20; gg++) pre = f4fma(__shfl_sync(PG_FULL, mine, gg), ldg4(w1t + gg * 128 + lane * 4), pre);
-    const float4 hid = ln_relu_row(pre, ldg4(g + lane * 4), ldg4(b + lane * 4));
-    const float logit = warp_sum(f4dot(hid, ldg4(w2 + lane * 4))) + __ldg(b2);
-    if (lane == 0) ew[e] = 1.0f / (1.0f + expf(-logit));
+    for (int gg = 0; gg < 20; gg++) w[gg] = ldg4(w1t + gg * 128 + lane * 4);
+    const float4 bias = ldg4(b1 + lane * 4), g4 = ldg4(g + lane * 4), b4 = ldg4(b + lane * 4), w24 = ldg4(w2 + lane * 4);
+    const float bb2 = __ldg(b2);
+    float mine_out = 0.f;
+    for (int r = 0; r < R; r++) {
+        const float dr = __shfl_sync(PG_FULL, dist, r);
+        const float mine = lane < 20 ? smear_val(dr, lane) : 0.f;
+        float4 pre = bias;
+#pragma unroll
+        for (int gg = 0; gg < 20; gg++) pre = f4fma(__shfl_sync(PG_FULL, mine, gg), w[gg], pre);
+        const float4 hid = ln_relu_row(pre, g4, b4);
+        const float logit = warp_sum(f4dot(hid, w24)) + bb2;
+        if (lane == r) mine_out = 1.0f / (1.0f + expf(-logit));
+    }
+    if (lane < R) ew[e0 + lane] = mine_out;
 }
 }  // namespace
 
@@ -609,7 +622,7 @@ int pg_launch_trip(const TripArgs& a, cudaStream_t s) {
 int pg_launch_edge_weight(const PlanDev& d, const float* x, const int* knn_src, const float* w1t, const float* b1,
                           const float* g, const float* b, const float* w2, const float* b2, float* ew, cudaStream_t s) {
     if (d.Ek <= 0) return PG_OK;
-    edge_weight_kernel<<<(unsigned)((d.Ek + 7) / 8), 256, 0, s>>>(d, x, knn_src, w1t, b1, g, b, w2, b2, ew);
+    edge_weight_kernel<<<(unsigned)((d.N + 7) / 8), 256, 0, s>>>(d, x, knn_src, w1t, b1, g, b, w2, b2, ew);
     PG_LAUNCH_CHECK();
     return PG_OK;
 }
