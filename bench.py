@@ -189,8 +189,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def stage(msg):                      # progress markers on stderr (PG_BENCH_TRACE=1): where a slow or stuck run is
+        if os.environ.get("PG_BENCH_TRACE"):
+            torch.cuda.synchronize(dev)
+            print(f"[bench] {msg}", file=sys.stderr, flush=True)
+
     # ---- warm-up (also captures the CUDA graph of the step)
+    stage("sampler built")
     smp.run(max(W, 3))
+    stage("warm-up + graph capture done")
     launches_per_step = None
     barrier()
     # ---- timed region: device-resident state, CUDA-graph replay of the whole step
@@ -209,6 +216,7 @@ def run_ours(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     clk = clocks.stop()
+    stage("timed region done")
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -220,6 +228,7 @@ def run_ours(args):
     eager = TrajectorySampler(model, None, G, dev, ligand_num_atoms=b["num_atoms"], save_traj=False, seed=1, use_cuda_graph=False,
                               phore_batch=ph)
     eager.run(2)
+    stage("eager sampler ran")
     c0 = eager.plan.launches
     eager.plan.timing(True)
     n_prof = 3
@@ -227,6 +236,7 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     timing = eager.plan.read_timing()
     eager.plan.timing(False)
+    stage("per-class timing pass done")
     launches_per_step = (eager.plan.launches - c0) // n_prof + 3          # + node/edge categorical + position kernels
     trip_ms, trip_n = timing["trip"]
     class_ms = {k: v[0] / n_prof for k, v in timing.items()}
@@ -258,6 +268,7 @@ def run_ours(args):
     for _ in range(3):
         e2e_step()
     barrier()
+    stage("e2e warm-up done")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_e2e = max(3, min(K, 10))
     e0.record()

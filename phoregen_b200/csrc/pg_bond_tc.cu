@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
     float* sB2 = sLn + 4 * 128;                     // b2v (128 or 16)
     uint64_t* bars = (uint64_t*)(sB2 + 128);
     uint32_t* tmem_slot = (uint32_t*)(bars + B_COUNT);
+    volatile int* sProg = (volatile int*)(tmem_slot + 1);   // tiles whose value LayerNorm is done (pacing of the prefetch warps)
     const PlanDev& d = a.d;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wq = warp & 3;
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
         tc::mbar_init(&bars[B_HIDK], ROW_THREADS); tc::mbar_init(&bars[B_HIDV], ROW_THREADS);
         tc::mbar_init(&bars[B_OUTK], 1); tc::mbar_init(&bars[B_OUTV], 1);
         tc::fence_barrier_init();
+        *sProg = 0;
     }
     // ---- resident weights: 16-byte chunks [mat 4][n][chunk 16] -> 128B-swizzled K-major tiles
     for (int idx = tid; idx < 4 * 128 * 16; idx += NTHREADS) {
@@ -138,7 +140,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
             // ================= idle warps: pull the next tile's per-edge rows (the only HBM stream) into L2 =================
             const int pt = tid - (MMA_WARP + 1) * 32;      // 0..95
             uint32_t ph = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
+            int k = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1, k++) {
                 const long long nt = tile + gridDim.x;
                 if (nt < ntiles) {
                     for (int s4 = 0; s4 < 4; s4++) {
@@ -150,7 +153,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
                         }
                     }
                 }
-                tc::mbar_wait(&bars[B_HIDV], ph);          // pace: one tile ahead of the row warps
+                // pace: one tile ahead of the row warps.  A monotonic counter, not an mbarrier parity wait: a prefetch warp
+                // that falls two phases behind would wait for a phase that never completes.
+                while (*sProg < k + 1) __nanosleep(100);
             }
         }
     } else {
@@ -217,12 +222,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
             s1 = tc::add2(s1, s1b); s2 = tc::add2(s2, s2b);
             // combine with the other three channel quarters of the same row (warps w +- 4k, same lane).  The barrier also
             // orders this lane quarter's reads of the previous tile's accumulators before the hid columns are rewritten.
-            float* st = sStat + ((mlp * 128 + wq * 32 + lane) * 4) * 2;
-            *reinterpret_cast<float2*>(st + cq * 2) = make_float2(s1.x + s1.y, s2.x + s2.y);
+            // quarter-major layout [mlp][quarter][row]: consecutive lanes touch consecutive 8-byte words (no bank conflicts)
+            float* st = sStat + ((size_t)(mlp * 4) * 128 + wq * 32 + lane) * 2;
+            *reinterpret_cast<float2*>(st + cq * 256) = make_float2(s1.x + s1.y, s2.x + s2.y);
             asm volatile("bar.sync %0, 128;" ::"r"(3 + wq) : "memory");
-            const float4 sa4 = ld4(st), sb4 = ld4(st + 4);
-            const float mu = ((sa4.x + sa4.z) + (sb4.x + sb4.z)) * (1.0f / 128.0f);
-            const float rstd = rsqrtf(fmaxf(fmaf(-mu, mu, ((sa4.y + sa4.w) + (sb4.y + sb4.w)) * (1.0f / 128.0f)), 0.f) + 1e-5f);
+            const float2 q0 = *reinterpret_cast<const float2*>(st), q1 = *reinterpret_cast<const float2*>(st + 256);
+            const float2 q2 = *reinterpret_cast<const float2*>(st + 512), q3 = *reinterpret_cast<const float2*>(st + 768);
+            const float mu = ((q0.x + q1.x) + (q2.x + q3.x)) * (1.0f / 128.0f);
+            const float rstd = rsqrtf(fmaxf(fmaf(-mu, mu, ((q0.y + q1.y) + (q2.y + q3.y)) * (1.0f / 128.0f)), 0.f) + 1e-5f);
             const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mu * rstd, -mu * rstd);
             const float* gam = sLn + mlp * 256 + cq * 32;
             const float* bet = gam + 128;
@@ -280,6 +287,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
             }
         };
         uint32_t ph = 0;
+        int tiles_done = 0;
         bool any = false;
         SegInfo sg = seg_info(d, blockIdx.x, wq);
         request_edge_rows(0, sg);
@@ -294,6 +302,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
             if (any) epilogue(ph ^ 1);
             // ---- value MLP
             layer_norm(1, sg, tmem + C_HIDV, more, 0, nsg);
+            if (warp == 0 && lane == 0) *sProg = ++tiles_done;
             // ---- logits of this thread's 4 heads, segment softmax across the 32 lanes (rows) of the warp
             {
                 // the key bias b2k shifts all logits of a (segment, head) by the same q . b: softmax-invariant, dropped

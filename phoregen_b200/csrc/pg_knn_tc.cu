@@ -274,7 +274,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
 
         int tcount = 0;
         // ---- post-processing of a finished tile (its out columns: buffer `ob`)
-        auto post = [&](uint32_t parity, uint32_t ob) {
+        // `wait`: only the drain call waits for OUT itself.  Inside the loop the LayerNorm of the current tile has already
+        // waited for OUT(t-1); waiting again here, after this thread's HID(t) arrival, could see OUT(t) completed as well and
+        // then block on the parity of a phase that needs this very thread (two-phase aliasing of the parity wait).
+        auto post = [&](uint32_t parity, uint32_t ob, bool wait) {
             const uint32_t out = tmem + C_OUT + ob * 128 + lane_base;
             if (PASS == 0) {
                 // logits of this thread's 4 heads (key bias dropped: softmax-invariant), softmax over the lanes, times e_w
@@ -284,7 +287,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
                 for (int i = 0; i < 8; i++) qv[i] = ld4(qrow + i * 4);
                 const float ew = pf.x;
                 KTRACE(0, 8);
-                tc::mbar_wait(&bars[B_OUT], parity);
+                if (wait) tc::mbar_wait(&bars[B_OUT], parity);
                 tc::tc_fence_after();
                 KTRACE(0, 9);
                 uint32_t vv[32];
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
                 if (psg.valid && lane == 0) st4(a.alpha_sum + (size_t)psg.v * 16 + cq * 4, make_float4(sw[0], sw[1], sw[2], sw[3]));
             } else {
                 const float4 a4 = pf;
-                tc::mbar_wait(&bars[B_OUT], parity);
+                if (wait) tc::mbar_wait(&bars[B_OUT], parity);
                 tc::tc_fence_after();
                 if (POS == 0) {
                     const float swc = pfs;
@@ -454,13 +457,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
                 s2 = tc::fma2(x2[i], x2[i], s2); s2b = tc::fma2(x2[i + 1], x2[i + 1], s2b);
             }
             s1 = tc::add2(s1, s1b); s2 = tc::add2(s2, s2b);
-            float* st = sStat + ((wq * 32 + lane) * 4) * 2;
-            *reinterpret_cast<float2*>(st + cq * 2) = make_float2(s1.x + s1.y, s2.x + s2.y);
+            // quarter-major layout [quarter][row]: consecutive lanes touch consecutive 8-byte words (no bank conflicts)
+            float* st = sStat + (wq * 32 + lane) * 2;
+            *reinterpret_cast<float2*>(st + cq * 256) = make_float2(s1.x + s1.y, s2.x + s2.y);
             asm volatile("bar.sync %0, 128;" ::"r"(3 + wq) : "memory");
             KTRACE(0, 4);
-            const float4 sa4 = ld4(st), sb4 = ld4(st + 4);
-            const float mu = ((sa4.x + sa4.z) + (sb4.x + sb4.z)) * (1.0f / 128.0f);
-            const float rstd = rsqrtf(fmaxf(fmaf(-mu, mu, ((sa4.y + sa4.w) + (sb4.y + sb4.w)) * (1.0f / 128.0f)), 0.f) + 1e-5f);
+            const float2 q0 = *reinterpret_cast<const float2*>(st), q1 = *reinterpret_cast<const float2*>(st + 256);
+            const float2 q2 = *reinterpret_cast<const float2*>(st + 512), q3 = *reinterpret_cast<const float2*>(st + 768);
+            const float mu = ((q0.x + q1.x) + (q2.x + q3.x)) * (1.0f / 128.0f);
+            const float rstd = rsqrtf(fmaxf(fmaf(-mu, mu, ((q0.y + q1.y) + (q2.y + q3.y)) * (1.0f / 128.0f)), 0.f) + 1e-5f);
             const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mu * rstd, -mu * rstd);
             const float* gam = sLn + cq * 32;
             const float* bet = gam + 128;
@@ -483,7 +488,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
             tc::mbar_arrive(&bars[B_HID]);
             KTRACE(0, 5);
             // ---- post-processing of the previous tile while the tensor pipe works on this one
-            if (any) { asm volatile("cp.async.wait_group 1;" ::: "memory"); __syncwarp(); post(ph ^ 1, ph ^ 1); }
+            if (any) { asm volatile("cp.async.wait_group 1;" ::: "memory"); __syncwarp(); post(ph ^ 1, ph ^ 1, false); }
             KTRACE(0, 6);
             psg = sg; prow = rowvalid; pf = nf; pfs = nfs;
             if (PASS == 1 && POS) {
@@ -497,7 +502,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
 #pragma unroll
             for (int i = 0; i < 8; i++) idx[i] = nidx[i];
         }
-        if (any) { asm volatile("cp.async.wait_group 0;" ::: "memory"); __syncwarp(); post(ph ^ 1, ph ^ 1); }
+        if (any) { asm volatile("cp.async.wait_group 0;" ::: "memory"); __syncwarp(); post(ph ^ 1, ph ^ 1, true); }
     }
     tc::tc_fence_before();
     __syncthreads();

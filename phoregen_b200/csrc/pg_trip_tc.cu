@@ -48,7 +48,10 @@ constexpr int NTHREADS = (ROW_WARPS + 4) * 32;
 constexpr int ROW_THREADS = ROW_WARPS * 32;
 
 // mbarrier slots
-enum { B_FEAT0 = 0, B_FEAT1, B_PREK, B_PREV, B_HIDK, B_HIDV, B_OUTK, B_OUTV, B_PSK, B_PSV, B_COUNT };
+// A parity wait is only safe while the barrier cannot complete a second time before the waiter looks at it.  B_PREV has
+// two kinds of waiters (row warps and the feature warps, which run ahead on their own clock), so it alternates between
+// two barriers by tile parity, like B_FEAT.
+enum { B_FEAT0 = 0, B_FEAT1, B_PREK, B_PREV0, B_PREV1, B_HIDK, B_HIDV, B_OUTK, B_OUTV, B_PSK, B_PSV, B_COUNT };
 
 // the sequence of (unit, tile) a CTA walks; every role steps through it redundantly
 struct TileIter {
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
     uint8_t* sWa = sW + SM_W;
     uint8_t* sFeat = sWa + SM_WA;
     float* sQR = (float*)(sFeat + SM_FEAT);         // [2][ q: 4x128 | R: 4x256 ]
-    float* sStat = sQR + SM_QR / 4;                 // [2 mlp][128 rows][4 quarters][2]  partial LayerNorm sums
+    float* sStat = sQR + SM_QR / 4;                 // [2 mlp][4 quarters][128 rows][2]  partial LayerNorm sums (quarter-major: conflict-free)
     float* sLn = sStat + SM_ALPHA / 4;              // gk, bk, gv, bv
     float* sB2 = sLn + 4 * 128;                     // b2k, b2v
     uint64_t* bars = (uint64_t*)(sB2 + 2 * 128);
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
     if (warp == MMA_WARP) tc::tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
         tc::mbar_init(&bars[B_FEAT0], 96 + 32); tc::mbar_init(&bars[B_FEAT1], 96 + 32);
-        tc::mbar_init(&bars[B_PREK], 1); tc::mbar_init(&bars[B_PREV], 1);
+        tc::mbar_init(&bars[B_PREK], 1); tc::mbar_init(&bars[B_PREV0], 1); tc::mbar_init(&bars[B_PREV1], 1);
         tc::mbar_init(&bars[B_HIDK], ROW_THREADS); tc::mbar_init(&bars[B_HIDV], ROW_THREADS);
         tc::mbar_init(&bars[B_OUTK], 1); tc::mbar_init(&bars[B_OUTV], 1);
         tc::mbar_init(&bars[B_PSK], 1); tc::mbar_init(&bars[B_PSV], 1);
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
         tc::mbar_wait(&bars[B_FEAT0], 0);
         tc::tc_fence_after();
         feat_mma(0, 0, tmem + 0, &bars[B_PREK]);
-        feat_mma(0, 1, tmem + 128, &bars[B_PREV]);
+        feat_mma(0, 1, tmem + 128, &bars[B_PREV0]);
         int tcount = 0;
         while (it.valid) {
             const uint32_t ph = tcount & 1;
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
                 tc::mbar_wait(&bars[B_OUTV], ph);
                 tc::tc_fence_after();
                 TRACE(2, 7);
-                feat_mma(tcount + 1, 1, hidV, &bars[B_PREV]);
+                feat_mma(tcount + 1, 1, hidV, &bars[(tcount + 1) & 1 ? B_PREV1 : B_PREV0]);
             }
             TRACE(2, 8);
             it = nx; tcount++;
@@ -323,7 +326,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             TileIter nx = it;
             iter_next(d, nx);
             // operand buffer (s+1)&1 was last read by the value-side angle MMA of tile s-1
-            if (s >= 1) tc::mbar_wait(&bars[B_PREV], (s - 1) & 1);
+            if (s >= 1) tc::mbar_wait(&bars[(s - 1) & 1 ? B_PREV1 : B_PREV0], ((s - 1) >> 1) & 1);
             if (nx.valid) {
                 if (nx.u != it.u) { xb ^= 1; stage_x(nx, xb); }
                 features(nx, xb, s + 1);
@@ -371,12 +374,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             s1 = tc::add2(s1, s1b); s2 = tc::add2(s2, s2b);
             // combine with the other three channel quarters of the same row (warps w +- 4k, same lane).  The barrier also
             // orders this lane quarter's reads of the previous tile's accumulators before the hid columns overwrite them.
-            float* st = sStat + ((mlp * 128 + wq * 32 + lane) * 4) * 2;
-            *reinterpret_cast<float2*>(st + cq * 2) = make_float2(s1.x + s1.y, s2.x + s2.y);
+            // quarter-major layout [mlp][quarter][row]: consecutive lanes touch consecutive 8-byte words (no bank conflicts)
+            float* st = sStat + ((size_t)(mlp * 4) * 128 + wq * 32 + lane) * 2;
+            *reinterpret_cast<float2*>(st + cq * 256) = make_float2(s1.x + s1.y, s2.x + s2.y);
             asm volatile("bar.sync %0, 128;" ::"r"(3 + wq) : "memory");
-            const float4 sa4 = ld4(st), sb4 = ld4(st + 4);
-            const float mu = ((sa4.x + sa4.z) + (sb4.x + sb4.z)) * (1.0f / 128.0f);
-            const float rstd = rsqrtf(fmaxf(fmaf(-mu, mu, ((sa4.y + sa4.w) + (sb4.y + sb4.w)) * (1.0f / 128.0f)), 0.f) + 1e-5f);
+            const float2 q0 = *reinterpret_cast<const float2*>(st), q1 = *reinterpret_cast<const float2*>(st + 256);
+            const float2 q2 = *reinterpret_cast<const float2*>(st + 512), q3 = *reinterpret_cast<const float2*>(st + 768);
+            const float mu = ((q0.x + q1.x) + (q2.x + q3.x)) * (1.0f / 128.0f);
+            const float rstd = rsqrtf(fmaxf(fmaf(-mu, mu, ((q0.y + q1.y) + (q2.y + q3.y)) * (1.0f / 128.0f)), 0.f) + 1e-5f);
             const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mu * rstd, -mu * rstd);
             const float* gam = sLn + mlp * 256 + cq * 32;
             const float* bet = gam + 128;
@@ -436,7 +441,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             TRACE(role, 4);
             // ---- value MLP
             if (staged_v != it.u) { tc::mbar_wait(&bars[B_PSV], psv); psv ^= 1; staged_v = it.u; }
-            tc::mbar_wait(&bars[B_PREV], ph);
+            tc::mbar_wait(&bars[ph ? B_PREV1 : B_PREV0], (tcount >> 1) & 1);
             tc::tc_fence_after();
             TRACE(role, 5);
             layer_norm(1, preV, hidV, trow, sR);
