@@ -453,3 +453,26 @@ def test_tensor_core_kernels_match_fp32_kernels(tmp_path):
     for k, what in enumerate(("pred_node", "pred_pos", "pred_edge")):
         assert_close(outs["tc"][k], outs["fp32"][k], f"tcgen05 vs fp32 kernels: {what}")
         assert_close(outs["fp32"][k], f[what], f"fp32 kernels vs reference golden: {what}")
+
+
+# ---------------------------------------------------------------- liveness of the persistent, mbarrier-pipelined kernels
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("seed", [1, 7])
+def test_many_tiles_per_cta_eager_steps_terminate_and_match_graph_replay(model, dev, seed):
+    """The tcgen05 kernels are persistent: at this size every CTA walks several tiles, which exercises the cross-tile
+    hand-offs (a wrong mbarrier parity wait shows up as a hang, not as a wrong number).  Eager and CUDA-graph replays of
+    the same trajectory must agree bit for bit."""
+    from phoregen_b200.diffusion import TrajectorySampler
+    m, _ = model
+    G = 320
+    b = O.synthetic_batch(2032 + seed, G, n_atoms=(26, 33))
+    outs = []
+    for graph in (False, True):
+        s = TrajectorySampler(m, None, G, dev, ligand_num_atoms=b["num_atoms"], save_traj=False, seed=seed, use_cuda_graph=graph,
+                              phore_batch=b["phore"])
+        s.run(5)
+        torch.cuda.synchronize()
+        outs.append((s.pos.clone(), s.node_cls.clone(), s.edge_cls.clone()))
+    assert torch.isfinite(outs[0][0]).all()
+    for a, c in zip(outs[0], outs[1]):
+        assert torch.equal(a, c)
