@@ -7,7 +7,8 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_uint64, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libphoregen_b200.so")
+# PHOREGEN_B200_LIB: load another build of the same library (A/B comparisons of kernel variants on one box)
+LIB_PATH = os.environ.get("PHOREGEN_B200_LIB") or os.path.join(_HERE, "libphoregen_b200.so")
 
 
 class PhoreGenLibraryError(RuntimeError):

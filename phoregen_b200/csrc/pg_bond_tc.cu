@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
 #pragma unroll
                 for (int mlp = 0; mlp < 2; mlp++) {
-                    tc::mbar_wait(&bars[mlp == 0 ? B_HIDK : B_HIDV], ph);
+                    tc::mbar_wait_wd(&bars[mlp == 0 ? B_HIDK : B_HIDV], ph);
                     tc::tc_fence_after();
                     if (lane == 0) {
                         const uint32_t hid = tmem + (mlp == 0 ? C_HIDK : C_HIDV);

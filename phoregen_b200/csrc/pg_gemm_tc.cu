@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(GemmArgs a) {
         for (long long mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
             for (int nt = 0; nt < a.ntiles; nt++, cnt++) {
                 const int s = cnt % NB;
-                tc::mbar_wait(&bars[B_EMPTY + s], ((cnt / NB) & 1) ^ 1);
+                tc::mbar_wait_wd(&bars[B_EMPTY + s], ((cnt / NB) & 1) ^ 1);
                 if (lane == 0) {
                     tc::mbar_arrive_expect_tx(&bars[B_FULL + s], B_BUF);
                     tc::bulk_copy_g2s(sB + s * B_BUF, reinterpret_cast<const uint8_t*>(a.Wbf) + (size_t)nt * B_BUF, B_BUF, &bars[B_FULL + s]);
@@ -204,11 +204,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(GemmArgs a) {
         long long cnt = 0, it = 0;
         for (long long mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x, it++) {
             const int buf = it & 1;
-            tc::mbar_wait(&bars[A_FULL + buf], (it >> 1) & 1);
+            tc::mbar_wait_wd(&bars[A_FULL + buf], (it >> 1) & 1);
             for (int nt = 0; nt < a.ntiles; nt++, cnt++) {
                 const int s = cnt % NB, ab = cnt & 1;
-                tc::mbar_wait(&bars[B_FULL + s], (cnt / NB) & 1);
-                tc::mbar_wait(&bars[ACC_EMPTY + ab], ((cnt >> 1) & 1) ^ 1);
+                tc::mbar_wait_wd(&bars[B_FULL + s], (cnt / NB) & 1);
+                tc::mbar_wait_wd(&bars[ACC_EMPTY + ab], ((cnt >> 1) & 1) ^ 1);
                 tc::tc_fence_after();
                 if (lane == 0) {
                     uint32_t acc = 0;

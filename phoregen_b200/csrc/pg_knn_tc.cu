@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
         int s_nxt = row_src(blockIdx.x + gridDim.x);
         features(blockIdx.x, s_cur);
         if (warp == MMA_WARP) {
-            tc::mbar_wait(&bars[B_FEAT], 0);
+            tc::mbar_wait_wd(&bars[B_FEAT], 0);
             tc::tc_fence_after();
             table_mma();
         }
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
             const bool more = nt < ntiles;
             KTRACE(1, 0);
             // features of the next tile as soon as the table MMA of this one has consumed the operand
-            tc::mbar_wait(&bars[B_PRE], ph);
+            tc::mbar_wait_wd(&bars[B_PRE], ph);
             KTRACE(1, 1);
             if (more) {
                 s_cur = s_nxt;
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
             }
             KTRACE(1, 2);
             if (warp == MMA_WARP) {
-                tc::mbar_wait(&bars[B_HID], ph);
+                tc::mbar_wait_wd(&bars[B_HID], ph);
                 KTRACE(1, 3);
                 tc::tc_fence_after();
                 if (lane == 0) {
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
                 __syncwarp();
                 KTRACE(1, 4);
                 if (more) {
-                    tc::mbar_wait(&bars[B_FEAT], ph ^ 1);   // features of the next tile (pre columns are free: HID(t) has fired)
+                    tc::mbar_wait_wd(&bars[B_FEAT], ph ^ 1);   // features of the next tile (pre columns are free: HID(t) has fired)
                     tc::tc_fence_after();
                     KTRACE(1, 5);
                     table_mma();

@@ -13,6 +13,7 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// Plain parity wait (row / producer / epilogue warps: the register-tight hot loops).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
@@ -24,6 +25,42 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
+}
+// Parity wait with a watchdog, used by the auxiliary warps (MMA issuer, loaders, feature warps).  In every hand-off cycle
+// of these kernels one of them is among the waiters, so a protocol error ("mbarrier parity waits")
+// surfaces as a launch failure of this kernel instead of a GPU that never comes back.  The wall clock is read every 4096
+// failed polls; 10 s are orders of magnitude above any legitimate wait here (tens of microseconds).
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
+#ifdef PG_NO_WATCHDOG
+    mbar_wait(bar, parity);
+#else
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .u32 polls, m;\n\t"
+        ".reg .u64 t0, t1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "mov.u32 polls, 0;\n\t"
+        "mov.u64 t0, 0;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "add.u32 polls, polls, 1;\n\t"
+        "and.b32 m, polls, 0xfff;\n\t"
+        "setp.ne.u32 q, m, 0;\n\t"
+        "@q bra WAIT_LOOP;\n\t"
+        "mov.u64 t1, %%globaltimer;\n\t"
+        "setp.eq.u64 q, t0, 0;\n\t"
+        "@q mov.u64 t0, t1;\n\t"
+        "sub.u64 t1, t1, t0;\n\t"
+        "setp.lt.u64 q, t1, 10000000000;\n\t"
+        "@q bra WAIT_LOOP;\n\t"
+        "trap;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
         load_qr(it, 0);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         tc::mbar_arrive(&bars[B_FEAT0]);
-        tc::mbar_wait(&bars[B_FEAT0], 0);
+        tc::mbar_wait_wd(&bars[B_FEAT0], 0);
         tc::tc_fence_after();
         feat_mma(0, 0, tmem + 0, &bars[B_PREK]);
         feat_mma(0, 1, tmem + 128, &bars[B_PREV0]);
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             const bool newu = nx.valid && nx.u != it.u;
             uint64_t* featbar = &bars[(tcount + 1) & 1 ? B_FEAT1 : B_FEAT0];
             TRACE(2, 0);
-            tc::mbar_wait(&bars[B_HIDK], ph);          // key activations of tile t are in TMEM; logits of tile t-1 are done
+            tc::mbar_wait_wd(&bars[B_HIDK], ph);          // key activations of tile t are in TMEM; logits of tile t-1 are done
             TRACE(2, 1);
             tc::tc_fence_after();
             if (nx.valid) load_qr(nx, (tcount + 1) & 1);
@@ -281,21 +281,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             if (nx.valid) {
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
                 tc::mbar_arrive(featbar);
-                tc::mbar_wait(&bars[B_OUTK], ph);      // hid_k(t) has been consumed: its columns take pre_k(t+1)
-                tc::mbar_wait(featbar, ((tcount + 1) >> 1) & 1);
+                tc::mbar_wait_wd(&bars[B_OUTK], ph);      // hid_k(t) has been consumed: its columns take pre_k(t+1)
+                tc::mbar_wait_wd(featbar, ((tcount + 1) >> 1) & 1);
                 tc::tc_fence_after();
                 TRACE(2, 3);
                 feat_mma(tcount + 1, 0, hidK, &bars[B_PREK]);
             }
             TRACE(2, 4);
-            tc::mbar_wait(&bars[B_HIDV], ph);
+            tc::mbar_wait_wd(&bars[B_HIDV], ph);
             TRACE(2, 5);
             tc::tc_fence_after();
             if (newu) load_ps(nx, 1);
             w2_mma(1, hidV, preV, &bars[B_OUTV]);
             TRACE(2, 6);
             if (nx.valid) {
-                tc::mbar_wait(&bars[B_OUTV], ph);
+                tc::mbar_wait_wd(&bars[B_OUTV], ph);
                 tc::tc_fence_after();
                 TRACE(2, 7);
                 feat_mma(tcount + 1, 1, hidV, &bars[(tcount + 1) & 1 ? B_PREV1 : B_PREV0]);
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             TileIter nx = it;
             iter_next(d, nx);
             // operand buffer (s+1)&1 was last read by the value-side angle MMA of tile s-1
-            if (s >= 1) tc::mbar_wait(&bars[(s - 1) & 1 ? B_PREV1 : B_PREV0], ((s - 1) >> 1) & 1);
+            if (s >= 1) tc::mbar_wait_wd(&bars[(s - 1) & 1 ? B_PREV1 : B_PREV0], ((s - 1) >> 1) & 1);
             if (nx.valid) {
                 if (nx.u != it.u) { xb ^= 1; stage_x(nx, xb); }
                 features(nx, xb, s + 1);
