@@ -5,6 +5,8 @@
 struct AttnW {
     const float *tab_k, *tab_v;                   // kNN: [4][24][128]; phore encoder: [128] distance column
     const float *lnk_g, *lnk_b, *lnv_g, *lnv_b;   // LayerNorm of the key / value MLPs
+    const float *lnk_bf, *lnv_bf, *fold;          // tensor-core kernels: beta, or beta / gamma where gamma > 0 was folded into
+                                                  //   the bf16 W2 images; fold = [fold_k, fold_v, -, -] (1.0 = folded)
     const float *w2k, *b2k;                       // key MLP second Linear   [128 out][128 in], [128]
     const float *w2v, *b2v;                       // value MLP second Linear [128|16 out][128 in], [128|16]
 };
@@ -97,6 +99,7 @@ struct TripTcArgs {
     const uint16_t* wa_bf;                 // [hi|lo][256][16] bf16 (angle slice, 13 used)
     int flags;                             // experiment switches (PG_TRIP_FLAGS): bit 0 = shuffle-butterfly softmax instead of REDUX
     const float *lnk_g, *lnk_b, *lnv_g, *lnv_b, *b2k, *b2v;
+    const float *lnk_bf, *lnv_bf, *fold;   // beta (/ gamma where folded into the W2 images), fold flags (see AttnW)
     float* hb;
     int maxn;
 };

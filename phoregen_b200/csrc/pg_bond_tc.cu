@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
     }
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     if (tid < 128) {
-        sLn[tid] = a.w.lnk_g[tid]; sLn[128 + tid] = a.w.lnk_b[tid]; sLn[256 + tid] = a.w.lnv_g[tid]; sLn[384 + tid] = a.w.lnv_b[tid];
+        sLn[tid] = a.w.lnk_g[tid]; sLn[128 + tid] = a.w.lnk_bf[tid]; sLn[256 + tid] = a.w.lnv_g[tid]; sLn[384 + tid] = a.w.lnv_bf[tid];
         if (tid < NV) sB2[tid] = a.w.b2v[tid];
     }
     tc::fence_proxy_async_smem();
@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // ================= row warps: thread = (row, channel quarter) =================
         const int cq = warp >> 2;
+        const bool fold[2] = {a.w.fold[0] > 0.5f, a.w.fold[1] > 0.5f};
         float al[4] = {0.f, 0.f, 0.f, 0.f};
         bool prev_valid = false;
         int prev_v = 0;
@@ -234,13 +235,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
             const float* gam = sLn + mlp * 256 + cq * 32;
             const float* bet = gam + 128;
             uint32_t hi[16], lo[16];
+            if (fold[mlp]) {
+                // gamma > 0 everywhere: it lives in the columns of W2, only beta / gamma is added here (half the broadcast loads)
 #pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-                const float4 g4 = ld4(gam + 2 * i), b4 = ld4(bet + 2 * i);
-                float2 y0 = tc::fma2(tc::fma2(x2[i], rs2, nm2), make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
-                float2 y1 = tc::fma2(tc::fma2(x2[i + 1], rs2, nm2), make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
-                tc::split_pair_relu(y0, hi[i], lo[i]);
-                tc::split_pair_relu(y1, hi[i + 1], lo[i + 1]);
+                for (int i = 0; i < 16; i += 2) {
+                    const float4 b4 = ld4(bet + 2 * i);
+                    tc::split_pair_relu(tc::add2(tc::fma2(x2[i], rs2, nm2), make_float2(b4.x, b4.y)), hi[i], lo[i]);
+                    tc::split_pair_relu(tc::add2(tc::fma2(x2[i + 1], rs2, nm2), make_float2(b4.z, b4.w)), hi[i + 1], lo[i + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    const float4 g4 = ld4(gam + 2 * i), b4 = ld4(bet + 2 * i);
+                    float2 y0 = tc::fma2(tc::fma2(x2[i], rs2, nm2), make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
+                    float2 y1 = tc::fma2(tc::fma2(x2[i + 1], rs2, nm2), make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
+                    tc::split_pair_relu(y0, hi[i], lo[i]);
+                    tc::split_pair_relu(y1, hi[i + 1], lo[i + 1]);
+                }
             }
             tc::tmem_st16(hid + lane_base + cq * 16, hi);
             tc::tmem_st16(hid + lane_base + 64 + cq * 16, lo);

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
         asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
         for (int i = tid; i < SM_FEAT / 16; i += NTHREADS) reinterpret_cast<uint4*>(sFeat)[i] = make_uint4(0, 0, 0, 0);
         if (tid < 128) {
-            sLn[tid] = (PASS == 0 ? a.w.lnk_g : a.w.lnv_g)[tid]; sLn[128 + tid] = (PASS == 0 ? a.w.lnk_b : a.w.lnv_b)[tid];
+            sLn[tid] = (PASS == 0 ? a.w.lnk_g : a.w.lnv_g)[tid]; sLn[128 + tid] = (PASS == 0 ? a.w.lnk_bf : a.w.lnv_bf)[tid];
             if (PASS == 1 && tid < NOUT) sB2[tid] = a.w.b2v[tid];
         }
     }
@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // ================= row warps: thread = (row, channel quarter) =================
         const int cq = warp >> 2;
+        const bool fold = a.w.fold[PASS] > 0.5f;
         const int sr = lane >> 3, ch = (lane & 7) * 4;
         float* xp = sXp + warp * (16 * XP_LD);
         float al[4] = {0.f, 0.f, 0.f, 0.f};
@@ -367,6 +368,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
                         const float* r4 = sRed + wq * 16 + lane;
                         a.out[(size_t)psg.v * 3 + lane] = psg.valid ? ((r4[0] + r4[4]) + (r4[8] + r4[12])) * (1.0f / 16.0f) : 0.f;
                     }
+                    // the next writer of sRed may be the drain call right after the loop, with no LayerNorm barrier in between
+                    asm volatile("bar.sync %0, 128;" ::"r"(3 + wq) : "memory");
                 }
             }
         };
@@ -470,13 +473,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
             const float* gam = sLn + cq * 32;
             const float* bet = gam + 128;
             uint32_t hi[16], lo[16];
+            if (fold) {
+                // gamma > 0 everywhere: it lives in the columns of W2, only beta / gamma is added here (half the broadcast loads)
 #pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-                const float4 g4 = ld4(gam + 2 * i), b4 = ld4(bet + 2 * i);
-                float2 y0 = tc::fma2(tc::fma2(x2[i], rs2, nm2), make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
-                float2 y1 = tc::fma2(tc::fma2(x2[i + 1], rs2, nm2), make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
-                tc::split_pair_relu(y0, hi[i], lo[i]);
-                tc::split_pair_relu(y1, hi[i + 1], lo[i + 1]);
+                for (int i = 0; i < 16; i += 2) {
+                    const float4 b4 = ld4(bet + 2 * i);
+                    tc::split_pair_relu(tc::add2(tc::fma2(x2[i], rs2, nm2), make_float2(b4.x, b4.y)), hi[i], lo[i]);
+                    tc::split_pair_relu(tc::add2(tc::fma2(x2[i + 1], rs2, nm2), make_float2(b4.z, b4.w)), hi[i + 1], lo[i + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    const float4 g4 = ld4(gam + 2 * i), b4 = ld4(bet + 2 * i);
+                    float2 y0 = tc::fma2(tc::fma2(x2[i], rs2, nm2), make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
+                    float2 y1 = tc::fma2(tc::fma2(x2[i + 1], rs2, nm2), make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
+                    tc::split_pair_relu(y0, hi[i], lo[i]);
+                    tc::split_pair_relu(y1, hi[i + 1], lo[i + 1]);
+                }
             }
             // the W2 MMA of the previous tile must be done with the hid columns before they are rewritten
             if (any) tc::mbar_wait(&bars[B_OUT], ph ^ 1);

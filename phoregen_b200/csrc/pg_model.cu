@@ -47,6 +47,7 @@ std::vector<PgSlotDesc> build_slots() {
             std::string S = L + kSub[s] + ".";
             add(S + "lnq_g", 128); add(S + "lnq_b", 128); add(S + "w2q_t", 128 * 128); add(S + "w2q_t.bf", 128 * 128); add(S + "b2q", 128);
             add(S + "lnk_g", 128); add(S + "lnk_b", 128); add(S + "lnv_g", 128); add(S + "lnv_b", 128);
+            add(S + "lnk_bf", 128); add(S + "lnv_bf", 128); add(S + "fold", 4);   // tensor-core kernels: beta (/ gamma when folded into W2), flags
             add(S + "w2k", 128 * 128); add(S + "b2k", 128);
             const bool pos = s >= 3;
             add(S + "w2v", (pos ? 16 : 128) * 128); add(S + "b2v", pos ? 16 : 128);
@@ -357,6 +358,7 @@ AttnW attn_w(const W& w, const std::string& S, bool tabs) {
     AttnW a;
     a.tab_k = tabs ? w(S + "tab_k") : nullptr; a.tab_v = tabs ? w(S + "tab_v") : nullptr;
     a.lnk_g = w(S + "lnk_g"); a.lnk_b = w(S + "lnk_b"); a.lnv_g = w(S + "lnv_g"); a.lnv_b = w(S + "lnv_b");
+    a.lnk_bf = w(S + "lnk_bf"); a.lnv_bf = w(S + "lnv_bf"); a.fold = w(S + "fold");
     a.w2k = w(S + "w2k"); a.b2k = w(S + "b2k"); a.w2v = w(S + "w2v"); a.b2v = w(S + "b2v");
     return a;
 }
@@ -428,6 +430,7 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
                 t.wa_bf = (const uint16_t*)w(L + "tr.wa.bf");
                 { static int fl = -1; if (fl < 0) { const char* e = getenv("PG_TRIP_FLAGS"); fl = e ? atoi(e) : 0; } t.flags = fl; }
                 t.lnk_g = a.w.lnk_g; t.lnk_b = a.w.lnk_b; t.lnv_g = a.w.lnv_g; t.lnv_b = a.w.lnv_b; t.b2k = a.w.b2k; t.b2v = a.w.b2v;
+                t.lnk_bf = a.w.lnk_bf; t.lnv_bf = a.w.lnv_bf; t.fold = a.w.fold;
                 t.hb = p->hb; t.maxn = std::min(d.max_n, PG_TRIP_TC_MAX_ATOMS);
                 { PgTimed timed(p, KC_OTHER, s); PG_TRY(pg_launch_trip_pr(t, s)); }
                 { PgTimed timed(p, KC_TRIP, s); PG_TRY(pg_launch_trip_tc(t, num_sms(), s)); } p->launches += 2;

@@ -162,10 +162,21 @@ def build_blob(sd):
     packed = pack_state_dict(sd)
     for name in [k for k in packed if k.endswith((".wt", "w2q_t", "wcat_t", "w1t")) and k != "G.ew.w1t"]:
         packed[name + ".bf"] = bf16_tiles64(packed[name])
-    for name in [k for k in packed if k.endswith(".tr.w2k") or k.endswith(".tr.w2v")]:
-        packed[name + ".bf"] = bf16_split(np.asarray(packed[name]).T)          # already [out][in] = [N][K]
-    for name in [k for k in packed if k.endswith((".nb.w2k", ".nb.w2v", ".pb.w2k", ".pb.w2v", ".nk.w2k", ".nk.w2v", ".pk.w2k", ".pk.w2v"))]:
-        packed[name + ".bf"] = bf16_split(np.asarray(packed[name]).T)          # [out][in]; pos value head: 16 outputs
+    # Tensor-core attention kernels: second Linear as bf16 hi/lo images.  Where every LayerNorm gain of the MLP is positive,
+    # relu(g*xn + b) = g * relu(xn + b/g), so g is folded into the columns of W2 (fp64) and the kernel only needs b/g
+    # ("<S>.ln{k,v}_bf" holds b/g, or plain b when not folded; "<S>.fold" = [fold_k, fold_v, 0, 0]).  The fp32 twins keep
+    # using the unfolded "<S>.w2k" / "<S>.lnk_b".
+    for S in sorted({k[:-len("lnk_g")] for k in packed if k.endswith((".tr.lnk_g", ".nb.lnk_g", ".pb.lnk_g", ".nk.lnk_g", ".pk.lnk_g"))}):
+        flags = np.zeros(4)
+        for i, kv in enumerate("kv"):
+            g = np.asarray(packed[S + f"ln{kv}_g"], dtype=np.float64)
+            b = np.asarray(packed[S + f"ln{kv}_b"], dtype=np.float64)
+            w2 = np.asarray(packed[S + f"w2{kv}"], dtype=np.float64)              # [out][in]
+            fold = bool(np.all(g > 1e-3))
+            flags[i] = 1.0 if fold else 0.0
+            packed[S + f"ln{kv}_bf"] = b / g if fold else b
+            packed[S + f"w2{kv}.bf"] = bf16_split((w2 * g[None, :] if fold else w2).T)   # [out][in]; pos value head: 16 outputs
+        packed[S + "fold"] = flags
     for name in [k for k in packed if k.endswith((".nk.tab_k", ".nk.tab_v", ".pk.tab_k", ".pk.tab_v"))]:
         packed[name + ".bf"] = bf16_split(np.asarray(packed[name]).reshape(96, 128))   # [type*24 + feat][128] -> [hi|lo][128][96]
     for name in [k for k in packed if k.endswith(".tr.wa")]:

@@ -476,3 +476,39 @@ def test_many_tiles_per_cta_eager_steps_terminate_and_match_graph_replay(model, 
     assert torch.isfinite(outs[0][0]).all()
     for a, c in zip(outs[0], outs[1]):
         assert torch.equal(a, c)
+
+
+def test_layernorm_gains_of_either_sign(dev):
+    """The tensor-core kernels fold positive LayerNorm gains into the second Linear (weights.py); a checkpoint with negative
+    or zero gains must take the unfolded path and still match the oracle."""
+    from phoregen_b200.diffusion import PhoreDiff
+    from phoregen_b200.testing import MODEL_CONFIG, random_state_dict
+    m = PhoreDiff(MODEL_CONFIG, "zinc_300")
+    sd = random_state_dict(m, 3)
+    rng = np.random.default_rng(5)
+    flipped = 0
+    for k in sorted(sd):
+        if k.endswith(".net.1.weight") and (".hk_func." in k or ".hv_func." in k) and rng.random() < 0.6:
+            g = sd[k].clone()
+            idx = torch.from_numpy(rng.choice(g.numel(), size=9, replace=False))
+            g[idx[:8]] = -g[idx[:8]]
+            g[idx[8]] = 0.0
+            sd[k] = g
+            flipped += 1
+    assert flipped > 10
+    m.load_state_dict(sd, strict=True)
+    m = m.eval().to(dev)
+    seed = 211
+    while True:
+        b = O.synthetic_batch(seed, 3, n_atoms=(9, 14))
+        ph = b["phore"]
+        times = [700, 321, 12]
+        stages = []
+        want = O.phorediff_forward({k: v.cpu() for k, v in sd.items()}, b["h_node"], b["pos"], b["batch_node"], b["h_edge"], b["edge_index"],
+                                   b["batch_edge"], torch.tensor(times), ph["x"], ph["pos"], ph["norm"], ph["batch"], stages=stages)
+        if O.forward_knn_margin(stages) >= 5e-4:
+            break
+        seed += 1000
+    got = _forward(m, b, times, dev)
+    for g, w, what in zip(got[:3], want[:3], ("logits_node", "pos", "logits_edge")):
+        assert_close(g, w, what)
