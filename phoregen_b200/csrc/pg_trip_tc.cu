@@ -1,22 +1,30 @@
 // BondUpdateLayer (uni_denoiser.py:123-165) on the 5th-gen tensor cores.
 //
-// One persistent CTA per SM walks the ligand atoms j ("units").  For a unit the per-edge partials
-// P[k->j] (n-1 rows x 256 channels, k|v) are staged once in shared memory; the n-1 segments (j->i) are processed
-// four at a time as a 128-row tile: TMEM lane = thread = triplet row (32 lanes per segment, rows k ascending).
+// One persistent CTA per SM (640 threads) walks the ligand atoms j ("units").  For a unit the per-edge partials
+// P[k->j] (n-1 rows x 256 channels, k|v; written by trip_pr_kernel below) are staged once in shared memory by bulk copies;
+// the n-1 segments (j->i) are processed four at a time as a 128-row tile: TMEM lane = triplet row (32 lanes per segment,
+// rows k ascending).
 //
-//   1. angular encoding (13 values per triplet) -> bf16 hi/lo A tile in smem; one tcgen05.mma (M128 N256 K16, x3 for
-//      bf16x3) against the angle slice of the first Linear gives the triplet-specific part of both pre-activations
-//      in TMEM columns [0,256).
-//   2. every thread reads its row (tcgen05.ld), adds P[k->j] (smem) and R[j->i] (the r_ji slice, per segment),
-//      applies LayerNorm + ReLU in registers (no shuffles: the row is thread-local), splits to bf16 hi/lo and writes
-//      the result back to TMEM (tcgen05.st) as the A operand of the second Linear.
+// Roles: 16 row warps, thread = (row, 32-channel quarter), warp w -> lane quarter w & 3, channel quarter w >> 2 (four row
+//        warps per scheduler); warp 16 issues every MMA and the cp.async / bulk copies; warps 17-19 compute the angular
+//        features of the tiles ahead.  setmaxnreg moves registers from the auxiliary warpgroup to the row warps (104 / 64).
+//
+//   1. angular encoding (13 values per triplet) -> bf16 hi/lo A tile in smem (double buffered); per MLP three
+//      tcgen05.mma (M128 N128 K16, bf16x3) against the angle slice of the first Linear -> pre-activation columns in TMEM.
+//   2. every thread reads its 32-channel slice (tcgen05.ld), adds P[k->j] (smem) and R[j->i] (per segment), applies
+//      LayerNorm + ReLU in registers with packed fp32x2 math (the four quarter statistics of a row meet in shared memory),
+//      splits to bf16 hi/lo with the ReLU fused into the conversions and writes the A operand of the second Linear back to
+//      TMEM (tcgen05.st).  Positive LayerNorm gains are folded into W2 at pack time (weights.py), so only beta/gamma is added.
 //   3. second Linear of the key and value MLPs: A from TMEM, B = W2 (bf16 hi/lo, resident in smem, 128B swizzle),
 //      24 tcgen05.mma (M128 N128 K16) each, fp32 accumulators in TMEM.
-//   4. epilogue: logits = q . k / sqrt(8) per head (thread-local dot), segment softmax across the 32 lanes of the
-//      warp, alpha-weighted sum of v over the lanes with a butterfly transpose-reduce, residual add into h_bond.
+//   4. logits = q . k per head (thread-local dot; the key bias is softmax-invariant and dropped), segment softmax across
+//      the 32 lanes on the REDUX unit, alpha-weighted sum of v over the lanes with a butterfly transpose-reduce, residual
+//      add into h_bond.
 //
-// TMEM map (512 columns): [0,128) pre_k -> reused for hid_v ; [128,256) pre_v -> reused for out_v ;
-//                         [256,384) out_k ; [384,512) hid_k.       (hid = 64 columns hi + 64 columns lo)
+// Software pipeline across tiles: the row warps run  LN-k(t) | epilogue(t-1) | LN-v(t) | logits(t)  while the tensor pipe
+// runs  W2k(t), angle-k(t+1) | W2v(t), angle-v(t+1).  The four 128-column TMEM blocks alternate roles per tile (pre/out of
+// one MLP in one block, hid in the other), so two tiles share the 512 columns.  All hand-offs are mbarriers; the ordering
+// argument behind every parity wait is in DESIGN.md ("mbarrier parity waits").
 // Precision: bf16x3 (hi*hi + hi*lo + lo*hi, fp32 accumulate) on every contraction, fp32 everywhere else.
 #include <algorithm>
 #include "pg_attn.h"

@@ -48,6 +48,47 @@ def test_weight_packer_fills_every_slot():
         np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
 
 
+def _bf16_image_to_f64(carrier, n_out, k=128):
+    """[hi|lo][n_out][k] bf16 carried in fp32 words (weights.bf16_split) -> hi + lo as float64 [n_out][k]."""
+    bits = np.asarray(carrier, dtype=np.float32).view(np.uint16).reshape(2, n_out, k)
+    f = (bits.astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+    return f[0] + f[1]
+
+
+def test_layernorm_gain_fold_of_the_tensor_core_weights():
+    """weights.build_blob folds positive LayerNorm gains into the bf16 W2 images (relu(g*x + b) = g*relu(x + b/g)) and falls
+    back to the plain image + beta when a gain is not positive; either way image . relu(.) reproduces W2 . relu(g*x + b)."""
+    from phoregen_b200 import _lib
+    from phoregen_b200.weights import build_blob
+    _, sd = build_model()
+    key = "denoiser.base_block.1.bond_ffn.hv_func.net.1.weight"
+    key = key if key in sd else next(k for k in sorted(sd) if k.endswith("hv_func.net.1.weight") and ".base_block.1." in k)
+    sd2 = dict(sd)
+    g = sd[key].clone(); g[5] = -g[5]
+    sd2[key] = g
+    rng = np.random.default_rng(1)
+    xn = rng.normal(size=128)
+    for state, expect_all_folded in ((sd, True), (sd2, False)):
+        blob, off = build_blob(state)
+        slot = {n: (int(o), int(m)) for (n, m), o in zip(_lib.slot_table(), off)}
+        get = lambda n: blob[slot[n][0]: slot[n][0] + slot[n][1]]
+        folded = []
+        for S in ("L1.tr.", "L1.nb.", "L1.pb.", "L1.nk.", "L1.pk."):
+            for i, kv in enumerate("kv"):
+                n_out = slot[S + f"w2{kv}"][1] // 128
+                w2 = get(S + f"w2{kv}").reshape(n_out, 128).astype(np.float64)
+                gam, bet = get(S + f"ln{kv}_g").astype(np.float64), get(S + f"ln{kv}_b").astype(np.float64)
+                fold = get(S + "fold")[i] > 0.5
+                folded.append(bool(fold))
+                assert fold == bool(np.all(gam > 1e-3))
+                img = _bf16_image_to_f64(get(S + f"w2{kv}.bf"), n_out)
+                bf = get(S + f"ln{kv}_bf").astype(np.float64)
+                hid = np.maximum(xn + bf, 0.0) if fold else np.maximum(gam * xn + bf, 0.0)
+                want = w2 @ np.maximum(gam * xn + bet, 0.0)
+                np.testing.assert_allclose(img @ hid, want, rtol=0, atol=3e-5 * (1.0 + np.abs(want).max()))
+        assert all(folded) == expect_all_folded
+
+
 def test_missing_library_fails_loudly(tmp_path, monkeypatch):
     from phoregen_b200 import _lib
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
