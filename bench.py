@@ -153,7 +153,7 @@ def run_reference_arm(args):
         "e2e": {"value": val, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -332,9 +332,18 @@ def run_ours(args):
                                     "sample": f"{args.cpu_molecules} molecules x {n} atoms, 1 warm-up + 2 timed reverse steps ({sec:.2f} s/step), extrapolated x1000"}
         if gathered is not None:
             line["config"]["gathered_molecules"] = int(gathered["num_atoms"].numel())
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_JSON_OUT = None
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -351,6 +360,13 @@ def main():
     args = ap.parse_args()
     if args.full_trajectory:
         args.steps = TRAJ_STEPS - max(args.warmup, 3)
+    # The contract is ONE JSON line on stdout.  Native libraries print there too (NCCL announces its version on stdout when
+    # NCCL_DEBUG=VERSION is set in the environment), so file descriptor 1 is pointed at stderr for the duration of the run and
+    # the JSON line goes to the saved descriptor.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args)
     else:
