@@ -303,7 +303,9 @@ def install(reference_root="/root/reference"):
     mod("torch_cluster", knn=knn, knn_graph=knn_graph)
     tg = mod("torch_geometric")
     tg.nn = mod("torch_geometric.nn", knn_graph=knn_graph, knn=knn, radius_graph=_not_needed, radius=_not_needed)
-    tg.utils = mod("torch_geometric.utils", remove_self_loops=remove_self_loops)
+    def k_hop_subgraph(*args, **kwargs):      # only MaskByPhore (training-time masking, outside the sampling path) calls it
+        raise NotImplementedError("torch_geometric.utils.k_hop_subgraph is not provided by the stand-ins")
+    tg.utils = mod("torch_geometric.utils", remove_self_loops=remove_self_loops, k_hop_subgraph=k_hop_subgraph)
     tg.data = mod("torch_geometric.data", HeteroData=HeteroData, Batch=Batch, Dataset=Dataset)
     mod("easydict", EasyDict=EasyDict)
     for name in ("rdkit", "rdkit.Chem", "rdkit.Chem.AllChem", "rdkit.Geometry", "rdkit.RDLogger",
