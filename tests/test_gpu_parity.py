@@ -512,3 +512,28 @@ def test_layernorm_gains_of_either_sign(dev):
     got = _forward(m, b, times, dev)
     for g, w, what in zip(got[:3], want[:3], ("logits_node", "pos", "logits_edge")):
         assert_close(g, w, what)
+
+
+def test_phore_files_to_decoded_molecules_end_to_end(model, dev, tmp_path):
+    """.phore files -> collate (two pharmacophores in one batch) -> sampler -> results -> per-molecule decode: the host-side
+    pieces around the hot path (phore_io.py, results.py) fit the sampler's interfaces."""
+    from test_cpu_phore_io import _write
+    from phoregen_b200 import phore_io, results as R
+    from phoregen_b200.diffusion import TrajectorySampler
+    m, _ = model
+    items = [phore_io.parse_phore_file(_write(str(tmp_path / f"p{i}.phore"))) for i in range(2)]
+    torch.manual_seed(0); np.random.seed(0)
+    items[1] = phore_io.AddPhoreNoise(0.1, 5.0)(items[1])
+    batch = phore_io.collate_phores(items, copies=[3, 2])
+    n_atoms = torch.tensor([9, 12, 7, 10, 8], dtype=torch.int32)
+    s = TrajectorySampler(m, None, 5, dev, ligand_num_atoms=n_atoms, save_traj=False, seed=3, use_cuda_graph=False, phore_batch=batch)
+    s.run(4)
+    res = s.results()
+    mols = R.unbatch_data(res, 5)
+    dec = R.decode_batch(res, 5)
+    assert [len(mm["pred"][0]) for mm in mols] == n_atoms.tolist()
+    for mm, d in zip(mols, dec):
+        one = R.decode_data([t.cpu() for t in mm["pred"]], mm["edge_index"].cpu())
+        assert d["element"] == one["element"] and torch.equal(d["atom_pos"], one["atom_pos"])
+        assert torch.equal(d["bond_type"], one["bond_type"]) and torch.equal(d["bond_index"], one["bond_index"])
+        assert torch.isfinite(d["atom_pos"]).all()
