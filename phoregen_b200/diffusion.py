@@ -172,8 +172,12 @@ class PhoreDiff(nn.Module):
         cnt = self.predict_atom_count(h_phore_emb, batch_phore, h_phore, n_graphs)
         return v, pos, b, cnt
 
-    def compute_loss(self, data):
-        raise NotImplementedError("training tier (diffusion.py:249-352) is scheduled after the sampling path; see DESIGN.md")
+    def compute_loss(self, data, rng_device=None):
+        """Value of the training objective (diffusion.py:249-352) -> (loss_total, loss_dict), forward only: what the
+        reference's validation loop evaluates under no_grad.  The backward pass is not built, so
+        `loss_total` has no autograd graph and `.backward()` on it fails loudly."""
+        from . import losses
+        return losses.compute_loss(self, data, rng_device=rng_device)
 
     # ------------------------------------------------------------------ D2 (diffusion.py:356-387)
     @torch.no_grad()

@@ -72,3 +72,41 @@ class PhoreData:
         if key != "phore":
             raise KeyError(key)
         return self._phore
+
+
+class _NS(dict):
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+
+class TrainBatch:
+    """PyG-free stand-in for the collated training batch `compute_loss` reads (diffusion.py:249-352):
+    data['ligand'].{x,pos,batch,ptr}, data['ligand','ligand'].{f_edge_attr,f_edge_index,f_edge_attr_batch,edge_index},
+    data['phore'].{x,pos,norm,batch}, data.num_graphs."""
+
+    def __init__(self, ligand, bonds, phore, num_graphs):
+        self._s = {"ligand": _NS(ligand), ("ligand", "ligand"): _NS(bonds), "phore": _NS(phore)}
+        self.num_graphs = num_graphs
+
+    def __getitem__(self, key):
+        return self._s[key]
+
+    def to(self, device):
+        for st in self._s.values():
+            for k, v in list(st.items()):
+                st[k] = v.to(device)
+        return self
+
+
+def training_batch_from_synthetic(b):
+    """`synthetic.synthetic_batch(..., edge_order="training")` -> TrainBatch with class-index targets (the one-hot rows of the
+    synthetic batch play the role of the clean molecule)."""
+    n = torch.bincount(b["batch_node"])
+    ptr = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(n, 0)])
+    ph = b["phore"]
+    return TrainBatch(
+        ligand=dict(x=b["h_node"].argmax(-1), pos=b["pos"].clone(), batch=b["batch_node"], ptr=ptr),
+        bonds=dict(f_edge_attr=b["h_edge"].argmax(-1), f_edge_index=b["edge_index"], f_edge_attr_batch=b["batch_edge"],
+                   edge_index=b["edge_index"]),
+        phore=dict(x=ph["x"], pos=ph["pos"], norm=ph["norm"], batch=ph["batch"]),
+        num_graphs=int(n.numel()))

@@ -537,3 +537,34 @@ def test_phore_files_to_decoded_molecules_end_to_end(model, dev, tmp_path):
         assert d["element"] == one["element"] and torch.equal(d["atom_pos"], one["atom_pos"])
         assert torch.equal(d["bond_type"], one["bond_type"]) and torch.equal(d["bond_index"], one["bond_index"])
         assert torch.isfinite(d["atom_pos"]).all()
+
+
+def test_compute_loss_value_matches_oracle_forward(model, dev):
+    """Forward-only training objective (diffusion.py:249-352): noise drawn on the CPU with the reference's draw order, forward
+    on the CUDA kernels, loss terms in torch - against the same objective evaluated with the CPU oracle's forward."""
+    from phoregen_b200 import losses
+    from phoregen_b200.testing import training_batch_from_synthetic
+    m, sd = model
+    seed = 300
+    while True:
+        b = O.synthetic_batch(seed, 4, n_atoms=(6, 11), edge_order="training")
+        data = training_batch_from_synthetic(b)
+        stages = []
+
+        def oracle_forward(**kw):
+            out = O.phorediff_forward(sd, kw["h_node_pert"], kw["pos_pert"], kw["batch_node"], kw["h_edge_pert"], kw["edge_index"],
+                                      kw["batch_edge"], kw["time_step"], kw["h_phore"], kw["pos_phore"], kw["phore_norm"],
+                                      kw["batch_phore"], stages=stages)
+            return out[0], out[1], out[2], out[3]
+
+        cpu_model, _ = build_model()
+        torch.manual_seed(9)
+        want_total, want = losses.compute_loss(cpu_model, data, forward=oracle_forward)
+        if O.forward_knn_margin(stages) >= 5e-4:
+            break
+        seed += 1000
+    torch.manual_seed(9)
+    got_total, got = m.compute_loss(training_batch_from_synthetic(b).to(dev), rng_device="cpu")
+    assert not got_total.requires_grad
+    for k in want:
+        assert got[k] == pytest.approx(want[k], rel=2e-3, abs=2e-4), k
