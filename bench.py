@@ -52,7 +52,7 @@ def f_exec_trip_flops(n):
     per 128-row tile (4 segments x 32 lanes) 3 MMAs M128 N256 K16 (angle slice, bf16x3) + 2 x 24 MMAs M128 N128 K16
     (second Linear of the key / value MLPs, bf16x3); ceil((n-1)/4) tiles per ligand atom.  Includes the padding rows and
     the x3 of the hi/lo split, so it is the work the tensor pipe really performs."""
-    tiles = n * ((n - 1 + 3) // 4)
+    tiles = n * ((n - 1 + 3) // 4) * max((n - 2 + 31) // 32, 1)      # segments longer than 32 rows: one tile per 32-row chunk
     macs_per_tile = 3 * 128 * 256 * 16 + 48 * 128 * 128 * 16
     return 2.0 * tiles * macs_per_tile
 

@@ -54,6 +54,40 @@ def well_conditioned_seed(sd, seed, n_graphs, n_atoms, times, n_ex=0):
         seed += 1
 
 
+def big_forward_fixture(ref, sd, seed, n_graphs, n_atoms, times, p_choices=(10, 11, 12), pos_scale=2.5, min_margin=5e-4):
+    """Forward outputs of the unmodified reference for molecules beyond one 32-row attention chunk (n up to 80)."""
+    while True:
+        b = O.synthetic_batch(seed, n_graphs, n_atoms=n_atoms, p_choices=p_choices, pos_scale=pos_scale)
+        ph = b["phore"]
+        stages = []
+        O.phorediff_forward(sd, b["h_node"], b["pos"], b["batch_node"], b["h_edge"], b["edge_index"], b["batch_edge"],
+                            torch.tensor(times), ph["x"], ph["pos"], ph["norm"], ph["batch"], stages=stages)
+        margin = O.forward_knn_margin(stages)
+        if margin >= min_margin:
+            break
+        print(f"  big seed {seed}: kNN margin {margin:.2e} too small, trying the next one", flush=True)
+        seed += 1
+    with torch.no_grad():
+        out = ref(b["h_node"], b["pos"], b["batch_node"], b["h_edge"], b["edge_index"], b["batch_edge"],
+                  torch.tensor(times, dtype=torch.long), ph["x"], ph["pos"], ph["norm"], ph["batch"])
+    return dict(seed=seed, knn_margin=margin, n_graphs=n_graphs, n_atoms=n_atoms, p_choices=p_choices, pos_scale=pos_scale,
+                times=times, pred_node=out[0], pred_pos=out[1], pred_edge=out[2])
+
+
+def big_main():
+    """python -m oracle.make_golden big  ->  tests/golden/forward_big.pt (minutes of CPU time: the reference evaluates
+    437-wide MLPs on 493k triplets per layer at n = 80)."""
+    torch.set_num_threads(os.cpu_count())
+    ref, sd, _ = reference_model(0)
+    cases = {}
+    for name, seed, G, na, times in (("n35", 201, 1, 35, [412]), ("n48", 202, 1, 48, [37]), ("n64", 203, 1, 64, [871]),
+                                     ("n78", 204, 1, 78, [5]), ("n80", 205, 1, 80, [640]),
+                                     ("ragged20_40", 206, 8, (20, 40), [999, 700, 512, 300, 123, 45, 1, 0])):
+        cases[name] = big_forward_fixture(ref, sd, seed, G, na, times, p_choices=(10, 11, 12) if G == 1 else (6, 7, 8))
+        print(name, "seed", cases[name]["seed"], "margin", cases[name]["knn_margin"], flush=True)
+        torch.save(dict(state_dict_digest=state_dict_digest(sd), cases=cases), os.path.join(GOLD, "forward_big.pt"))
+
+
 def forward_fixture(ref, seed, n_graphs, n_atoms, times, n_ex=0, stages=True, sd=None):
     seed, margin = well_conditioned_seed(sd, seed, n_graphs, n_atoms, times, n_ex)
     b = O.synthetic_batch(seed, n_graphs, n_atoms=n_atoms, n_ex=n_ex)
@@ -210,4 +244,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    big_main() if "big" in sys.argv[1:] else main()

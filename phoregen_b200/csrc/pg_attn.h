@@ -69,7 +69,7 @@ struct KnnTcArgs {
     float* out;              // node mode [N,128]; pos mode [N,3]
 };
 int pg_launch_knn_tc(const KnnTcArgs& a, int pos, int num_sms, cudaStream_t s);
-constexpr int PG_BOND_TC_MAX_ROWS = 32;    // one TMEM lane quarter per segment
+constexpr int PG_BOND_TC_SINGLE_CHUNK_ROWS = 32;    // n-1 <= 32: one TMEM lane quarter per segment, else 32-row chunks
 int pg_launch_bond_tc(const BondTcArgs& a, int pos, int num_sms, cudaStream_t s);
 
 struct TripArgs {
@@ -85,7 +85,8 @@ struct TripArgs {
     int min_atoms;           // units of molecules with fewer atoms are skipped (they ran on the tcgen05 kernel)
 };
 
-// tcgen05 version of the triplet layer (csrc/pg_trip_tc.cu); handles molecules with n - 2 <= 32 rows per segment
+// tcgen05 version of the triplet layer (csrc/pg_trip_tc.cu); segments of up to 32 rows are one TMEM lane quarter, longer
+// ones are cut into 32-row chunks with an on-line softmax across the chunks (any n up to PG_MAX_ATOMS)
 struct TripTcArgs {
     PlanDev d;
     const float* x;
@@ -103,7 +104,7 @@ struct TripTcArgs {
     float* hb;
     int maxn;
 };
-constexpr int PG_TRIP_TC_MAX_ATOMS = 34;
+constexpr int PG_TRIP_TC_SINGLE_CHUNK_ATOMS = 34;   // n - 2 <= 32: the single-chunk instantiation serves the batch
 int pg_launch_trip_pr(const TripTcArgs& a, cudaStream_t s);               // per-edge partials P, R (elementwise, HBM-bound)
 int pg_launch_trip_tc(const TripTcArgs& a, int num_sms, cudaStream_t s);  // the tcgen05 triplet kernel proper
 size_t pg_trip_tc_smem(int maxn);

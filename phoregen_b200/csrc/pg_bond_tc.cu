@@ -15,7 +15,9 @@
 //
 // Software pipeline across tiles, as in the triplet kernel:  LN-k(t) | epilogue(t-1) | LN-v(t) | logits(t)  on the row
 // warps while the tensor pipe runs W2k(t) | W2v(t).  TMEM: hid_k [0,128) out_k [128,256) hid_v [256,384) out_v [384,512).
-// Atoms whose segment does not fit a lane quarter (n-1 > 32) or has no rows are left to the fp32 kernel (pg_attn.cu).
+// MULTI: batches with segments longer than one lane quarter (n-1 > 32).  A segment then takes C = ceil((n-1)/32) quarters
+// of the same tile (4/C atoms per tile, tile table in the plan); the softmax statistics and the per-quarter outputs of
+// the C row warps of a (segment, channel quarter) meet in shared memory.
 #include <algorithm>
 #include "pg_attn.h"
 #include "pg_tc.cuh"
@@ -24,10 +26,12 @@ namespace {
 constexpr int W_TILE = 32768;               // one [128 x 128] bf16 matrix in two 128B-swizzled K blocks
 constexpr int SM_W = 4 * W_TILE;            // (k,v) x (hi,lo)
 constexpr int SM_STAT = 128 * 16 * 4;       // [2 mlp][128 rows][4 quarters][2] partial LayerNorm sums
-constexpr int SM_RED = 4 * 4 * 4 * 4;       // pos layer: [segment][quarter][4] partial coordinate updates
+constexpr int SM_RED = 2 * 4 * 4 * 4 * 4;   // pos layer: [tile parity][segment][quarter][4] partial coordinate updates
+constexpr int SM_EX = 4 * 4 * 8 * 4;        // MULTI: [channel quarter][lane quarter][max 4 | sum 4] softmax statistics of a chunk
+constexpr int SM_OX = 4 * 128 * 4;          // MULTI, node layer: [lane quarter][128] per-chunk outputs
 constexpr int XP_LD = 36;                   // padded row stride (floats) of a warp's transpose tile [32 rows][32 channels]
 constexpr int SM_XP = 16 * 32 * XP_LD * 4;  // one tile per row warp
-constexpr int SM_TOTAL = SM_W + SM_XP + SM_STAT + SM_RED + 5 * 128 * 4 /*ln + b2v*/ + 128 /*barriers*/ + 1024 /*alignment*/;
+constexpr int SM_TOTAL = SM_W + SM_XP + SM_STAT + SM_RED + SM_EX + SM_OX + 5 * 128 * 4 /*ln + b2v*/ + 128 /*barriers*/ + 1024 /*alignment*/;
 constexpr float kInvSqrtD = 0.35355339059327373f;
 constexpr int ROW_WARPS = 16;
 constexpr int MMA_WARP = ROW_WARPS;
@@ -38,24 +42,40 @@ enum { B_HIDK = 0, B_HIDV, B_OUTK, B_OUTV, B_COUNT };
 struct SegInfo {
     bool valid;
     int n, il, v, ctx0;
+    int r0, nch, wq0;       // first row of this quarter's chunk, chunks of the segment, lane quarter of its first chunk
     long long e0;
 };
+template <bool MULTI>
 __device__ __forceinline__ SegInfo seg_info(const PlanDev& d, long long tile, int wq) {
     SegInfo s;
-    const long long u = tile * 4 + wq;
-    s.valid = false; s.n = 2; s.il = 0; s.v = 0; s.ctx0 = 0; s.e0 = 0;
-    if (u < d.Nl) {
-        const int g = d.lig_graph[u];
-        s.n = d.g_n[g]; s.il = (int)(u - d.lig_off[g]);
-        s.ctx0 = d.ctx_off[g] + d.g_p[g];
-        s.v = s.ctx0 + s.il;
-        s.e0 = d.eoff[g] + (long long)s.il * (s.n - 1);
-        s.valid = s.n - 1 >= 1 && s.n - 1 <= PG_BOND_TC_MAX_ROWS;
+    s.valid = false; s.n = 2; s.il = 0; s.v = 0; s.ctx0 = 0; s.e0 = 0; s.r0 = 0; s.nch = 1; s.wq0 = wq;
+    if (!MULTI) {
+        const long long u = tile * 4 + wq;
+        if (u < d.Nl) {
+            const int g = d.lig_graph[u];
+            s.n = d.g_n[g]; s.il = (int)(u - d.lig_off[g]);
+            s.ctx0 = d.ctx_off[g] + d.g_p[g];
+            s.v = s.ctx0 + s.il;
+            s.e0 = d.eoff[g] + (long long)s.il * (s.n - 1);
+            s.valid = s.n - 1 >= 1 && s.n - 1 <= 32;
+        }
+    } else if (tile < d.nbt) {
+        const int g = d.btile_graph[tile];
+        const int n = d.g_n[g], nch = pg_bond_chunks(n), apt = pg_bond_atoms_per_tile(n);
+        const int slot = wq / nch;
+        const int il = (int)(tile - d.btile_off[g]) * apt + slot;
+        if (slot < apt && il < n) {
+            s.n = n; s.il = il; s.nch = nch; s.wq0 = slot * nch; s.r0 = (wq - s.wq0) * 32;
+            s.ctx0 = d.ctx_off[g] + d.g_p[g];
+            s.v = s.ctx0 + il;
+            s.e0 = d.eoff[g] + (long long)il * (n - 1);
+            s.valid = true;
+        }
     }
     return s;
 }
 
-template <int POS>
+template <int POS, bool MULTI>
 __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -63,7 +83,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
     float* sXp = (float*)(sW + SM_W);
     float* sStat = sXp + SM_XP / 4;
     float* sRed = sStat + SM_STAT / 4;
-    float* sLn = sRed + SM_RED / 4;                 // gk, bk, gv, bv
+    float* sEx = sRed + SM_RED / 4;
+    float* sOx = sEx + SM_EX / 4;
+    float* sLn = sOx + SM_OX / 4;                   // gk, bk, gv, bv
     float* sB2 = sLn + 4 * 128;                     // b2v (128 or 16)
     uint64_t* bars = (uint64_t*)(sB2 + 128);
     uint32_t* tmem_slot = (uint32_t*)(bars + B_COUNT);
@@ -101,7 +123,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
     constexpr uint32_t C_HIDK = 0, C_OUTK = 128, C_HIDV = 256, C_OUTV = 384;
-    const long long ntiles = (d.Nl + 3) / 4;
+    const long long ntiles = MULTI ? d.nbt : (d.Nl + 3) / 4;
 
     if (warp >= MMA_WARP) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -145,9 +167,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
                 const long long nt = tile + gridDim.x;
                 if (nt < ntiles) {
                     for (int s4 = 0; s4 < 4; s4++) {
-                        const SegInfo sg = seg_info(d, nt, s4);
+                        const SegInfo sg = seg_info<MULTI>(d, nt, s4);
                         if (!sg.valid) continue;
-                        for (int r = pt; r < sg.n - 1; r += 96) {
+                        for (int r = sg.r0 + pt; r < min(sg.n - 1, sg.r0 + 32); r += 96) {
                             const float* row = a.B + (size_t)(sg.e0 + r) * a.ldb + a.b_k;
                             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row), "r"((a.b_v - a.b_k + 128) * 4) : "memory");
                         }
@@ -180,7 +202,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
             const uint32_t dst = tc::smem_u32(xp + sr * XP_LD + ch);
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                const int row = (i * 4 + sr) < nrow ? (i * 4 + sr) : 0;
+                const int row = (sg.r0 + i * 4 + sr) < nrow ? (sg.r0 + i * 4 + sr) : 0;
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 4 * XP_LD * 4), "l"(pb + (size_t)(sg.e0 + row) * a.ldb) : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -196,7 +218,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
                 float4 u[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    const int row = (i * 4 + sr) < nrow ? (i * 4 + sr) : 0;
+                    const int row = (sg.r0 + i * 4 + sr) < nrow ? (sg.r0 + i * 4 + sr) : 0;
                     u[i] = ldg4(ps + (size_t)(sg.ctx0 + row + (row >= sg.il)) * a.nc.lda);
                 }
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -259,6 +281,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
             tc::tc_fence_before();
             tc::mbar_arrive(&bars[mlp == 0 ? B_HIDK : B_HIDV]);
         };
+        int prev_nch = 1, prev_wq0 = 0, prev_r0 = 0;
         auto epilogue = [&](uint32_t parity) {
             tc::mbar_wait(&bars[B_OUTV], parity);
             tc::tc_fence_after();
@@ -273,9 +296,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
                     v[i] = pr.x; v[i + 1] = pr.y;
                 }
                 const float o = transpose_reduce32(v, lane);
-                if (prev_valid) {
-                    const int c = cq * 32 + lane;
-                    a.out[(size_t)prev_v * 128 + c] = o + sB2[c];                          // sum(alpha) = 1
+                const int c = cq * 32 + lane;
+                if (!MULTI) {
+                    if (prev_valid) a.out[(size_t)prev_v * 128 + c] = o + sB2[c];          // sum(alpha) = 1
+                } else {
+                    // the chunks of a segment sit in consecutive lane quarters: their partial outputs meet in shared memory
+                    sOx[wq * 128 + c] = o;
+                    asm volatile("bar.sync %0, 128;" ::"r"(7 + cq) : "memory");
+                    if (prev_valid && prev_r0 == 0) {
+                        float t = sOx[prev_wq0 * 128 + c];
+                        for (int k = 1; k < prev_nch; k++) t += sOx[(prev_wq0 + k) * 128 + c];
+                        a.out[(size_t)prev_v * 128 + c] = t + sB2[c];
+                    }
                 }
             } else {
                 float vh[4];
@@ -288,25 +320,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
                 for (int o = 16; o > 0; o >>= 1) {
                     p0 += __shfl_xor_sync(PG_FULL, p0, o); p1 += __shfl_xor_sync(PG_FULL, p1, o); p2 += __shfl_xor_sync(PG_FULL, p2, o);
                 }
-                float* rd = sRed + (wq * 4 + cq) * 4;
+                float* red = sRed + (parity & 1) * 64;      // double-buffered by tile parity (readers of other quarters, MULTI)
+                float* rd = red + (wq * 4 + cq) * 4;
                 if (lane == 0) { rd[0] = p0; rd[1] = p1; rd[2] = p2; }
-                asm volatile("bar.sync %0, 128;" ::"r"(3 + wq) : "memory");
-                if (cq == 0 && lane < 3 && prev_valid) {
-                    const float* r4 = sRed + wq * 16 + lane;
-                    a.out[(size_t)prev_v * 3 + lane] = ((r4[0] + r4[4]) + (r4[8] + r4[12])) * (1.0f / 16.0f);
+                if (!MULTI) {
+                    asm volatile("bar.sync %0, 128;" ::"r"(3 + wq) : "memory");
+                    if (cq == 0 && lane < 3 && prev_valid) {
+                        const float* r4 = red + wq * 16 + lane;
+                        a.out[(size_t)prev_v * 3 + lane] = ((r4[0] + r4[4]) + (r4[8] + r4[12])) * (1.0f / 16.0f);
+                    }
+                } else {
+                    asm volatile("bar.sync 11, %0;" ::"n"(ROW_THREADS) : "memory");
+                    if (cq == 0 && lane < 3 && prev_valid && prev_r0 == 0) {
+                        float t = 0.f;
+                        for (int k = 0; k < prev_nch; k++) {
+                            const float* r4 = red + (prev_wq0 + k) * 16 + lane;
+                            t += (r4[0] + r4[4]) + (r4[8] + r4[12]);
+                        }
+                        a.out[(size_t)prev_v * 3 + lane] = t * (1.0f / 16.0f);
+                    }
                 }
             }
         };
         uint32_t ph = 0;
         int tiles_done = 0;
         bool any = false;
-        SegInfo sg = seg_info(d, blockIdx.x, wq);
+        SegInfo sg = seg_info<MULTI>(d, blockIdx.x, wq);
         request_edge_rows(0, sg);
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
-            const bool rowvalid = sg.valid && lane < sg.n - 1;
-            const int r = rowvalid ? lane : 0;
+            const bool rowvalid = sg.valid && sg.r0 + lane < sg.n - 1;
+            const int r = rowvalid ? sg.r0 + lane : 0;
             const bool more = tile + gridDim.x < ntiles;
-            const SegInfo nsg = seg_info(d, more ? tile + gridDim.x : tile, wq);
+            const SegInfo nsg = seg_info<MULTI>(d, more ? tile + gridDim.x : tile, wq);
             // ---- key MLP
             layer_norm(0, sg, tmem + C_HIDK, true, 1, sg);
             // ---- value epilogue of the previous tile (its W2v MMA ran during that tile's logits and the LayerNorm above)
@@ -339,18 +384,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
                     al[h] = rowvalid ? (s0.x + s0.y) * kScale : -INFINITY;
                 }
                 // segment softmax across the 32 lanes: max and sum on the REDUX unit
+                float mx[4], ssum[4];
 #pragma unroll
                 for (int h = 0; h < 4; h++) {
-                    const float mx = tc::warp_max_redux(al[h]);
-                    al[h] = rowvalid ? tc::ex2_approx(al[h] - mx) : 0.f;
+                    mx[h] = tc::warp_max_redux(al[h]);
+                    al[h] = rowvalid ? tc::ex2_approx(al[h] - mx[h]) : 0.f;
                 }
 #pragma unroll
-                for (int h = 0; h < 4; h++) {
-                    const float ssum = tc::warp_sum01_redux(al[h]);      // every lane takes part in the reduction (not under the ?:)
-                    al[h] = rowvalid ? al[h] * __frcp_rn(ssum) : 0.f;
+                for (int h = 0; h < 4; h++) ssum[h] = tc::warp_sum01_redux(al[h]);   // every lane takes part in the reduction
+                if (!MULTI) {
+#pragma unroll
+                    for (int h = 0; h < 4; h++) al[h] = rowvalid ? al[h] * __frcp_rn(ssum[h]) : 0.f;
+                } else {
+                    // (max, sum) of every chunk of the segment -> global max M and sum L; alpha = p 2^(m - M) / L
+                    float* ex = sEx + (cq * 4 + wq) * 8;
+                    if (lane == 0) { st4(ex, make_float4(mx[0], mx[1], mx[2], mx[3])); st4(ex + 4, make_float4(ssum[0], ssum[1], ssum[2], ssum[3])); }
+                    asm volatile("bar.sync %0, 128;" ::"r"(7 + cq) : "memory");
+                    float M[4] = {mx[0], mx[1], mx[2], mx[3]}, L[4] = {0.f, 0.f, 0.f, 0.f};
+                    const float* e0 = sEx + (cq * 4 + sg.wq0) * 8;
+                    for (int k = 0; k < sg.nch; k++) {
+                        const float4 m4 = ld4(e0 + k * 8);
+                        M[0] = fmaxf(M[0], m4.x); M[1] = fmaxf(M[1], m4.y); M[2] = fmaxf(M[2], m4.z); M[3] = fmaxf(M[3], m4.w);
+                    }
+                    for (int k = 0; k < sg.nch; k++) {
+                        const float4 m4 = ld4(e0 + k * 8), l4 = ld4(e0 + k * 8 + 4);
+                        L[0] = fmaf(l4.x, tc::ex2_approx(m4.x - M[0]), L[0]); L[1] = fmaf(l4.y, tc::ex2_approx(m4.y - M[1]), L[1]);
+                        L[2] = fmaf(l4.z, tc::ex2_approx(m4.z - M[2]), L[2]); L[3] = fmaf(l4.w, tc::ex2_approx(m4.w - M[3]), L[3]);
+                    }
+#pragma unroll
+                    for (int h = 0; h < 4; h++) al[h] = rowvalid ? al[h] * __fdividef(tc::ex2_approx(mx[h] - M[h]), L[h]) : 0.f;
                 }
             }
-            prev_valid = sg.valid; prev_v = sg.v;
+            prev_valid = sg.valid; prev_v = sg.v; prev_nch = sg.nch; prev_wq0 = sg.wq0; prev_r0 = sg.r0;
             if (POS) {
                 const int sj = sg.ctx0 + r + (r >= sg.il);
                 rel0 = a.x[(size_t)sg.v * 3] - a.x[(size_t)sj * 3];                        // rel_x = x[dst] - x[src]
@@ -372,14 +437,24 @@ int pg_launch_bond_tc(const BondTcArgs& a, int pos, int num_sms, cudaStream_t s)
     if (a.d.Nl <= 0) return PG_OK;
     static bool init = false;
     if (!init) {
-        PG_CUDA_CHECK(cudaFuncSetAttribute(bond_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-        PG_CUDA_CHECK(cudaFuncSetAttribute(bond_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        PG_CUDA_CHECK(cudaFuncSetAttribute(bond_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        PG_CUDA_CHECK(cudaFuncSetAttribute(bond_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        PG_CUDA_CHECK(cudaFuncSetAttribute(bond_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        PG_CUDA_CHECK(cudaFuncSetAttribute(bond_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
         init = true;
     }
-    const long long ntiles = (a.d.Nl + 3) / 4;
+    // every segment fits one lane quarter (n-1 <= 32): atoms packed four to a tile across the batch; otherwise the
+    // per-graph tile table with 4/C atoms per tile
+    const bool multi = a.d.max_n - 1 > PG_BOND_TC_SINGLE_CHUNK_ROWS;
+    const long long ntiles = multi ? a.d.nbt : (a.d.Nl + 3) / 4;
     const unsigned grid = (unsigned)std::min<long long>(ntiles, num_sms);
-    if (pos == 0) bond_tc_kernel<0><<<grid, NTHREADS, SM_TOTAL, s>>>(a);
-    else bond_tc_kernel<1><<<grid, NTHREADS, SM_TOTAL, s>>>(a);
+    if (!multi) {
+        if (pos == 0) bond_tc_kernel<0, false><<<grid, NTHREADS, SM_TOTAL, s>>>(a);
+        else bond_tc_kernel<1, false><<<grid, NTHREADS, SM_TOTAL, s>>>(a);
+    } else {
+        if (pos == 0) bond_tc_kernel<0, true><<<grid, NTHREADS, SM_TOTAL, s>>>(a);
+        else bond_tc_kernel<1, true><<<grid, NTHREADS, SM_TOTAL, s>>>(a);
+    }
     PG_LAUNCH_CHECK();
     return PG_OK;
 }

@@ -41,7 +41,14 @@ struct PlanDev {
     const int* edge_graph;  // [Eb] reference-order edge -> graph
     const int* esrc_node;   // [Eb] internal edge -> context node of src (j)
     const int* edst_node;   // [Eb] internal edge -> context node of dst (i)
+    // bond-graph attention tiles when some segment is longer than one 32-row TMEM lane quarter (pg_bond_tc.cu): a graph
+    // whose segments take C = ceil((n-1)/32) quarters places 4/C atoms in a tile, ceil(n / (4/C)) tiles per graph
+    int nbt;                // number of such tiles in the batch
+    const int* btile_off;   // [G+1] first tile of graph g
+    const int* btile_graph; // [nbt] tile -> graph
 };
+__host__ __device__ inline int pg_bond_chunks(int n) { return (n - 1 + 31) >> 5; }                // quarters per segment
+__host__ __device__ inline int pg_bond_atoms_per_tile(int n) { const int c = pg_bond_chunks(n); return c <= 4 ? 4 / c : 0; }
 
 // ---------------------------------------------------------------- small vector helpers
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }

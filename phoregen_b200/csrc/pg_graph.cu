@@ -64,6 +64,7 @@ void carve(Carver& c, const Sizes& s, int G, PgPlan* pl) {
     int* perm = I(s.Eb); int* inv_perm = I(s.Eb); int* edge_graph = I(s.Eb);
     int* esrc = I(s.Eb); int* edst = I(s.Eb);
     int* flag = I(4);
+    int* btile_off = I(G + 1); int* btile_graph = I(s.Nl);
     float* h = F(s.N * 128); float* x = F(s.N * 3 + 4); float* hb = F(s.Eb * 128);
     float* nbuf = F(s.N * 1920);
     float* qn1 = F(s.N * 128); float* qn2 = F(s.N * 128);
@@ -81,6 +82,7 @@ void carve(Carver& c, const Sizes& s, int G, PgPlan* pl) {
         d.ctx_off = ctx_off; d.lig_off = lig_off; d.ph_off = ph_off; d.eoff = eoff; d.koff = koff; d.t3off = t3off;
         d.g_n = g_n; d.g_p = g_p; d.node_graph = node_graph; d.lig_graph = lig_graph; d.ph_graph = ph_graph;
         d.perm = perm; d.edge_graph = edge_graph; d.esrc_node = esrc; d.edst_node = edst;
+        d.btile_off = btile_off; d.btile_graph = btile_graph;
         pl->inv_perm = inv_perm; pl->flag = flag;
         pl->h = h; pl->x = x; pl->hb = hb; pl->nbuf = nbuf; pl->qn1 = qn1; pl->qn2 = qn2; pl->o1 = o1; pl->o2 = o2;
         pl->dx1 = dx1; pl->dx2 = dx2; pl->ebuf = ebuf; pl->qt = qt; pl->rbuf = rbuf; pl->pbuf2 = pbuf2; pl->abuf = abuf; pl->ew = ew;
@@ -158,6 +160,14 @@ extern "C" int pg_plan_create(PgPlan** out, int G, const int32_t* na, const int3
     }
     std::vector<int> node_graph(s.N), lig_graph(s.Nl), ph_graph(s.P), perm(s.Eb), inv_perm(s.Eb), edge_graph(s.Eb),
         esrc(s.Eb), edst(s.Eb);
+    std::vector<int> btile_off(G + 1, 0), btile_graph;
+    for (int g = 0; g < G; g++) {
+        const int apt = std::max(pg_bond_atoms_per_tile(na[g]), 1);
+        const int nt = (na[g] + apt - 1) / apt;
+        btile_off[g + 1] = btile_off[g] + nt;
+        btile_graph.insert(btile_graph.end(), nt, g);
+    }
+    d.nbt = btile_off[G];
     for (int g = 0; g < G; g++) {
         int n = na[g], p = np[g];
         for (int v = pl->ctx_off[g]; v < pl->ctx_off[g + 1]; v++) node_graph[v] = g;
@@ -200,6 +210,8 @@ extern "C" int pg_plan_create(PgPlan** out, int G, const int32_t* na, const int3
     e = e ? e : up(d.ph_graph, ph_graph.data(), s.P * 4);
     e = e ? e : up(d.esrc_node, esrc.data(), s.Eb * 4);
     e = e ? e : up(d.edst_node, edst.data(), s.Eb * 4);
+    e = e ? e : up(d.btile_off, btile_off.data(), (G + 1) * 4);
+    e = e ? e : up(d.btile_graph, btile_graph.data(), (size_t)d.nbt * 4);
     e = e ? e : cudaMemsetAsync(pl->flag, 0, 16, stream);
     if (edge_order != 2) {
         e = e ? e : up(d.perm, perm.data(), s.Eb * 4);

@@ -276,14 +276,14 @@ int num_sms() {
     if (!v) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); if (v <= 0) v = 148; }
     return v;
 }
-// tcgen05 triplet kernel unless PG_TRIP=fp32; molecules above its segment-length limit take the fp32 kernel
+// tcgen05 triplet kernel unless PG_TRIP=fp32
 bool use_tc_trip(const PlanDev& d) {
     static int v = -1;
     if (v < 0) { const char* e = getenv("PG_TRIP"); v = (e && !strcmp(e, "fp32")) ? 0 : 1; }
     return v == 1 && d.max_n >= 3;
 }
 
-// tcgen05 bond-graph attention unless PG_BOND=fp32; atoms outside its segment range take the fp32 kernel
+// tcgen05 bond-graph attention unless PG_BOND=fp32 (the FFMA reference kernel, A/B validation only)
 bool use_tc_bond() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("PG_BOND"); v = (e && !strcmp(e, "fp32")) ? 0 : 1; }
@@ -300,8 +300,7 @@ int launch_bond(PgPlan* p, const BondAttnArgs& a0, const W& w, const std::string
         t.w2k_bf = (const uint16_t*)w(S + "w2k.bf"); t.w2v_bf = (const uint16_t*)w(S + "w2v.bf"); t.out = a.out;
         PG_TRY(pg_launch_bond_tc(t, pos, num_sms(), s));
         p->launches++;
-        a.tc_max_rows = PG_BOND_TC_MAX_ROWS;
-        if (a.d.max_n - 1 <= PG_BOND_TC_MAX_ROWS && a.d.min_n >= 2) return PG_OK;
+        return PG_OK;       // every atom has 1 <= n-1 <= 127 incoming edges (pg_plan_create): all segments ran there
     }
     PG_TRY(pg_launch_bond_attn(a, pos, s));
     p->launches++;
@@ -431,12 +430,12 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
                 { static int fl = -1; if (fl < 0) { const char* e = getenv("PG_TRIP_FLAGS"); fl = e ? atoi(e) : 0; } t.flags = fl; }
                 t.lnk_g = a.w.lnk_g; t.lnk_b = a.w.lnk_b; t.lnv_g = a.w.lnv_g; t.lnv_b = a.w.lnv_b; t.b2k = a.w.b2k; t.b2v = a.w.b2v;
                 t.lnk_bf = a.w.lnk_bf; t.lnv_bf = a.w.lnv_bf; t.fold = a.w.fold;
-                t.hb = p->hb; t.maxn = std::min(d.max_n, PG_TRIP_TC_MAX_ATOMS);
+                t.hb = p->hb; t.maxn = d.max_n;
                 { PgTimed timed(p, KC_OTHER, s); PG_TRY(pg_launch_trip_pr(t, s)); }
                 { PgTimed timed(p, KC_TRIP, s); PG_TRY(pg_launch_trip_tc(t, num_sms(), s)); } p->launches += 2;
-                a.min_atoms = PG_TRIP_TC_MAX_ATOMS + 1;
+            } else {   // PG_TRIP=fp32: the FFMA reference kernel (A/B validation only)
+                PgTimed timed(p, KC_TRIP, s); PG_TRY(pg_launch_trip(a, s)); p->launches++;
             }
-            if (a.min_atoms == 0 || d.max_n >= a.min_atoms) { PgTimed timed(p, KC_TRIP, s); PG_TRY(pg_launch_trip(a, s)); p->launches++; }
         }
         // h <- h + lin_node(o1 + o2)
         PG_TRY(gemm(p, s, PRO_SUM2, N, p->o1, 128, w, L + "lin.wt", 128, w(L + "lin.b"), p->h, 128, 1, p->o2, 128, nullptr,

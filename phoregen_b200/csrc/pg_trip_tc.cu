@@ -41,6 +41,8 @@ extern "C" int pg_debug_trip_trace(long long* h_out) { return cudaMemcpyFromSymb
 
 namespace {
 constexpr int PS_LD = 260;                 // padded row stride of the staged P rows (conflict-free LDS.128 across rows)
+// staged P rows: all n-1 rows of a unit while a segment is one chunk (n-1 <= 33), else the 33 rows of one chunk
+__host__ __device__ constexpr int ps_rows(int maxn) { return maxn - 1 < 33 ? maxn - 1 : 33; }
 constexpr int W_TILE = 32768;              // one [128 x 128] bf16 matrix in two 128B-swizzled K blocks
 constexpr int SM_W = 4 * W_TILE;           // (k,v) x (hi,lo)
 constexpr int SM_WA = 2 * 8192;            // angle slice of the first Linear: (hi,lo) x [256 x 16] bf16, no swizzle
@@ -62,34 +64,49 @@ constexpr int ROW_THREADS = ROW_WARPS * 32;
 enum { B_FEAT0 = 0, B_FEAT1, B_PREK, B_PREV0, B_PREV1, B_HIDK, B_HIDV, B_OUTK, B_OUTV, B_PSK, B_PSV, B_COUNT };
 
 // the sequence of (unit, tile) a CTA walks; every role steps through it redundantly
+// MULTI: a segment longer than 32 rows is cut into chunks of 32 rows; a tile is then (group of 4 segments) x (chunk c),
+// the chunks of a group on consecutive tiles (chunk-inner order), and the softmax runs on-line across them.
+// `stage` counts the refills of the staged P rows: once per unit when a segment is a single chunk (all n-1 rows of the
+// unit stay resident), once per tile otherwise (the 33 rows k -> j of chunk c).
 struct TileIter {
-    int u, tile, ntile, n, jl, ctx0;
+    int u, tile, ntile, n, jl, ctx0, nchunk, chunk, grp, stage;
     long long eoff;
     bool valid;
 };
+template <bool MULTI>
 __device__ __forceinline__ void iter_load_unit(const PlanDev& d, TileIter& it) {
     it.valid = false;
     while (it.u < d.Nl) {
         const int g = d.lig_graph[it.u];
         const int n = d.g_n[g];
-        if (n >= 3 && n - 2 <= 32) {        // larger molecules take the fp32 kernel
+        if (n >= 3 && (MULTI || n - 2 <= 32)) {
             it.n = n; it.jl = it.u - d.lig_off[g]; it.ctx0 = d.ctx_off[g] + d.g_p[g]; it.eoff = d.eoff[g];
-            it.ntile = (n - 1 + 3) >> 2; it.tile = 0; it.valid = true;
+            it.nchunk = MULTI ? (n - 2 + 31) >> 5 : 1;
+            it.ntile = ((n - 1 + 3) >> 2) * it.nchunk; it.tile = 0; it.chunk = 0; it.grp = 0; it.stage++; it.valid = true;
             return;
         }
         it.u += gridDim.x;
     }
 }
+template <bool MULTI>
 __device__ __forceinline__ void iter_next(const PlanDev& d, TileIter& it) {
-    if (++it.tile < it.ntile) return;
+    if (++it.tile < it.ntile) {
+        if (MULTI && it.nchunk > 1) {
+            it.stage++;
+            if (++it.chunk == it.nchunk) { it.chunk = 0; it.grp++; }
+        } else {
+            it.grp = it.tile;
+        }
+        return;
+    }
     it.u += gridDim.x;
-    iter_load_unit(d, it);
+    iter_load_unit<MULTI>(d, it);
 }
 // segment handled by lane quadrant wq in this tile
 struct Seg { bool valid; int il, ti; long long eji; };
 __device__ __forceinline__ Seg seg_of(const TileIter& it, int wq) {
     Seg s;
-    const int sidx = it.tile * 4 + wq;
+    const int sidx = it.grp * 4 + wq;
     s.valid = sidx < it.n - 1;
     s.il = s.valid ? sidx + (sidx >= it.jl) : (it.jl == 0 ? 1 : 0);
     s.ti = s.il - (s.il > it.jl);
@@ -106,8 +123,9 @@ __device__ __forceinline__ void write_features(const float* xs, const TileIter& 
     float f[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) f[i] = 0.f;
-    if (sg.valid && lane < it.n - 2) {
-        const int trow = lane + (lane >= sg.ti);
+    const int srow = it.chunk * 32 + lane;          // row inside the segment
+    if (sg.valid && srow < it.n - 2) {
+        const int trow = srow + (srow >= sg.ti);
         const float4 xj = ld4(xs + it.jl * 4), xi = ld4(xs + sg.il * 4), xk = ld4(xs + (trow + (trow >= it.jl)) * 4);
         const float xi0 = xi.x, xi1 = xi.y, xi2 = xi.z;
         const float pj0 = xj.x - xi0, pj1 = xj.y - xi1, pj2 = xj.z - xi2;
@@ -134,6 +152,7 @@ __device__ __forceinline__ void write_features(const float* xs, const TileIter& 
     *reinterpret_cast<uint4*>(ph + 4096 + 128) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
 }
 
+template <bool MULTI>
 __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     // offset arithmetic on the __shared__ array (not a uintptr_t round trip) so the compiler keeps emitting LDS/STS
@@ -147,8 +166,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
     float* sB2 = sLn + 4 * 128;                     // b2k, b2v
     uint64_t* bars = (uint64_t*)(sB2 + 2 * 128);
     uint32_t* tmem_slot = (uint32_t*)(bars + B_COUNT);
-    float* sPs = (float*)(smem + SM_FIXED);         // [(maxn-1)][260]
-    float* sX = sPs + (size_t)(a.maxn - 1) * PS_LD; // [2][maxn][4] ligand coordinates of the current / next unit
+    float* sPs = (float*)(smem + SM_FIXED);         // [min(maxn-1, 33)][260]
+    float* sX = sPs + (size_t)ps_rows(a.maxn) * PS_LD; // [2][maxn][4] ligand coordinates of the current / next unit
     const PlanDev& d = a.d;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wq = warp & 3;
@@ -188,8 +207,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
 
     TileIter it;
-    it.u = blockIdx.x;
-    iter_load_unit(d, it);
+    it.u = blockIdx.x; it.stage = 0;
+    iter_load_unit<MULTI>(d, it);
     if (!it.valid) {
         __syncthreads();
         if (warp == MMA_WARP) tc::tmem_dealloc<512>(tmem);
@@ -222,10 +241,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
         // unit's last tile is done, so the next unit's half is requested a whole phase before it is needed.
         auto load_ps = [&](const TileIter& t, int mlp) {
             uint64_t* bar = &bars[mlp == 0 ? B_PSK : B_PSV];
-            if (lane == 0) tc::mbar_arrive_expect_tx(bar, (uint32_t)(t.n - 1) * 512u);
+            // rows k -> j of chunk c: segment rows [32c, 32c+32) map to unit rows [32c, 32c+33) (the row k = i is skipped)
+            const int r0 = t.chunk * 32, nr = min(33, t.n - 1 - r0);
+            if (lane == 0) tc::mbar_arrive_expect_tx(bar, (uint32_t)nr * 512u);
             __syncwarp();
-            const float* src = a.P + (size_t)(t.eoff + (long long)t.jl * (t.n - 1)) * 256 + mlp * 128;
-            for (int r = lane; r < t.n - 1; r += 32) tc::bulk_copy_g2s(sPs + (size_t)r * PS_LD + mlp * 128, src + (size_t)r * 256, 512u, bar);
+            const float* src = a.P + (size_t)(t.eoff + (long long)t.jl * (t.n - 1) + r0) * 256 + mlp * 128;
+            for (int r = lane; r < nr; r += 32) tc::bulk_copy_g2s(sPs + (size_t)r * PS_LD + mlp * 128, src + (size_t)r * 256, 512u, bar);
         };
         // angle slice of the first Linear for one MLP of tile `tl` (operand buffer tl & 1) -> pre-activation columns `dcol`
         auto feat_mma = [&](int tl, int mlp, uint32_t dcol, uint64_t* bar) {
@@ -275,8 +296,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             const uint32_t preK = tmem + (ph ? 256 : 0), hidK = tmem + (ph ? 0 : 256);
             const uint32_t preV = tmem + (ph ? 384 : 128), hidV = tmem + (ph ? 128 : 384);
             TileIter nx = it;
-            iter_next(d, nx);
-            const bool newu = nx.valid && nx.u != it.u;
+            iter_next<MULTI>(d, nx);
+            const bool newu = nx.valid && nx.stage != it.stage;     // the staged P rows change with the next tile
             uint64_t* featbar = &bars[(tcount + 1) & 1 ? B_FEAT1 : B_FEAT0];
             TRACE(2, 0);
             tc::mbar_wait_wd(&bars[B_HIDK], ph);          // key activations of tile t are in TMEM; logits of tile t-1 are done
@@ -332,7 +353,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
         features(it, 0, 0);
         while (it.valid) {
             TileIter nx = it;
-            iter_next(d, nx);
+            iter_next<MULTI>(d, nx);
             // operand buffer (s+1)&1 was last read by the value-side angle MMA of tile s-1
             if (s >= 1) tc::mbar_wait_wd(&bars[(s - 1) & 1 ? B_PREV1 : B_PREV0], ((s - 1) >> 1) & 1);
             if (nx.valid) {
@@ -358,6 +379,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
         float al[4] = {0.f, 0.f, 0.f, 0.f};
         bool prev_valid = false;
         long long prev_eji = 0;
+        // MULTI: on-line softmax state of the open segment (warp-uniform: running maximum and sum per head, the factor
+        // the running output is rescaled by when the previous tile's chunk is added) and this lane's output channel
+        float mrun[4] = {0.f, 0.f, 0.f, 0.f}, lrun[4] = {0.f, 0.f, 0.f, 0.f}, psc[4] = {0.f, 0.f, 0.f, 0.f}, oacc = 0.f;
+        bool prev_first = true, prev_last = true;
         // pre-activation slice -> LayerNorm + ReLU -> bf16 hi/lo A operand of the second Linear
         auto layer_norm = [&](int mlp, uint32_t pre, uint32_t hid, int trow, const float* sR) {
             const int c0 = mlp * 128 + cq * 32;          // first of this thread's 32 channels inside the 256-wide (k|v) row
@@ -433,9 +458,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
                 v[i] = pr.x; v[i + 1] = pr.y;
             }
             const float o = transpose_reduce32(v, lane);
-            if (prev_valid) {
-                const int c = cq * 32 + lane;
-                a.hb[(size_t)prev_eji * 128 + c] += o + sB2[128 + c];     // sum(alpha) = 1; residual (uni_denoiser.py:285)
+            const int c = cq * 32 + lane;
+            if (!MULTI) {
+                if (prev_valid) a.hb[(size_t)prev_eji * 128 + c] += o + sB2[128 + c];     // sum(alpha) = 1; residual (uni_denoiser.py:285)
+            } else {
+                // channel c belongs to head cq*4 + (lane >> 3): rescale the running output by that head's factor, add the
+                // chunk, and divide by the running sum once the segment's last chunk is in
+                const int hs = lane >> 3;
+                const float sc = hs == 0 ? psc[0] : hs == 1 ? psc[1] : hs == 2 ? psc[2] : psc[3];
+                oacc = prev_first ? o : fmaf(oacc, sc, o);
+                if (prev_valid && prev_last) {
+                    const float l = hs == 0 ? lrun[0] : hs == 1 ? lrun[1] : hs == 2 ? lrun[2] : lrun[3];
+                    a.hb[(size_t)prev_eji * 128 + c] += __fdividef(oacc, l) + sB2[128 + c];
+                }
             }
         };
         while (it.valid) {
@@ -443,13 +478,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             const uint32_t preK = tmem + (ph ? 256 : 0), hidK = tmem + (ph ? 0 : 256);
             const uint32_t preV = tmem + (ph ? 384 : 128), hidV = tmem + (ph ? 128 : 384);
             const Seg sg = seg_of(it, wq);
-            const bool rowvalid = sg.valid && lane < it.n - 2;
-            const int trow = rowvalid ? lane + (lane >= sg.ti) : 0;
+            const int srow = it.chunk * 32 + lane;                  // row inside the segment
+            const bool rowvalid = sg.valid && srow < it.n - 2;
+            const int trow = rowvalid ? lane + (srow >= sg.ti) : 0;   // staged row: unit row (srow + skip of k = i) - 32 * chunk
             const float* sQ = sQR + (tcount & 1) * (SM_QR / 8);
             const float* sR = sQ + 4 * 128;
             TRACE(role, 0);
             // ---- key MLP
-            if (staged_k != it.u) { tc::mbar_wait(&bars[B_PSK], psk); psk ^= 1; staged_k = it.u; }   // P rows (key half) landed
+            if (staged_k != it.stage) { tc::mbar_wait(&bars[B_PSK], psk); psk ^= 1; staged_k = it.stage; }   // P rows (key half) landed
             tc::mbar_wait(&bars[B_PREK], ph);
             tc::tc_fence_after();
             TRACE(role, 1);
@@ -459,7 +495,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             if (tcount > 0) epilogue(ph ? 128 + tmem : 384 + tmem, ph ^ 1);
             TRACE(role, 4);
             // ---- value MLP
-            if (staged_v != it.u) { tc::mbar_wait(&bars[B_PSV], psv); psv ^= 1; staged_v = it.u; }
+            if (staged_v != it.stage) { tc::mbar_wait(&bars[B_PSV], psv); psv ^= 1; staged_v = it.stage; }
             tc::mbar_wait(&bars[ph ? B_PREV1 : B_PREV0], (tcount >> 1) & 1);
             tc::tc_fence_after();
             TRACE(role, 5);
@@ -487,7 +523,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
                     s0 = tc::add2(s0, s1);
                     al[h] = rowvalid ? (s0.x + s0.y) * kScale : -INFINITY;
                 }
-                if (!(a.flags & 1)) {
+                if (MULTI) {
+                    // on-line softmax across the chunks of the segment: weights stay un-normalised (relative to the running
+                    // maximum), the epilogue rescales the running output and divides by the running sum at the end
+                    const bool first = it.chunk == 0;
+#pragma unroll
+                    for (int h = 0; h < 4; h++) {
+                        const float mold = first ? -INFINITY : mrun[h];
+                        const float mnew = fmaxf(mold, tc::warp_max_redux(al[h]));
+                        al[h] = rowvalid ? tc::ex2_approx(al[h] - mnew) : 0.f;
+                        const float sc = mold == -INFINITY ? 0.f : tc::ex2_approx(mold - mnew);
+                        const float ls = tc::warp_sum01_redux(al[h]);
+                        lrun[h] = first ? ls : fmaf(lrun[h], sc, ls);
+                        mrun[h] = mnew; psc[h] = sc;
+                    }
+                } else if (!(a.flags & 1)) {
                     // segment softmax across the 32 lanes: max and sum on the REDUX unit
 #pragma unroll
                     for (int h = 0; h < 4; h++) {
@@ -516,7 +566,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             }
             TRACE(role, 8);
             prev_valid = sg.valid; prev_eji = sg.eji;
-            iter_next(d, it);
+            if (MULTI) { prev_first = it.chunk == 0; prev_last = it.chunk == it.nchunk - 1; }
+            iter_next<MULTI>(d, it);
             tcount++;
         }
         // drain: value epilogue of the last tile
@@ -609,16 +660,23 @@ int pg_launch_trip_pr(const TripTcArgs& a, cudaStream_t s) {
     return PG_OK;
 }
 
-size_t pg_trip_tc_smem(int maxn) { return (size_t)SM_FIXED + ((size_t)(maxn - 1) * PS_LD + 2 * (size_t)maxn * 4) * sizeof(float) + 1024; }
+size_t pg_trip_tc_smem(int maxn) { return (size_t)SM_FIXED + ((size_t)ps_rows(maxn) * PS_LD + 2 * (size_t)maxn * 4) * sizeof(float) + 1024; }
 
 int pg_launch_trip_tc(const TripTcArgs& a, int num_sms, cudaStream_t s) {
     if (a.d.Nl <= 0) return PG_OK;
     const size_t smem = pg_trip_tc_smem(a.maxn);
     if (smem > 227 * 1024) { pg_set_error("trip_tc: shared memory budget exceeded"); return PG_ELIMIT; }
     static size_t cur = 0;
-    if (smem > cur) { PG_CUDA_CHECK(cudaFuncSetAttribute(trip_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cur = smem; }
+    if (smem > cur) {
+        PG_CUDA_CHECK(cudaFuncSetAttribute(trip_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PG_CUDA_CHECK(cudaFuncSetAttribute(trip_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cur = smem;
+    }
     const unsigned grid = (unsigned)std::min<long long>(a.d.Nl, num_sms);
-    trip_tc_kernel<<<grid, NTHREADS, smem, s>>>(a);
+    // segments of every molecule fit one 32-row chunk (n - 2 <= 32): the single-chunk kernel; otherwise the chunked one
+    // serves the whole batch (molecules of either kind)
+    if (a.maxn <= PG_TRIP_TC_SINGLE_CHUNK_ATOMS) trip_tc_kernel<false><<<grid, NTHREADS, smem, s>>>(a);
+    else trip_tc_kernel<true><<<grid, NTHREADS, smem, s>>>(a);
     PG_LAUNCH_CHECK();
     return PG_OK;
 }

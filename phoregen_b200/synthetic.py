@@ -53,9 +53,11 @@ def synthetic_phore(rng, p, n_ex=0):
     return x, pos, nrm.astype(np.float32)
 
 
-def synthetic_batch(seed, n_graphs, n_atoms=30, p_choices=(6, 7, 8), n_ex=0, edge_order="sampling"):
+def synthetic_batch(seed, n_graphs, n_atoms=30, p_choices=(6, 7, 8), n_ex=0, edge_order="sampling", pos_scale=1.0):
     """Seeded synthetic ligand+pharmacophore batch in the reference's tensor layout (config[1] shapes).
-    n_atoms: int or (lo, hi) inclusive range."""
+    n_atoms: int or (lo, hi) inclusive range.  Ligand coordinates are N(0, 1) * pos_scale (the reference's initial state is
+    N(0, 1); large molecules are spread by pos_scale > 1 in the parity fixtures so that 80 atoms are not packed into a
+    unit ball, where near-ties of the k=32 neighbour selection are unavoidable)."""
     rng = np.random.default_rng(seed)
     if isinstance(n_atoms, int):
         na = np.full(n_graphs, n_atoms)
@@ -74,6 +76,8 @@ def synthetic_batch(seed, n_graphs, n_atoms=30, p_choices=(6, 7, 8), n_ex=0, edg
     node_cls = torch.from_numpy(rng.integers(0, 12, size=Nl).astype(np.int64))
     edge_cls = torch.from_numpy(rng.integers(0, 6, size=ei.shape[1]).astype(np.int64))
     pos = torch.from_numpy(rng.normal(0.0, 1.0, size=(Nl, 3)).astype(np.float32))
+    if pos_scale != 1.0:
+        pos = pos * pos_scale
     return dict(num_atoms=torch.from_numpy(na.astype(np.int64)), batch_node=batch_node, edge_index=ei,
                 batch_edge=eb, h_node=F.one_hot(node_cls, 12).float(), h_edge=F.one_hot(edge_cls, 6).float(),
                 pos=pos, phore=phore, n_graphs=n_graphs)

@@ -155,6 +155,50 @@ def test_forward_matches_oracle(model, dev, seed, n_graphs, n_atoms, n_ex):
         assert_close(g, w, what)
 
 
+# ---------------------------------------------------------------- molecules beyond one 32-row attention chunk
+@pytest.mark.parametrize("case", ["n35", "n48", "n64", "n78", "n80", "ragged20_40"])
+def test_forward_big_molecules_match_reference_golden(model, dev, case):
+    """n-2 > 32 (triplet segments) / n-1 > 32 (bond segments): chunked segments with the on-line / cross-quarter softmax of
+    trip_tc_kernel<true> and bond_tc_kernel<*, true>; outputs of the unmodified reference (oracle/make_golden.py big)."""
+    m, _ = model
+    from phoregen_b200.testing import state_dict_digest
+    big = load_golden("forward_big.pt")
+    f = big["cases"][case]
+    b = O.synthetic_batch(f["seed"], f["n_graphs"], n_atoms=f["n_atoms"], p_choices=f["p_choices"], pos_scale=f["pos_scale"])
+    got = _forward(m, b, f["times"], dev)
+    assert_close(got[0], f["pred_node"], "logits_node")
+    assert_close(got[1], f["pred_pos"], "pos")
+    assert_close(got[2], f["pred_edge"], "logits_edge")
+
+
+def test_forward_mixed_chunk_batch_equals_single_molecule_runs(model, dev):
+    """A batch mixing 1-, 2- and 3-chunk molecules takes the chunked kernels for every molecule; each molecule's outputs
+    must equal (bit for bit: per-molecule arithmetic is batch-independent) the ones it gets alone, where the small ones
+    run on the single-chunk kernels only up to the softmax normalisation order -> tolerance for those."""
+    m, _ = model
+    b = O.synthetic_batch(311, 4, n_atoms=(12, 70), p_choices=(6, 9), pos_scale=2.0)
+    na = b["num_atoms"].tolist()
+    assert max(na) > 34 and min(na) <= 33
+    times = [900, 400, 50, 0]
+    got = _forward(m, b, times, dev)
+    ph = b["phore"]
+    eoff = np.concatenate([[0], np.cumsum([n * (n - 1) for n in na])])
+    aoff = np.concatenate([[0], np.cumsum(na)])
+    # reference-order edges are molecule-major (utils/sample_utils.py:40-54)
+    for g in range(4):
+        sel_a = slice(int(aoff[g]), int(aoff[g + 1]))
+        sel_e = slice(int(eoff[g]), int(eoff[g + 1]))
+        pm = ph["batch"] == g
+        one = dict(h_node=b["h_node"][sel_a], pos=b["pos"][sel_a], batch_node=torch.zeros(na[g], dtype=torch.long),
+                   h_edge=b["h_edge"][sel_e], edge_index=b["edge_index"][:, sel_e] - int(aoff[g]),
+                   batch_edge=torch.zeros(na[g] * (na[g] - 1), dtype=torch.long),
+                   phore=dict(x=ph["x"][pm], pos=ph["pos"][pm], norm=ph["norm"][pm], batch=torch.zeros(int(pm.sum()), dtype=torch.long)))
+        alone = _forward(m, one, [times[g]], dev)
+        assert_close(got[0][sel_a], alone[0], f"molecule {g} logits_node", rtol=2e-4, atol=2e-5)
+        assert_close(got[1][sel_a], alone[1], f"molecule {g} pos", rtol=2e-4, atol=2e-5)
+        assert_close(got[2][sel_e], alone[2], f"molecule {g} logits_edge", rtol=2e-4, atol=2e-5)
+
+
 def test_forward_training_edge_order(model, dev):
     """dst-major f_edge_index (datasets/transform.py:488-501) gives the same per-edge logits as the sampling order."""
     m, sd = model
@@ -457,15 +501,14 @@ def test_tensor_core_kernels_match_fp32_kernels(tmp_path):
 
 # ---------------------------------------------------------------- liveness of the persistent, mbarrier-pipelined kernels
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("seed", [1, 7])
-def test_many_tiles_per_cta_eager_steps_terminate_and_match_graph_replay(model, dev, seed):
+@pytest.mark.parametrize("seed,G,n_atoms", [(1, 320, (26, 33)), (7, 320, (26, 33)), (3, 160, (30, 50)), (5, 48, (60, 80))])
+def test_many_tiles_per_cta_eager_steps_terminate_and_match_graph_replay(model, dev, seed, G, n_atoms):
     """The tcgen05 kernels are persistent: at this size every CTA walks several tiles, which exercises the cross-tile
     hand-offs (a wrong mbarrier parity wait shows up as a hang, not as a wrong number).  Eager and CUDA-graph replays of
     the same trajectory must agree bit for bit."""
     from phoregen_b200.diffusion import TrajectorySampler
     m, _ = model
-    G = 320
-    b = O.synthetic_batch(2032 + seed, G, n_atoms=(26, 33))
+    b = O.synthetic_batch(2032 + seed, G, n_atoms=n_atoms)      # (30, 50) / (60, 80): the chunked-segment kernels
     outs = []
     for graph in (False, True):
         s = TrajectorySampler(m, None, G, dev, ligand_num_atoms=b["num_atoms"], save_traj=False, seed=seed, use_cuda_graph=graph,
