@@ -207,7 +207,9 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    smp.run(K)
+    K = smp.run(K)            # steps actually executed (the sampler stops at the end of the 1000-step trajectory)
+    if K <= 0:
+        raise SystemExit("bench.py: --warmup + --steps exceed the 1000-step trajectory")
     gathered = None
     if world > 1:
         local = pack_results(smp.pos + smp.center, smp.node_cls, smp.edge_cls, smp.num_atoms)

@@ -127,12 +127,23 @@ int pg_position_step(int rows, const float* d_x_t, const float* d_x_recon, const
                      const float* d_coef_x0, const float* d_coef_xt, const float* d_std,
                      const int64_t* d_time_step, const int32_t* d_row_graph, const float* d_normal, uint64_t seed,
                      uint32_t stream_id, const int64_t* d_step_counter, float* d_x_prev,
-                     float* d_traj_pos /*[T+1,rows,3] or NULL*/, const float* d_center /*[3] or NULL*/, void* stream);
+                     float* d_traj_pos /*[T+1,rows,3] or NULL*/, const float* d_center /*[3], [G,3] or NULL*/,
+                     int center_per_graph /*1: d_center holds one centre per graph (multi-pharmacophore batches)*/, void* stream);
 /* T5: closed-form gradient of the guidance energies (utils/sample_utils.py:135-165; diffusion.py:476-502).
- * flags bit0 = atom_prox(min_d,max_d), bit1 = center_prox(d_phore_center[3]).  d_edge_cls: sampled classes,
- * reference edge order.  Output d_grad [Nl,3] (overwritten). */
+ * flags bit0 = atom_prox(min_d,max_d), bit1 = center_prox(d_phore_center), bit2 = add onto d_grad instead of overwriting
+ * it (the reference sums one gradient per pos_guidance_opt entry: diffusion.py:479-501), bit3 = d_phore_center is [G,3]
+ * (one pharmacophore per graph) instead of [3].  d_edge_cls: sampled classes, reference edge order.  Output d_grad [Nl,3]. */
 int pg_guidance_grad(const PgPlan* p, const float* d_pos, const int32_t* d_edge_cls, int flags, float min_d,
                      float max_d, const float* d_phore_center, float* d_grad, void* stream);
+
+/* O2 / D2: atom-count heads (reference models/diffusion.py:148-163 `predict_atom_count`, and the interval of
+ * `sample_nodes` :374-380).  d_h_phore_emb [P,128] is pg_phore_encode's output, d_h_phore [P,18] the raw features
+ * (column ex_col == 1 marks exclusion spheres: 12 for zinc_300 / pdbbind, else 10).  Outputs per graph: count_l, count_u
+ * [G] f32 and, if d_lo / d_hi are given, round(count * (max_atom - min_atom) + min_atom) as int32 (round half to even,
+ * like torch.round). */
+int pg_atom_count(const PgModel* m, PgPlan* p, const float* d_h_phore_emb, const float* d_h_phore, int ex_col,
+                  float min_atom, float max_atom, float* d_count_l, float* d_count_u, int32_t* d_lo, int32_t* d_hi,
+                  void* stream);
 
 /* ---------------------------------------------------------------- M1 building block: K = 128 contraction
  * C[M, 128*ntiles128] = pro(A)[M,128] @ W + bias (+ resid): the Linear layers of models/common.py:99-119 after the

@@ -464,7 +464,7 @@ def guidance_grad(pos, batch_node, edge_cls, edge_index, batch_edge, opts, phore
         elif drift["type"] == "center_prox":
             n = seg_sum(torch.ones(pos.shape[0]), batch_node, n_graphs)
             c = seg_sum(pos, batch_node, n_graphs) / n.unsqueeze(-1)
-            diff = c - phore_center.view(1, 3)
+            diff = c - phore_center.view(-1, 3)      # [1,3]: the reference's single pharmacophore; [G,3]: one per graph
             nr = diff.norm(dim=-1, keepdim=True)
             u = diff / nr.clamp(min=1e-30)
             g = g + (u / n.unsqueeze(-1) / n_graphs)[batch_node]
@@ -481,6 +481,16 @@ def init_log_prob(kind, K):
         p = np.ones(K)
     p = p / p.sum()
     return torch.log(torch.from_numpy(p) + 1e-30).clamp_min(-32.0)
+
+
+def sample_init(init_prob, uniform):
+    """models/transition.py:331-339 (`sample_init` of GeneralCategoricalTransition) with the uniform draw supplied:
+    log prior broadcast to every row, Gumbel arg-max (common.py:425-431), log one-hot of the drawn class
+    (common.py:398-402).  -> (classes [rows], log one-hot [rows,K])."""
+    K = uniform.shape[1]
+    logp = torch.log(torch.as_tensor(init_prob) + 1e-30).clamp_min(-32.0).float().unsqueeze(0).expand(uniform.shape[0], K)
+    cls = log_sample_categorical(logp, uniform)
+    return cls, torch.log(F.one_hot(cls, K).float().clamp(min=1e-30))
 
 
 def reverse_step(sd, state, t_scalar, topo, phore, draws, guidance=None):

@@ -49,7 +49,8 @@ _SIGS = {
     "pg_phore_encode": (c_int, [_P] * 6),
     "pg_phorediff_forward": (c_int, [_P] * 13),
     "pg_categorical_step": (c_int, [c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_uint64, c_uint32, _P, _P, _P, _P, _P]),
-    "pg_position_step": (c_int, [c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_uint64, c_uint32, _P, _P, _P, _P, _P]),
+    "pg_position_step": (c_int, [c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_uint64, c_uint32, _P, _P, _P, _P, c_int, _P]),
+    "pg_atom_count": (c_int, [_P, _P, _P, _P, c_int, c_float, c_float, _P, _P, _P, _P, _P]),
     "pg_guidance_grad": (c_int, [_P, _P, _P, c_int, c_float, c_float, _P, _P, _P]),
     "pg_gemm_k128": (c_int, [c_int, c_int, c_int64, _P, c_int64, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, c_int, _P]),
     "pg_plan_ligand_graph": (_P, [_P]),

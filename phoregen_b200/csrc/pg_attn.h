@@ -50,6 +50,8 @@ struct BondTcArgs {
     const float* q;
     AttnW w;
     const uint16_t *w2k_bf, *w2v_bf;       // [hi|lo][128][128] and [hi|lo][128 | 16][128] bf16, K-major
+    const uint16_t* w2k_h;                 // [128][128] fp16, K-major (single-pass key MLP)
+    int key_bf16x3;                        // 1: key MLP in bf16x3 (PG_KEY=bf16x3, A/B only)
     float* out;
 };
 // tcgen05 version of the kNN-graph attention (pg_knn_tc.cu): key pass + value pass
@@ -63,6 +65,8 @@ struct KnnTcArgs {
     const float* q;          // [N,128]
     AttnW w;
     const uint16_t *w2k_bf, *w2v_bf;       // [hi|lo][128][128] and [hi|lo][128 | 16][128] bf16, K-major
+    const uint16_t* w2k_h;                 // [128][128] fp16, K-major (single-pass key MLP)
+    int key_bf16x3;                        // 1: key MLP in bf16x3 (PG_KEY=bf16x3, A/B only)
     const uint16_t *tabk_bf, *tabv_bf;     // [hi|lo][128][96] bf16: first-Linear slices of the 4 edge types x 24 features
     float* alpha;            // scratch [Ek,16]: softmax weights times e_w
     float* alpha_sum;        // scratch [N,16]: their per-head sums
@@ -97,8 +101,9 @@ struct TripTcArgs {
     float* P;                              // [Eb,256] work space: per-edge partial of the first Linear (k->j role)
     const float *wrkj, *wrji;              // [20][256] fp32
     const uint16_t *w2k_bf, *w2v_bf;       // [hi|lo][128][128] bf16, K-major
+    const uint16_t* w2k_h;                 // [128][128] fp16, K-major: the key MLP's second Linear at single precision-16
     const uint16_t* wa_bf;                 // [hi|lo][256][16] bf16 (angle slice, 13 used)
-    int flags;                             // experiment switches (PG_TRIP_FLAGS): bit 0 = shuffle-butterfly softmax instead of REDUX
+    int flags;                             // switches (PG_TRIP_FLAGS): bit 0 = shuffle-butterfly softmax instead of REDUX; bit 1 = key MLP in bf16x3
     const float *lnk_g, *lnk_b, *lnv_g, *lnv_b, *b2k, *b2v;
     const float *lnk_bf, *lnv_bf, *fold;   // beta (/ gamma where folded into the W2 images), fold flags (see AttnW)
     float* hb;

@@ -75,7 +75,8 @@ __device__ __forceinline__ SegInfo seg_info(const PlanDev& d, long long tile, in
     return s;
 }
 
-template <int POS, bool MULTI>
+// KF16: the key MLP's second Linear as a single-pass fp16 contraction (8 MMAs; pg_trip_tc.cu explains the error budget)
+template <int POS, bool MULTI, bool KF16>
 __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -106,8 +107,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
     for (int idx = tid; idx < 4 * 128 * 16; idx += NTHREADS) {
         const int mat = idx >> 11, n = (idx >> 4) & 127, c = idx & 15;
         const bool isv = mat >> 1;
-        if (isv && n >= NV) continue;
-        const uint16_t* src = (isv ? a.w2v_bf : a.w2k_bf) + ((size_t)(mat & 1) * (isv ? NV : 128) + n) * 128 + c * 8;
+        if ((isv && n >= NV) || (KF16 && mat == 1)) continue;
+        const uint16_t* src = (isv ? a.w2v_bf : (KF16 ? a.w2k_h : a.w2k_bf)) + ((size_t)(mat & 1) * (isv ? NV : 128) + n) * 128 + c * 8;
         const uint32_t dst = tc::smem_u32(sW) + mat * W_TILE + (c >> 3) * 16384 + tc::sw128_chunk(n, c & 7);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
     }
@@ -138,7 +139,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
                 for (int mlp = 0; mlp < 2; mlp++) {
                     tc::mbar_wait_wd(&bars[mlp == 0 ? B_HIDK : B_HIDV], ph);
                     tc::tc_fence_after();
-                    if (lane == 0) {
+                    if (lane == 0 && KF16 && mlp == 0) {
+                        constexpr uint32_t idesc16 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // A, B = F16
+#pragma unroll
+                        for (int ks = 0; ks < 8; ks++) {
+                            const uint64_t bd = tc::umma_desc_sw128(sW_u32 + (ks >> 2) * 16384 + (ks & 3) * 32);
+                            tc::umma_bf16_ts(tmem + C_OUTK, tmem + C_HIDK + ks * 8, bd, idesc16, ks > 0);
+                        }
+                        tc::umma_commit(&bars[B_OUTK]);
+                    } else if (lane == 0) {
                         const uint32_t hid = tmem + (mlp == 0 ? C_HIDK : C_HIDV);
                         const uint32_t dcol = tmem + (mlp == 0 ? C_OUTK : C_OUTV);
                         uint32_t acc = 0;
@@ -256,6 +265,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
             const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mu * rstd, -mu * rstd);
             const float* gam = sLn + mlp * 256 + cq * 32;
             const float* bet = gam + 128;
+            if (KF16 && mlp == 0) {
+                // key MLP: one fp16 value per activation (its output only feeds the softmax logits; see pg_trip_tc.cu)
+                uint32_t hh[16];
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    const float4 b4 = ld4(bet + 2 * i);
+                    float2 y0 = tc::fma2(x2[i], rs2, nm2), y1 = tc::fma2(x2[i + 1], rs2, nm2);
+                    if (fold[0]) {
+                        y0 = tc::add2(y0, make_float2(b4.x, b4.y)); y1 = tc::add2(y1, make_float2(b4.z, b4.w));
+                    } else {
+                        const float4 g4 = ld4(gam + 2 * i);
+                        y0 = tc::fma2(y0, make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
+                        y1 = tc::fma2(y1, make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
+                    }
+                    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(hh[i]) : "f"(y0.y), "f"(y0.x));
+                    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(hh[i + 1]) : "f"(y1.y), "f"(y1.x));
+                }
+                tc::tmem_st16(hid + lane_base + cq * 16, hh);
+                tc::tmem_st_wait();
+                tc::tc_fence_before();
+                tc::mbar_arrive(&bars[B_HIDK]);
+                return;
+            }
             uint32_t hi[16], lo[16];
             if (fold[mlp]) {
                 // gamma > 0 everywhere: it lives in the columns of W2, only beta / gamma is added here (half the broadcast loads)
@@ -437,10 +469,10 @@ int pg_launch_bond_tc(const BondTcArgs& a, int pos, int num_sms, cudaStream_t s)
     if (a.d.Nl <= 0) return PG_OK;
     static bool init = false;
     if (!init) {
-        PG_CUDA_CHECK(cudaFuncSetAttribute(bond_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-        PG_CUDA_CHECK(cudaFuncSetAttribute(bond_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-        PG_CUDA_CHECK(cudaFuncSetAttribute(bond_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-        PG_CUDA_CHECK(cudaFuncSetAttribute(bond_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+#define PG_BOND_ATTR(P, M, K) PG_CUDA_CHECK(cudaFuncSetAttribute(bond_tc_kernel<P, M, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL))
+        PG_BOND_ATTR(0, false, false); PG_BOND_ATTR(1, false, false); PG_BOND_ATTR(0, true, false); PG_BOND_ATTR(1, true, false);
+        PG_BOND_ATTR(0, false, true); PG_BOND_ATTR(1, false, true); PG_BOND_ATTR(0, true, true); PG_BOND_ATTR(1, true, true);
+#undef PG_BOND_ATTR
         init = true;
     }
     // every segment fits one lane quarter (n-1 <= 32): atoms packed four to a tile across the batch; otherwise the
@@ -448,13 +480,15 @@ int pg_launch_bond_tc(const BondTcArgs& a, int pos, int num_sms, cudaStream_t s)
     const bool multi = a.d.max_n - 1 > PG_BOND_TC_SINGLE_CHUNK_ROWS;
     const long long ntiles = multi ? a.d.nbt : (a.d.Nl + 3) / 4;
     const unsigned grid = (unsigned)std::min<long long>(ntiles, num_sms);
-    if (!multi) {
-        if (pos == 0) bond_tc_kernel<0, false><<<grid, NTHREADS, SM_TOTAL, s>>>(a);
-        else bond_tc_kernel<1, false><<<grid, NTHREADS, SM_TOTAL, s>>>(a);
+#define PG_BOND_GO(P, M, K) bond_tc_kernel<P, M, K><<<grid, NTHREADS, SM_TOTAL, s>>>(a)
+    if (a.key_bf16x3) {
+        if (!multi) { if (pos == 0) PG_BOND_GO(0, false, false); else PG_BOND_GO(1, false, false); }
+        else { if (pos == 0) PG_BOND_GO(0, true, false); else PG_BOND_GO(1, true, false); }
     } else {
-        if (pos == 0) bond_tc_kernel<0, true><<<grid, NTHREADS, SM_TOTAL, s>>>(a);
-        else bond_tc_kernel<1, true><<<grid, NTHREADS, SM_TOTAL, s>>>(a);
+        if (!multi) { if (pos == 0) PG_BOND_GO(0, false, true); else PG_BOND_GO(1, false, true); }
+        else { if (pos == 0) PG_BOND_GO(0, true, true); else PG_BOND_GO(1, true, true); }
     }
+#undef PG_BOND_GO
     PG_LAUNCH_CHECK();
     return PG_OK;
 }

@@ -70,7 +70,8 @@ __device__ __forceinline__ KSeg kseg(const PlanDev& d, long long tile, int wq) {
     return s;
 }
 
-template <int PASS, int POS>
+// KF16 (key pass only): the second Linear as a single-pass fp16 contraction (8 MMAs; pg_trip_tc.cu explains the error budget)
+template <int PASS, int POS, bool KF16>
 __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -98,10 +99,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
     }
     // ---- resident operands of this pass
     {
-        const uint16_t* w2 = PASS == 0 ? a.w2k_bf : a.w2v_bf;
+        const uint16_t* w2 = PASS == 0 ? (KF16 ? a.w2k_h : a.w2k_bf) : a.w2v_bf;
         for (int idx = tid; idx < 2 * 128 * 16; idx += NTHREADS) {        // [part 2][n][chunk 16] -> 128B-swizzled K-major
             const int part = idx >> 11, n = (idx >> 4) & 127, c = idx & 15;
-            if (n >= NOUT) continue;
+            if (n >= NOUT || (KF16 && part == 1)) continue;
             const uint16_t* src = w2 + ((size_t)part * NOUT + n) * 128 + c * 8;
             const uint32_t dst = tc::smem_u32(sW) + part * W_TILE + (c >> 3) * 16384 + tc::sw128_chunk(n, c & 7);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -232,7 +233,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
                 tc::mbar_wait_wd(&bars[B_HID], ph);
                 KTRACE(1, 3);
                 tc::tc_fence_after();
-                if (lane == 0) {
+                if (lane == 0 && KF16) {
+                    constexpr uint32_t idesc16 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // A, B = F16
+#pragma unroll
+                    for (int ks = 0; ks < 8; ks++) {
+                        const uint64_t bd = tc::umma_desc_sw128(sW_u32 + (ks >> 2) * 16384 + (ks & 3) * 32);
+                        tc::umma_bf16_ts(tmem + C_OUT + ph * 128, tmem + C_HID + ks * 8, bd, idesc16, ks > 0);
+                    }
+                    tc::umma_commit(&bars[B_OUT]);
+                } else if (lane == 0) {
                     const uint32_t dcol = tmem + C_OUT + ph * 128;
                     uint32_t acc = 0;
 #pragma unroll
@@ -472,6 +481,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
             const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mu * rstd, -mu * rstd);
             const float* gam = sLn + cq * 32;
             const float* bet = gam + 128;
+            if (KF16) {
+                // key MLP: one fp16 value per activation (its output only feeds the softmax logits; see pg_trip_tc.cu)
+                uint32_t hh[16];
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    const float4 b4 = ld4(bet + 2 * i);
+                    float2 y0 = tc::fma2(x2[i], rs2, nm2), y1 = tc::fma2(x2[i + 1], rs2, nm2);
+                    if (fold) {
+                        y0 = tc::add2(y0, make_float2(b4.x, b4.y)); y1 = tc::add2(y1, make_float2(b4.z, b4.w));
+                    } else {
+                        const float4 g4 = ld4(gam + 2 * i);
+                        y0 = tc::fma2(y0, make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
+                        y1 = tc::fma2(y1, make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
+                    }
+                    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(hh[i]) : "f"(y0.y), "f"(y0.x));
+                    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(hh[i + 1]) : "f"(y1.y), "f"(y1.x));
+                }
+                if (any) tc::mbar_wait(&bars[B_OUT], ph ^ 1);
+                tc::tc_fence_after();
+                tc::tmem_st16(tmem + C_HID + lane_base + cq * 16, hh);
+            } else {
             uint32_t hi[16], lo[16];
             if (fold) {
                 // gamma > 0 everywhere: it lives in the columns of W2, only beta / gamma is added here (half the broadcast loads)
@@ -496,6 +526,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
             tc::tc_fence_after();
             tc::tmem_st16(tmem + C_HID + lane_base + cq * 16, hi);
             tc::tmem_st16(tmem + C_HID + lane_base + 64 + cq * 16, lo);
+            }
             tc::tmem_st_wait();
             tc::tc_fence_before();
             tc::mbar_arrive(&bars[B_HID]);
@@ -527,17 +558,19 @@ int pg_launch_knn_tc(const KnnTcArgs& a, int pos, int num_sms, cudaStream_t s) {
     if (a.d.N <= 0) return PG_OK;
     static bool init = false;
     if (!init) {
-        PG_CUDA_CHECK(cudaFuncSetAttribute(knn_tc_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-        PG_CUDA_CHECK(cudaFuncSetAttribute(knn_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-        PG_CUDA_CHECK(cudaFuncSetAttribute(knn_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        PG_CUDA_CHECK((cudaFuncSetAttribute(knn_tc_kernel<0, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)));
+        PG_CUDA_CHECK((cudaFuncSetAttribute(knn_tc_kernel<0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)));
+        PG_CUDA_CHECK((cudaFuncSetAttribute(knn_tc_kernel<1, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)));
+        PG_CUDA_CHECK((cudaFuncSetAttribute(knn_tc_kernel<1, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL)));
         init = true;
     }
     const long long ntiles = (a.d.N + 3) / 4;
     const unsigned grid = (unsigned)std::min<long long>(ntiles, num_sms);
-    knn_tc_kernel<0, 0><<<grid, NTHREADS, SM_TOTAL, s>>>(a);          // key pass: alpha * e_w -> scratch
+    if (a.key_bf16x3) knn_tc_kernel<0, 0, false><<<grid, NTHREADS, SM_TOTAL, s>>>(a);          // key pass: alpha * e_w -> scratch
+    else knn_tc_kernel<0, 0, true><<<grid, NTHREADS, SM_TOTAL, s>>>(a);
     PG_LAUNCH_CHECK();
-    if (pos == 0) knn_tc_kernel<1, 0><<<grid, NTHREADS, SM_TOTAL, s>>>(a);
-    else knn_tc_kernel<1, 1><<<grid, NTHREADS, SM_TOTAL, s>>>(a);
+    if (pos == 0) knn_tc_kernel<1, 0, false><<<grid, NTHREADS, SM_TOTAL, s>>>(a);
+    else knn_tc_kernel<1, 1, false><<<grid, NTHREADS, SM_TOTAL, s>>>(a);
     PG_LAUNCH_CHECK();
     return PG_OK;
 }

@@ -35,6 +35,10 @@ std::vector<PgSlotDesc> build_slots() {
     add("G.ew.w1t", 20 * 128); add("G.ew.b1", 128); add("G.ew.ln_g", 128); add("G.ew.ln_b", 128);
     add("G.ew.w2", 128); add("G.ew.b2", 4);
     add("G.vinf.w1t", 128 * 128); add("G.vinf.w1t.bf", 128 * 128); add("G.vinf.b1", 128); add("G.vinf.w2", 12 * 128); add("G.vinf.b2", 12);
+    for (int c = 0; c < 2; c++) {     // atom-count heads atom_mlp / atom_mlp_1 (diffusion.py:77-88)
+        const std::string C = "G.cnt" + std::to_string(c) + ".";
+        add(C + "w1t", 128 * 256); add(C + "b1", 256); add(C + "w2", 256); add(C + "b2", 4);
+    }
     add("G.binf.w1t", 128 * 128); add("G.binf.w1t.bf", 128 * 128); add("G.binf.b1", 128); add("G.binf.w2", 6 * 128); add("G.binf.b2", 8);
     for (int l = 0; l < PG_NUM_LAYERS; l++) {
         std::string L = "L" + std::to_string(l) + ".";
@@ -53,6 +57,7 @@ std::vector<PgSlotDesc> build_slots() {
             add(S + "w2v", (pos ? 16 : 128) * 128); add(S + "b2v", pos ? 16 : 128);
             if (s == 0 || s == 3) { add(S + "tab_k", 4 * 24 * 128); add(S + "tab_v", 4 * 24 * 128); }
             if (s != 2) { add(S + "w2k.bf", 128 * 128); add(S + "w2v.bf", (pos ? 16 : 128) * 128); }   // bond_tc / knn_tc
+            add(S + "w2k.h", 128 * 64);                                                                 // key second Linear as fp16
             if (s == 0 || s == 3) { add(S + "tab_k.bf", 96 * 128); add(S + "tab_v.bf", 96 * 128); }
             if (s == 2) {
                 add(S + "wrkj", 20 * 256); add(S + "wrji", 20 * 256); add(S + "wa", 13 * 256);
@@ -283,6 +288,16 @@ bool use_tc_trip(const PlanDev& d) {
     return v == 1 && d.max_n >= 3;
 }
 
+// Precision of the key MLPs' second Linear (its output only feeds softmax logits).  Default bf16x3 everywhere.  Opt-in
+// single-pass fp16 (measured, configs[1]): PG_KEY=trip16 (triplet kernel only) 71.8 -> 67.1 ms/step, model outputs at
+// 0.50 x tolerance but the internal h_bond at 1.07 x; PG_KEY=fp16 (all three attention kernels) 65.4 ms/step, outputs at
+// 0.72 x, internal h / h_bond at 1.36 x / 1.20 x.  Not the default because of the internal-state bar.
+int key_mode() {      // 0 bf16x3 everywhere, 2 fp16 everywhere, 3 fp16 in the triplet kernel only
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PG_KEY"); v = !e ? 0 : !strcmp(e, "fp16") ? 2 : !strcmp(e, "trip16") ? 3 : 0; }
+    return v;
+}
+
 // tcgen05 bond-graph attention unless PG_BOND=fp32 (the FFMA reference kernel, A/B validation only)
 bool use_tc_bond() {
     static int v = -1;
@@ -298,6 +313,7 @@ int launch_bond(PgPlan* p, const BondAttnArgs& a0, const W& w, const std::string
         BondTcArgs t;
         t.d = a.d; t.x = a.x; t.nc = a.nc; t.B = a.B; t.ldb = a.ldb; t.b_k = a.b_k; t.b_v = a.b_v; t.q = a.q; t.w = a.w;
         t.w2k_bf = (const uint16_t*)w(S + "w2k.bf"); t.w2v_bf = (const uint16_t*)w(S + "w2v.bf"); t.out = a.out;
+        t.w2k_h = (const uint16_t*)w(S + "w2k.h"); t.key_bf16x3 = key_mode() != 2;
         PG_TRY(pg_launch_bond_tc(t, pos, num_sms(), s));
         p->launches++;
         return PG_OK;       // every atom has 1 <= n-1 <= 127 incoming edges (pg_plan_create): all segments ran there
@@ -321,6 +337,7 @@ int launch_knn_attn(PgPlan* p, const KnnAttnArgs& a, const W& w, const std::stri
         t.d = a.d; t.x = a.x; t.comb = a.comb; t.knn_src = a.knn_src; t.ew = a.ew; t.nc = a.nc; t.q = a.q; t.w = a.w;
         t.w2k_bf = (const uint16_t*)w(S + "w2k.bf"); t.w2v_bf = (const uint16_t*)w(S + "w2v.bf");
         t.tabk_bf = (const uint16_t*)w(S + "tab_k.bf"); t.tabv_bf = (const uint16_t*)w(S + "tab_v.bf");
+        t.w2k_h = (const uint16_t*)w(S + "w2k.h"); t.key_bf16x3 = key_mode() != 2;
         t.alpha = p->abuf; t.alpha_sum = p->abuf + (size_t)a.d.Ek * 16; t.out = a.out;
         PG_TRY(pg_launch_knn_tc(t, pos, num_sms(), s));
         p->launches += 2;
@@ -426,8 +443,9 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
                 t.hk_k = a.hk_k; t.hj_k = a.hj_k; t.hk_v = a.hk_v; t.hj_v = a.hj_v; t.q = p->qt; t.R = p->rbuf; t.P = p->pbuf2;
                 t.wrkj = a.wrkj; t.wrji = a.wrji;
                 t.w2k_bf = (const uint16_t*)w(L + "tr.w2k.bf"); t.w2v_bf = (const uint16_t*)w(L + "tr.w2v.bf");
+                t.w2k_h = (const uint16_t*)w(L + "tr.w2k.h");
                 t.wa_bf = (const uint16_t*)w(L + "tr.wa.bf");
-                { static int fl = -1; if (fl < 0) { const char* e = getenv("PG_TRIP_FLAGS"); fl = e ? atoi(e) : 0; } t.flags = fl; }
+                { static int fl = -1; if (fl < 0) { const char* e = getenv("PG_TRIP_FLAGS"); fl = e ? atoi(e) : 0; } t.flags = fl | (key_mode() >= 2 ? 0 : 2); }       // bit 1 set = bf16x3 key MLP
                 t.lnk_g = a.w.lnk_g; t.lnk_b = a.w.lnk_b; t.lnv_g = a.w.lnv_g; t.lnv_b = a.w.lnv_b; t.b2k = a.w.b2k; t.b2v = a.w.b2v;
                 t.lnk_bf = a.w.lnk_bf; t.lnv_bf = a.w.lnv_bf; t.fold = a.w.fold;
                 t.hb = p->hb; t.maxn = d.max_n;
@@ -532,6 +550,69 @@ extern "C" int pg_phorediff_forward(const PgModel* m, PgPlan* p, const float* d_
     head_out_kernel<PG_EDGE_CLASSES, 1><<<(unsigned)((d.Eb + 7) / 8), 256, 0, s>>>(d, p->qt, w("G.binf.w2"), w("G.binf.b2"),
                                                                                    d_logits_edge, nullptr, nullptr);
     PG_LAUNCH_CHECK(); p->launches++;
+    return PG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ O2 / D2: atom-count heads
+// predict_atom_count (diffusion.py:148-163): count = mean_g sigmoid(atom_mlp(h_p)); count_l = mean over the non-EX nodes of
+// sigmoid(atom_mlp_1(h_p)); count_u = count_l + relu(count - count_l).  One CTA per graph, thread = hidden unit of the
+// 128 -> 256 -> 1 heads, nodes of the graph in order (deterministic sums).  Also emits the integer interval of
+// sample_nodes (diffusion.py:379-380): round-half-even(c * (max_atom - min_atom) + min_atom).
+namespace {
+__global__ void __launch_bounds__(256) atom_count_kernel(PlanDev d, const float* __restrict__ hp, const float* __restrict__ xph,
+                                                         int ex_col, const float* __restrict__ w1t0, const float* __restrict__ b10,
+                                                         const float* __restrict__ w20, const float* __restrict__ b20,
+                                                         const float* __restrict__ w1t1, const float* __restrict__ b11,
+                                                         const float* __restrict__ w21, const float* __restrict__ b21,
+                                                         float min_atom, float max_atom, float* __restrict__ cl, float* __restrict__ cu,
+                                                         int* __restrict__ lo, int* __restrict__ hi) {
+    const int g = blockIdx.x, j = threadIdx.x;
+    __shared__ float row[128];
+    __shared__ float red[2][8];
+    const int p0 = d.ph_off[g], p = d.g_p[g];
+    float s0 = 0.f, s1 = 0.f;
+    int n1 = 0;
+    for (int v = 0; v < p; v++) {
+        if (j < 128) row[j] = hp[(size_t)(p0 + v) * 128 + j];
+        __syncthreads();
+        const bool nonex = xph[(size_t)(p0 + v) * PG_PHORE_FEAT + ex_col] != 1.0f;
+        float a0 = b10[j], a1 = b11[j];
+#pragma unroll 8
+        for (int k = 0; k < 128; k++) { a0 = fmaf(row[k], w1t0[k * 256 + j], a0); a1 = fmaf(row[k], w1t1[k * 256 + j], a1); }
+        float t0 = fmaxf(a0, 0.f) * w20[j], t1 = fmaxf(a1, 0.f) * w21[j];
+        t0 = warp_sum(t0); t1 = warp_sum(t1);
+        if ((j & 31) == 0) { red[0][j >> 5] = t0; red[1][j >> 5] = t1; }
+        __syncthreads();
+        if (j == 0) {
+            float u0 = b20[0], u1 = b21[0];
+            for (int w = 0; w < 8; w++) { u0 += red[0][w]; u1 += red[1][w]; }
+            s0 += 1.0f / (1.0f + expf(-u0));
+            if (nonex) { s1 += 1.0f / (1.0f + expf(-u1)); n1++; }
+        }
+        __syncthreads();
+    }
+    if (j == 0) {
+        const float c = s0 / (float)max(p, 1);
+        const float l = s1 / (float)max(n1, 1);           // scatter-mean of an empty set is 0 (torch_scatter clamps the count)
+        const float u = l + fmaxf(c - l, 0.f);
+        cl[g] = l; cu[g] = u;
+        if (lo) { lo[g] = (int)rintf(l * (max_atom - min_atom) + min_atom); hi[g] = (int)rintf(u * (max_atom - min_atom) + min_atom); }
+    }
+}
+}  // namespace
+
+extern "C" int pg_atom_count(const PgModel* m, PgPlan* p, const float* d_h_phore_emb, const float* d_h_phore, int ex_col,
+                             float min_atom, float max_atom, float* d_count_l, float* d_count_u, int32_t* d_lo, int32_t* d_hi,
+                             void* stream) {
+    if (!d_h_phore_emb || !d_h_phore || !d_count_l || !d_count_u || ex_col < 0 || ex_col >= PG_PHORE_FEAT || (!d_lo) != (!d_hi)) {
+        pg_set_error("pg_atom_count: bad argument"); return PG_EINVAL;
+    }
+    const W w{m};
+    atom_count_kernel<<<(unsigned)p->d.G, 256, 0, (cudaStream_t)stream>>>(
+        p->d, d_h_phore_emb, d_h_phore, ex_col, w("G.cnt0.w1t"), w("G.cnt0.b1"), w("G.cnt0.w2"), w("G.cnt0.b2"), w("G.cnt1.w1t"),
+        w("G.cnt1.b1"), w("G.cnt1.w2"), w("G.cnt1.b2"), min_atom, max_atom, d_count_l, d_count_u, d_lo, d_hi);
+    PG_LAUNCH_CHECK();
+    p->launches++;
     return PG_OK;
 }
 

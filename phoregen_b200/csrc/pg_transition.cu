@@ -94,10 +94,13 @@ __global__ void __launch_bounds__(256) position_step_kernel(int rows, const floa
                                                             const int64_t* __restrict__ tstep, const int* __restrict__ row_graph,
                                                             const float* __restrict__ normal, uint64_t seed, uint32_t stream_id,
                                                             const int64_t* __restrict__ step_counter, float* __restrict__ x_prev,
-                                                            float* __restrict__ traj, const float* __restrict__ center) {
+                                                            float* __restrict__ traj, const float* __restrict__ center,
+                                                            int center_per_graph) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
-    const int t = (int)tstep[row_graph[r]];
+    const int gr = row_graph[r];
+    const int t = (int)tstep[gr];
+    if (center && center_per_graph) center += (size_t)gr * 3;
     const float a = c0[t], b = ct[t], sg = sd[t];
     float z[3] = {0.f, 0.f, 0.f};
     if (t != 0) {
@@ -132,9 +135,12 @@ __global__ void __launch_bounds__(128) guidance_kernel(PlanDev d, const int* __r
     const long long e0 = d.eoff[g];
     __shared__ float red[128];
     __shared__ float cen[3];
-    for (int i = tid; i < n * 3; i += blockDim.x) grad[(size_t)a0 * 3 + i] = 0.f;
+    if (!(flags & 4)) {                           // bit 2: accumulate onto the gradient of a previous drift entry
+        for (int i = tid; i < n * 3; i += blockDim.x) grad[(size_t)a0 * 3 + i] = 0.f;
+    }
     __syncthreads();
     const float invG = 1.0f / (float)d.G;
+    if (flags & 8) center += (size_t)g * 3;       // one pharmacophore centre per graph
     if (flags & 1) {
         // number of bonded directed edges of this graph
         float c = 0.f;
@@ -204,13 +210,14 @@ extern "C" int pg_categorical_step(int rows, int K, const float* d_pred, float* 
 extern "C" int pg_position_step(int rows, const float* d_x_t, const float* d_x_recon, const float* d_energy_grad,
                                 const float* d_coef_x0, const float* d_coef_xt, const float* d_std, const int64_t* d_time_step,
                                 const int32_t* d_row_graph, const float* d_normal, uint64_t seed, uint32_t stream_id,
-                                const int64_t* d_step_counter, float* d_x_prev, float* d_traj, const float* d_center, void* stream) {
+                                const int64_t* d_step_counter, float* d_x_prev, float* d_traj, const float* d_center,
+                                int center_per_graph, void* stream) {
     if (rows <= 0) return PG_OK;
     if (d_traj && !d_step_counter) { pg_set_error("pg_position_step: trajectory output needs the step counter"); return PG_EINVAL; }
     if (!d_normal && !d_step_counter) { pg_set_error("pg_position_step: need normals or a step counter"); return PG_EINVAL; }
     position_step_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         rows, d_x_t, d_x_recon, d_energy_grad, d_coef_x0, d_coef_xt, d_std, d_time_step, d_row_graph, d_normal, seed, stream_id,
-        d_step_counter, d_x_prev, d_traj, d_center);
+        d_step_counter, d_x_prev, d_traj, d_center, center_per_graph);
     PG_LAUNCH_CHECK();
     return PG_OK;
 }

@@ -130,32 +130,37 @@ class PhoreDiff(nn.Module):
         return self._packed
 
     def _plan_for(self, batch_node, batch_phore, edge_index, n_graphs, device):
-        key = (int(batch_node.numel()), int(batch_phore.numel()), int(edge_index.shape[1]), edge_index.data_ptr(),
-               batch_node.data_ptr(), batch_phore.data_ptr())
-        if self._plan is None or self._plan_key != key or not torch.equal(self._plan_edges, edge_index):
-            na = torch.bincount(batch_node, minlength=n_graphs).cpu().numpy()
-            npn = torch.bincount(batch_phore, minlength=n_graphs).cpu().numpy()
-            if bool((batch_node[1:] < batch_node[:-1]).any()) or bool((batch_phore[1:] < batch_phore[:-1]).any()):
-                raise ValueError("batch vectors must be sorted by graph")
+        """Plan of this batch's topology.  A cached plan is reused only when the CONTENTS agree: the per-graph atom and
+        pharmacophore counts and the sortedness are recomputed on every call (one small D2H), the edge list is compared
+        element-wise.  Tensor addresses are not part of the key (the caching allocator hands the same address to
+        different batches)."""
+        chk = torch.stack([(batch_node[1:] < batch_node[:-1]).any(), (batch_phore[1:] < batch_phore[:-1]).any()])
+        counts = torch.cat([torch.bincount(batch_node, minlength=n_graphs), torch.bincount(batch_phore, minlength=n_graphs),
+                            chk.long()]).cpu().numpy()
+        if counts[-2] or counts[-1]:
+            raise ValueError("batch vectors must be sorted by graph")
+        if counts.size != 2 * n_graphs + 2:
+            raise ValueError("graph ids in the batch vectors exceed the number of graphs")
+        na, npn = counts[:n_graphs].astype(np.int32), counts[n_graphs:2 * n_graphs].astype(np.int32)
+        pl = self._plan
+        if pl is None or pl.device != torch.device(device) or not np.array_equal(pl.num_atoms, na) or not np.array_equal(pl.num_phore, npn) \
+                or self._plan_edges.shape != edge_index.shape or not torch.equal(self._plan_edges, edge_index):
             self._plan = BatchPlan(na, npn, device, ref_edge_index=edge_index)
-            self._plan_key, self._plan_edges = key, edge_index.clone()
+            self._plan_edges = edge_index.clone()
         return self._plan
 
-    # ------------------------------------------------------------------ O2 (tiny, off the sampling loop)
-    def predict_atom_count(self, h_p, batch_p, _h_p, n_graphs=None):
-        """diffusion.py:148-163.  [P,128] x two 2-layer heads; not on the per-step path of sample() (its result is
-        discarded there, diffusion.py:436) so it stays a handful of cuBLAS calls on the module's own parameters."""
-        n_graphs = int(batch_p.max().item()) + 1 if n_graphs is None else n_graphs
+    # ------------------------------------------------------------------ O2 (diffusion.py:148-163)
+    @property
+    def _ex_col(self):
+        return 12 if self.data_name in ("zinc_300", "pdbbind") else 10
 
-        def gmean(v, b):
-            s = torch.zeros(n_graphs, 1, device=v.device).index_add_(0, b, v)
-            c = torch.zeros(n_graphs, 1, device=v.device).index_add_(0, b, torch.ones_like(v)).clamp(min=1)
-            return s / c
-        cnt = gmean(self.atom_mlp(h_p), batch_p)
-        col = 12 if self.data_name in ("zinc_300", "pdbbind") else 10
-        m = _h_p[:, col] != 1
-        cl = gmean(self.atom_mlp_1(h_p[m]), batch_p[m])
-        return cl, cl + F.relu(cnt - cl)
+    def predict_atom_count(self, h_p, batch_p, _h_p, n_graphs=None, plan=None):
+        """(count_l [G,1], count_u [G,1]) from the encoded pharmacophore nodes: one launch of atom_count_kernel
+        (pg_atom_count) over the plan's pharmacophore segments."""
+        if plan is None:
+            n_graphs = int(batch_p.max().item()) + 1 if n_graphs is None else n_graphs
+            plan = BatchPlan(np.full(n_graphs, 2, np.int32), torch.bincount(batch_p, minlength=n_graphs).cpu().numpy(), h_p.device, edge_order=1)
+        return plan.atom_count(self.packed(h_p.device), h_p, _h_p, self._ex_col, self.min_atom, self.max_atom)
 
     # ------------------------------------------------------------------ forward (diffusion.py:175-246)
     @torch.no_grad()
@@ -169,7 +174,7 @@ class PhoreDiff(nn.Module):
             h_phore_emb = plan.phore_encode(pm, h_phore, pos_phore)
         v, pos, b = plan.phorediff_forward(pm, h_node_pert, pos_pert, h_edge_pert, time_step.to(torch.int64).contiguous(),
                                            h_phore_emb, pos_phore, phore_norm)
-        cnt = self.predict_atom_count(h_phore_emb, batch_phore, h_phore, n_graphs)
+        cnt = self.predict_atom_count(h_phore_emb, batch_phore, h_phore, n_graphs, plan=plan)
         return v, pos, b, cnt
 
     def compute_loss(self, data, rng_device=None):
@@ -181,20 +186,43 @@ class PhoreDiff(nn.Module):
 
     # ------------------------------------------------------------------ D2 (diffusion.py:356-387)
     @torch.no_grad()
-    def sample_nodes(self, data, batch_size, device, sample_mode="uniform", normal_scale=4.0):
+    def atom_count_intervals(self, phore_x, phore_pos, phore_batch, n_graphs, device):
+        """Integer atom-count interval [lo, hi] of every graph of a pharmacophore batch (diffusion.py:356-380), on the
+        device: phore encoder + atom_count_kernel, no host synchronisation.  -> (lo [G] int32, hi [G] int32)."""
+        device = torch.device(device)
+        num_phore = torch.bincount(phore_batch, minlength=n_graphs).cpu().numpy().astype(np.int32)
+        plan = BatchPlan(np.full(n_graphs, 2, np.int32), num_phore, device, edge_order=1)   # ligand side unused by the encoder
+        pm = self.packed(device)
+        x, pos = phore_x.to(device).float().contiguous(), phore_pos.to(device).float().contiguous()
+        h_p = plan.phore_encode(pm, x, pos)
+        _, _, lo, hi = plan.atom_count(pm, h_p, x, self._ex_col, self.min_atom, self.max_atom, intervals=True)
+        return lo, hi
+
+    @staticmethod
+    def sample_from_intervals(lo, hi, mode="uniform", scale=4.0, generator=None):
+        """utils/sample_utils.py:28-37 for per-graph intervals, drawn on the device of `lo` (one draw per graph)."""
+        lo_f, hi_f = lo.float(), hi.float()
+        if mode == "uniform":                                   # randint(lo, hi + 1)
+            u = torch.rand(lo.shape, device=lo.device, generator=generator)
+            return (lo + torch.floor(u * (hi_f - lo_f + 1.0)).to(lo.dtype)).clamp(max=hi)
+        if mode == "normal":
+            z = torch.randn(lo.shape, device=lo.device, generator=generator)
+            n = (lo_f + hi_f) / 2 + z * (hi_f - lo_f) / scale
+            return torch.minimum(torch.maximum(n, lo_f), hi_f).round().to(lo.dtype)
+        raise NotImplementedError(f"The sample nodes mode {mode} is not implemented.")
+
+    @torch.no_grad()
+    def sample_nodes(self, data, batch_size, device, sample_mode="uniform", normal_scale=4.0, return_interval=False):
+        """diffusion.py:356-387: `batch_size` atom counts for ONE pharmacophore.  The interval comes from the device
+        kernels; the draws use the CPU generator like the reference's sample_from_interval (sample_utils.py:28-37), so
+        a seeded run draws the same counts as the reference."""
         ph = data["phore"]
-        x, pos = ph.x.to(device).float(), ph.pos.to(device).float()
-        plan = BatchPlan([2], [x.shape[0]], device, edge_order=1)          # single-graph plan for the encoder
-        h_p = plan.phore_encode(self.packed(device), x, pos)
-        cnt = self.atom_mlp(h_p).mean(0, keepdim=True)
-        col = 12 if self.data_name in ("zinc_300", "pdbbind") else 10
-        m = x[:, col] != 1
-        cl = self.atom_mlp_1(h_p[m]).mean(0, keepdim=True)
-        cu = cl + F.relu(cnt - cl)
-        scale = self.max_atom - self.min_atom
-        lo = int((cl * scale + self.min_atom).round().int().item())
-        hi = int((cu * scale + self.min_atom).round().int().item())
-        if sample_mode == "uniform":                                        # utils/sample_utils.py:28-37 (CPU RNG)
+        x = ph.x.to(device).float()
+        lo, hi = self.atom_count_intervals(x, ph.pos, torch.zeros(x.shape[0], dtype=torch.long, device=device), 1, device)
+        lo, hi = int(lo.item()), int(hi.item())
+        if return_interval:
+            return lo, hi
+        if sample_mode == "uniform":
             n = torch.randint(lo, hi + 1, (batch_size,))
         elif sample_mode == "normal":
             n = torch.normal((lo + hi) / 2, (hi - lo) / normal_scale, (batch_size,)).clamp(lo, hi).round().int()
@@ -205,7 +233,8 @@ class PhoreDiff(nn.Module):
     # ------------------------------------------------------------------ D1 (diffusion.py:390-525)
     @torch.no_grad()
     def sample(self, data, n_graphs, device, pos_guidance_opt=None, sample_mode="uniform", normal_scale=4.0,
-               ligand_num_atoms=None, save_traj=True, seed=None, use_cuda_graph=True, num_steps=None, **kwargs):
+               ligand_num_atoms=None, save_traj=True, seed=None, use_cuda_graph=True, num_steps=None, traj_layout="compact",
+               phore_batch=None, **kwargs):
         """Reverse diffusion for `n_graphs` copies of one pharmacophore.  Returns the reference's dict
         {'pred': [logits_node, pos+center, logits_edge], 'traj': [node, pos, edge], 'lig_info': [...]}.
         Extensions (keyword-only in spirit): `ligand_num_atoms` bypasses the atom-count head, `save_traj=False`
@@ -214,9 +243,9 @@ class PhoreDiff(nn.Module):
         device = torch.device(device)
         sampler = TrajectorySampler(self, data, n_graphs, device, ligand_num_atoms=ligand_num_atoms,
                                     sample_mode=sample_mode, normal_scale=normal_scale, guidance=pos_guidance_opt,
-                                    save_traj=save_traj, seed=seed, use_cuda_graph=use_cuda_graph)
+                                    save_traj=save_traj, seed=seed, use_cuda_graph=use_cuda_graph, phore_batch=phore_batch)
         sampler.run(num_steps)
-        return sampler.results()
+        return sampler.results(traj_layout)
 
 
 class TrajectorySampler:
@@ -245,17 +274,30 @@ class TrajectorySampler:
             self.px, self.ppos, self.pnorm = px.repeat(n_graphs, 1), ppos.repeat(n_graphs, 1).contiguous(), pnorm.repeat(n_graphs, 1).contiguous()
             single_x, single_pos = px, ppos
         else:
-            if ligand_num_atoms is None:
-                raise ValueError("phore_batch needs explicit ligand_num_atoms")
             self.px = phore_batch["x"].to(device).float().contiguous()
             self.ppos = phore_batch["pos"].to(device).float().contiguous()
             self.pnorm = phore_batch["norm"].to(device).float().contiguous()
-            num_phore = torch.bincount(phore_batch["batch"], minlength=n_graphs).cpu().numpy().astype(np.int32)
-            center = None
+            pb = phore_batch["batch"].to(device)
+            cnt = torch.bincount(pb, minlength=n_graphs)
+            bad = torch.stack([(pb[1:] < pb[:-1]).any(), (cnt == 0).any(), torch.as_tensor(cnt.numel() != n_graphs, device=device)])
+            num_phore = torch.cat([cnt, bad.long()]).cpu().numpy()
+            if num_phore[-3:].any():
+                raise ValueError("phore_batch['batch'] must be sorted by graph, with at least one feature for each of the n_graphs graphs")
+            num_phore = num_phore[:-3].astype(np.int32)
+            if ligand_num_atoms is None:        # D2 for a batch of pharmacophores: intervals and draws on the device
+                gen = None
+                if seed is not None:
+                    gen = torch.Generator(device=device)
+                    gen.manual_seed(int(seed) ^ 0x5DEECE66D)
+                lo, hi = model.atom_count_intervals(self.px, self.ppos, pb, n_graphs, device)
+                ligand_num_atoms = model.sample_from_intervals(lo, hi, sample_mode, normal_scale, generator=gen)
+            center = phore_batch.get("center")    # [G,3] per-graph centres (collate_phores) or None: positions stay centred
             single_x = single_pos = None
         self.num_atoms = torch.as_tensor(ligand_num_atoms).to(device)
         na = self.num_atoms.cpu().numpy().astype(np.int32)
         self.center = (torch.zeros(3, device=device) if center is None else torch.as_tensor(center).to(device).float()).contiguous()
+        if self.center.dim() == 2 and self.center.shape != (n_graphs, 3):
+            raise ValueError("per-graph centres must be [n_graphs, 3]")
         plan = self.plan = BatchPlan(na, num_phore, device, edge_order=0)
         self.h_phore_emb = plan.phore_encode(pm, self.px, self.ppos)      # step-invariant (SURVEY.md §8(d) reduction 4)
         self.batch_node = torch.repeat_interleave(torch.arange(n_graphs, device=device), self.num_atoms.long())
@@ -265,7 +307,8 @@ class TrajectorySampler:
         gen = torch.Generator(device=device)
         gen.manual_seed(self.seed)
         # initial state (diffusion.py:406-408; transition.py:65-69,331-339)
-        self.pos = (torch.randn(Nl, 3, device=device, generator=gen) - self.center).contiguous()
+        self.center_rows = self.center[self.batch_node] if self.center.dim() == 2 else self.center     # [Nl,3] or [3]
+        self.pos = (torch.randn(Nl, 3, device=device, generator=gen) - self.center_rows).contiguous()
         self.log_node = torch.empty(Nl, 12, device=device)
         self.log_edge = torch.empty(Eb, 6, device=device)
         self.h_node, self.node_cls = self._init_categorical(model.node_transition, Nl, self.log_node, gen)
@@ -277,10 +320,15 @@ class TrajectorySampler:
         self.grad = torch.zeros(Nl, 3, device=device) if guidance else None
         self.phore_center = None
         if guidance:
-            if single_x is None:
-                raise NotImplementedError("guidance needs the single-pharmacophore form (its energy uses one phore centre)")
-            col = 12 if model.data_name in ("zinc_300", "pdbbind") else 10
-            self.phore_center = single_pos[single_x[:, col] != 1].mean(0).contiguous()   # diffusion.py:493-497
+            col = model._ex_col
+            if single_x is not None:
+                self.phore_center = single_pos[single_x[:, col] != 1].mean(0).contiguous()   # diffusion.py:493-497
+            else:   # one pharmacophore per graph: centre of each graph's non-EX features (segment mean, once per batch)
+                keep = (self.px[:, col] != 1).float().unsqueeze(1)
+                pbatch = phore_batch["batch"].to(device)
+                s = torch.zeros(n_graphs, 3, device=device).index_add_(0, pbatch, self.ppos * keep)
+                c = torch.zeros(n_graphs, 1, device=device).index_add_(0, pbatch, keep)
+                self.phore_center = (s / c).contiguous()          # 0/0 = nan for a graph without non-EX features, as torch.mean of an empty set
         self.save_traj = save_traj
         if save_traj:
             try:
@@ -322,9 +370,16 @@ class TrajectorySampler:
         self.step_counter.add_(1)
 
     def run(self, num_steps=None):
+        """Advance the trajectory; returns the number of steps actually executed (at most the steps that are left)."""
         n = self.T - self.steps_done if num_steps is None else min(num_steps, self.T - self.steps_done)
         if n <= 0:
-            return
+            return 0
+        with torch.cuda.device(self.device):      # capture and replay on the plan's GPU whatever device is current in the caller
+            self._run(n)
+        self.steps_done += n
+        return n
+
+    def _run(self, n):
         if not self.use_cuda_graph:
             for _ in range(n):
                 self._step()
@@ -345,7 +400,6 @@ class TrajectorySampler:
                     self._step()
             for _ in range(n):
                 self.graph.replay()
-        self.steps_done += n
 
     def _state_tensors(self):
         ts = [self.h_node, self.pos, self.h_edge, self.log_node, self.log_edge, self.node_cls, self.edge_cls,
@@ -354,15 +408,25 @@ class TrajectorySampler:
             ts += [self.traj_node[1], self.traj_edge[1], self.traj_pos[1]]
         return ts
 
-    def results(self):
-        pred_pos = self.pred[1] + self.center                                  # reference quirk 3 (diffusion.py:519)
+    def results(self, layout="compact"):
+        """The reference's result dict (diffusion.py:519-525).  `layout`:
+          "compact"   (default) the categorical trajectories stay class indices: `traj` = [ClassTrajectory(node),
+                      pos [T+1,Nl,3] f32, ClassTrajectory(edge)].  A ClassTrajectory indexes like the reference's one-hot
+                      tensor ([:, mask], [-1], .cpu(), .shape) and expands to one-hot f32 only for the slice that is read,
+                      so unbatch_data (sample_utils.py:57-93) consumes it unchanged while the device never holds the
+                      [T+1,E_b,6] f32 tensor (21 GB at configs[1]);
+          "reference" the dense one-hot f32 tensors of diffusion.py:418-426 (small batches / tests)."""
+        pred_pos = self.pred[1] + self.center_rows                             # reference quirk 3 (diffusion.py:519)
         if self.save_traj:
-            # reference layout: one-hot f32 with time as dim 0 (diffusion.py:418-426)
-            node_traj = F.one_hot(self.traj_node.long(), 12).float()
-            edge_traj = F.one_hot(self.traj_edge.long(), 6).float()
             pos_traj = self.traj_pos                                           # slot 0 is the un-centred init (diffusion.py:425)
+            if layout == "reference":
+                node_traj = F.one_hot(self.traj_node.long(), 12).float()
+                edge_traj = F.one_hot(self.traj_edge.long(), 6).float()
+            else:
+                from .results import ClassTrajectory
+                node_traj, edge_traj = ClassTrajectory(self.traj_node, 12), ClassTrajectory(self.traj_edge, 6)
         else:
-            node_traj, pos_traj, edge_traj = self.h_node[None], (self.pos + self.center)[None], self.h_edge[None]
+            node_traj, pos_traj, edge_traj = self.h_node[None], (self.pos + self.center_rows)[None], self.h_edge[None]
         return {"pred": [self.pred[0], pred_pos, self.pred[2]],
                 "traj": [node_traj, pos_traj, edge_traj],
                 "lig_info": [self.num_atoms, self.batch_node, self.edge_index, self.edge_batch]}

@@ -20,8 +20,25 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    """Current stream OF `device` (not of the process's current device): every launch of a plan goes to the stream of the
+    plan's own GPU, whatever device is current in the caller."""
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _on_device(method):
+    """Run a BatchPlan method with the plan's device current (kernel launches, cudaFuncSetAttribute and event calls inside
+    the library act on the current device) and check that tensor arguments live there."""
+    import functools
+
+    @functools.wraps(method)
+    def wrapped(self, *args, **kwargs):
+        for t in list(args) + list(kwargs.values()):
+            if isinstance(t, torch.Tensor) and t.is_cuda and t.device != self.device:
+                raise ValueError(f"{method.__name__}: tensor on {t.device}, plan on {self.device}")
+        with torch.cuda.device(self.device):
+            return method(self, *args, **kwargs)
+    return wrapped
 
 
 def _f32(t):
@@ -42,6 +59,8 @@ class PackedModel:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.PhoreGenLibraryError("phoregen_b200 runs on CUDA devices only (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.blob, offsets = blob_to_device(state_dict, self.device)
         self._offsets = offsets
         h = ctypes.c_void_p()
@@ -66,6 +85,8 @@ class BatchPlan:
 
     def __init__(self, num_atoms, num_phore, device, edge_order=0, ref_edge_index=None):
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         na = np.ascontiguousarray(np.asarray(num_atoms, dtype=np.int32))
         npn = np.ascontiguousarray(np.asarray(num_phore, dtype=np.int32))
         assert na.shape == npn.shape and na.ndim == 1
@@ -86,7 +107,7 @@ class BatchPlan:
         h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             check(lib.pg_plan_create(ctypes.byref(h), self.G, pa, pp, edge_order, _ptr(ref_edge_index),
-                                     ctypes.c_void_p(aligned), nbytes, _stream()), "pg_plan_create")
+                                     ctypes.c_void_p(aligned), nbytes, _stream(self.device)), "pg_plan_create")
         self.handle = h
         self.Nl = int(lib.pg_plan_num_ligand_atoms(h))
         self.P = int(lib.pg_plan_num_phore_nodes(h))
@@ -109,9 +130,11 @@ class BatchPlan:
 
     KERNEL_CLASSES = ("gemm", "knn_attn", "bond_attn", "trip", "knn_graph", "other")
 
+    @_on_device
     def timing(self, on):
         check(lib.pg_plan_timing_enable(self.handle, int(bool(on))), "pg_plan_timing_enable")
 
+    @_on_device
     def read_timing(self):
         """-> {class: (total_ms, launches)} measured with CUDA events on the launching stream."""
         out = {}
@@ -122,17 +145,20 @@ class BatchPlan:
         return out
 
     # ---- graph artefacts (G1, B1, K1) ------------------------------------------------------
+    @_on_device
     def bond_edges(self):
         ei = _alloc((2, self.Eb), torch.int64, self.device)
         eb = _alloc((self.Eb,), torch.int64, self.device)
-        check(lib.pg_plan_export_bond_edges(self.handle, _ptr(ei), _ptr(eb), _stream()), "pg_plan_export_bond_edges")
+        check(lib.pg_plan_export_bond_edges(self.handle, _ptr(ei), _ptr(eb), _stream(self.device)), "pg_plan_export_bond_edges")
         return ei, eb
 
+    @_on_device
     def triplets(self):
         outs = [_alloc((self.E3,), torch.int64, self.device) for _ in range(5)]
-        check(lib.pg_plan_export_triplets(self.handle, *[_ptr(o) for o in outs], _stream()), "pg_plan_export_triplets")
+        check(lib.pg_plan_export_triplets(self.handle, *[_ptr(o) for o in outs], _stream(self.device)), "pg_plan_export_triplets")
         return outs
 
+    @_on_device
     def knn_graph(self, x, mode=0):
         """mode 0: k=32 joint graph in context numbering; mode 1: k=3 ligand-only graph in ligand numbering."""
         x = _f32(x)
@@ -142,27 +168,30 @@ class BatchPlan:
         else:
             E = int(sum(int(n) * min(3, int(n) - 1) for n in self.num_atoms))
         ei = _alloc((2, E), torch.int64, self.device)
-        check(lib.pg_knn_graph(self.handle, _ptr(x), mode, _ptr(ei), _stream()), "pg_knn_graph")
+        check(lib.pg_knn_graph(self.handle, _ptr(x), mode, _ptr(ei), _stream(self.device)), "pg_knn_graph")
         return ei
 
     # ---- forward passes ---------------------------------------------------------------------
+    @_on_device
     def phore_encode(self, model, h_phore, pos_phore):
         h_phore, pos_phore = _f32(h_phore), _f32(pos_phore)
         assert h_phore.shape == (self.P, 18) and pos_phore.shape == (self.P, 3)
         out = _alloc((self.P, 128), torch.float32, self.device)
-        check(lib.pg_phore_encode(model.handle, self.handle, _ptr(h_phore), _ptr(pos_phore), _ptr(out), _stream()),
+        check(lib.pg_phore_encode(model.handle, self.handle, _ptr(h_phore), _ptr(pos_phore), _ptr(out), _stream(self.device)),
               "pg_phore_encode")
         return out
 
+    @_on_device
     def denoiser_forward(self, model, h, x, h_bond, phore_norm):
         h, x, h_bond, phore_norm = _f32(h), _f32(x), _f32(h_bond), _f32(phore_norm)
         assert h.shape == (self.N, 128) and x.shape == (self.N, 3) and h_bond.shape == (self.Eb, 128)
         assert phore_norm.shape == (self.P, 3)
         ho, xo, bo = torch.empty_like(h), torch.empty_like(x), torch.empty_like(h_bond)
         check(lib.pg_denoiser_forward(model.handle, self.handle, _ptr(h), _ptr(x), _ptr(h_bond), _ptr(phore_norm),
-                                      _ptr(ho), _ptr(xo), _ptr(bo), _stream()), "pg_denoiser_forward")
+                                      _ptr(ho), _ptr(xo), _ptr(bo), _stream(self.device)), "pg_denoiser_forward")
         return ho, xo, bo
 
+    @_on_device
     def phorediff_forward(self, model, h_node, pos, h_edge, time_step, h_phore_emb, pos_phore, phore_norm, out=None):
         h_node, pos, h_edge = _f32(h_node), _f32(pos), _f32(h_edge)
         assert h_node.shape == (self.Nl, 12) and pos.shape == (self.Nl, 3) and h_edge.shape == (self.Eb, 6)
@@ -174,10 +203,23 @@ class BatchPlan:
                    _alloc((self.Eb, 6), torch.float32, self.device))
         check(lib.pg_phorediff_forward(model.handle, self.handle, _ptr(h_node), _ptr(pos), _ptr(h_edge), _ptr(time_step),
                                        _ptr(h_phore_emb), _ptr(pos_phore), _ptr(phore_norm),
-                                       _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _stream()), "pg_phorediff_forward")
+                                       _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _stream(self.device)), "pg_phorediff_forward")
         return out
 
+    @_on_device
+    def atom_count(self, model, h_phore_emb, h_phore, ex_col=12, min_atom=4, max_atom=78, intervals=False):
+        """-> (count_l [G,1], count_u [G,1]) and, with intervals=True, the int32 bounds (lo [G], hi [G]) of sample_nodes."""
+        h_phore_emb, h_phore = _f32(h_phore_emb), _f32(h_phore)
+        assert h_phore_emb.shape == (self.P, 128) and h_phore.shape == (self.P, 18)
+        cl, cu = _alloc((self.G, 1), torch.float32, self.device), _alloc((self.G, 1), torch.float32, self.device)
+        lo = _alloc((self.G,), torch.int32, self.device) if intervals else None
+        hi = _alloc((self.G,), torch.int32, self.device) if intervals else None
+        check(lib.pg_atom_count(model.handle, self.handle, _ptr(h_phore_emb), _ptr(h_phore), ex_col, float(min_atom), float(max_atom),
+                                _ptr(cl), _ptr(cu), _ptr(lo), _ptr(hi), _stream(self.device)), "pg_atom_count")
+        return (cl, cu, lo, hi) if intervals else (cl, cu)
+
     # ---- transitions -----------------------------------------------------------------------
+    @_on_device
     def categorical_step(self, model, kind, pred, log_vt, time_step, uniform=None, seed=0, step_counter=None,
                          onehot=None, cls=None, traj=None):
         K = 12 if kind == "node" else 6
@@ -192,9 +234,10 @@ class BatchPlan:
             cls = _alloc((rows,), torch.int32, self.device)
         check(lib.pg_categorical_step(rows, K, _ptr(pred), _ptr(log_vt), _ptr(qm), _ptr(tq), _ptr(time_step),
                                       ctypes.c_void_p(rg), _ptr(uniform), seed, 1 if kind == "node" else 2,
-                                      _ptr(step_counter), _ptr(onehot), _ptr(cls), _ptr(traj), _stream()), "pg_categorical_step")
+                                      _ptr(step_counter), _ptr(onehot), _ptr(cls), _ptr(traj), _stream(self.device)), "pg_categorical_step")
         return onehot, cls
 
+    @_on_device
     def position_step(self, model, x_t, x_recon, time_step, normal=None, energy_grad=None, seed=0, step_counter=None,
                       out=None, traj=None, center=None):
         assert x_t.shape == (self.Nl, 3) and x_recon.shape == (self.Nl, 3)
@@ -204,19 +247,31 @@ class BatchPlan:
         check(lib.pg_position_step(self.Nl, _ptr(x_t), _ptr(x_recon), _ptr(energy_grad), _ptr(t["pos_transition.coef_x0"]),
                                    _ptr(t["pos_transition.coef_xt"]), _ptr(t["pos_transition.std"]), _ptr(time_step),
                                    ctypes.c_void_p(self._lig_graph_ptr), _ptr(normal), seed, 3, _ptr(step_counter),
-                                   _ptr(out), _ptr(traj), _ptr(center), _stream()), "pg_position_step")
+                                   _ptr(out), _ptr(traj), _ptr(center), int(center is not None and center.dim() == 2),
+                                   _stream(self.device)), "pg_position_step")
         return out
 
+    @_on_device
     def guidance_grad(self, pos, edge_cls, opts, phore_center, out=None):
-        flags, min_d, max_d = 0, 0.0, 0.0
-        for o in opts or []:
-            if o["type"] == "atom_prox":
-                flags |= 1
-                min_d, max_d = float(o["min_d"]), float(o["max_d"])
-            elif o["type"] == "center_prox":
-                flags |= 2
+        """Sum of the drift gradients of every entry of `pos_guidance_opt` (diffusion.py:479-501 adds one gradient per
+        list entry; unknown types contribute nothing there and are rejected here).  `phore_center`: [3] (one
+        pharmacophore for the whole batch) or [G,3] (one per graph)."""
         if out is None:
             out = torch.empty_like(pos)
-        check(lib.pg_guidance_grad(self.handle, _ptr(pos), _ptr(edge_cls), flags, min_d, max_d,
-                                   _ptr(phore_center), _ptr(out), _stream()), "pg_guidance_grad")
+        per_graph = 1 if (phore_center is not None and phore_center.dim() == 2) else 0
+        if per_graph:
+            assert phore_center.shape == (self.G, 3)
+        first = True
+        for o in opts or []:
+            if o["type"] == "atom_prox":
+                flags, min_d, max_d = 1, float(o["min_d"]), float(o["max_d"])
+            elif o["type"] == "center_prox":
+                flags, min_d, max_d = 2, 0.0, 0.0
+            else:
+                raise NotImplementedError(f"pos_guidance_opt type {o['type']!r}")
+            check(lib.pg_guidance_grad(self.handle, _ptr(pos), _ptr(edge_cls), flags | (0 if first else 4) | (8 * per_graph),
+                                       min_d, max_d, _ptr(phore_center), _ptr(out), _stream(self.device)), "pg_guidance_grad")
+            first = False
+        if first:
+            out.zero_()
         return out

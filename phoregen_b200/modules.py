@@ -181,24 +181,28 @@ class UniTransformerO2TwoUpdateGeneralBond(nn.Module):
                 return_all=False, packed=None, plan=None):
         if group_idx is not None:
             raise NotImplementedError("group_idx is always None in the reference (diffusion.py:213)")
-        if return_all:
-            raise NotImplementedError("return_all=True (per-block history) is not provided by the fused path")
         if torch.is_grad_enabled() and any(t.requires_grad for t in (h, x, h_bond)):
-            raise NotImplementedError("phoregen_b200 round 1 implements the inference forward only (no autograd)")
+            raise NotImplementedError("the stand-alone denoiser module is forward only; gradients flow through PhoreDiff.compute_loss")
         dev = h.device
         if plan is None:
-            key = (h.shape[0], h_bond.shape[0], bond_index.data_ptr(), batch.data_ptr())
-            if self._plan is None or self._plan_key != key or not torch.equal(self._plan_bond_index, bond_index):
-                num_phore, num_atoms = topology_from_context(batch, mask_ligand)
+            # The cached plan is reused only if the CONTENTS agree: per-graph counts (recomputed on every call: two small
+            # D2H copies) and the bond index.  Addresses are not a key - the caching allocator reuses them across batches.
+            num_phore, num_atoms = topology_from_context(batch, mask_ligand)
+            pl = self._plan
+            if pl is None or pl.device != dev or not np.array_equal(pl.num_atoms, num_atoms) or not np.array_equal(pl.num_phore, num_phore) \
+                    or self._plan_bond_index.shape != bond_index.shape or not torch.equal(self._plan_bond_index, bond_index):
                 lig_rows = mask_ligand.nonzero()[:, 0]
                 ctx_to_lig = torch.full((h.shape[0],), -1, dtype=torch.int64, device=dev)
                 ctx_to_lig[lig_rows] = torch.arange(lig_rows.numel(), device=dev)
                 self._plan = BatchPlan(num_atoms, num_phore, dev, ref_edge_index=ctx_to_lig[bond_index])
-                self._plan_key, self._plan_bond_index = key, bond_index.clone()
+                self._plan_bond_index = bond_index.clone()
             plan = self._plan
         packed = packed or self._get_packed(dev)
         ho, xo, bo = plan.denoiser_forward(packed, h, x, h_bond, phore_norm)
-        return {"x": xo, "h": ho, "h_bond": bo}
+        out = {"x": xo, "h": ho, "h_bond": bo}
+        if return_all:      # uni_denoiser.py:398-430 with num_blocks = 1: the inputs, then the state after the block
+            out.update({"all_x": [x, xo], "all_h": [h, ho], "all_h_bond": [h_bond, bo]})
+        return out
 
 
 def get_denoiser_net(config):

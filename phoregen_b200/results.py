@@ -13,6 +13,59 @@ import torch
 ATOM_TYPES = [5, 6, 7, 8, 9, 14, 15, 16, 17, 35, 53]   # utils/sample_utils.py:17 (the mask atom is class 11, the last one)
 
 
+class ClassTrajectory:
+    """Categorical trajectory kept as class indices: the compact stand-in for the reference's `[T+1, rows, K]` one-hot f32
+    trajectory tensors (models/diffusion.py:418-426).  It supports exactly what the reference's consumers do with them -
+    `.cpu()` (sample_all.py:104), `[:, mask]` per molecule (utils/sample_utils.py:74-76), `[t]` and `len()` per time step
+    (sample_all.py:138-143) - and materialises one-hot f32 only for the `[t]` slice that is read.  At configs[1] the dense
+    edge trajectory is 21 GB; this holds 0.9 GB."""
+
+    def __init__(self, classes, num_classes):
+        assert classes.dim() == 2 and classes.dtype == torch.uint8
+        self.classes, self.num_classes = classes, int(num_classes)
+
+    # ---- tensor-like surface
+    @property
+    def shape(self):
+        return torch.Size((*self.classes.shape, self.num_classes))
+
+    @property
+    def device(self):
+        return self.classes.device
+
+    @property
+    def is_cuda(self):
+        return self.classes.is_cuda
+
+    def __len__(self):
+        return self.classes.shape[0]
+
+    def cpu(self):
+        return ClassTrajectory(self.classes.cpu(), self.num_classes)
+
+    def to(self, *args, **kwargs):
+        kwargs.pop("dtype", None)
+        args = [a for a in args if not isinstance(a, torch.dtype)]
+        return ClassTrajectory(self.classes.to(*args, **kwargs), self.num_classes)
+
+    def dense(self):
+        """The reference's tensor: one-hot f32 [T+1, rows, K]."""
+        return torch.nn.functional.one_hot(self.classes.long(), self.num_classes).float()
+
+    def __getitem__(self, idx):
+        if isinstance(idx, tuple):
+            if len(idx) > 2:
+                return self.dense()[idx]
+            sub = self.classes[idx[0]]                       # time index first, then the row selection on the last dim
+            if len(idx) == 2:
+                sub = sub[..., idx[1]]
+        else:
+            sub = self.classes[idx]
+        if sub.dim() == 2:
+            return ClassTrajectory(sub, self.num_classes)
+        return torch.nn.functional.one_hot(sub.long(), self.num_classes).float()      # one time step (or one row): dense
+
+
 def _offsets(num_atoms):
     n = torch.as_tensor(num_atoms).detach().to("cpu", torch.int64)
     node_off = torch.zeros(n.numel() + 1, dtype=torch.int64)

@@ -62,6 +62,10 @@ def pack_state_dict(sd):
     out["G.ew.b2"] = np.concatenate([e["b2"], np.zeros(3)])
     out["G.vinf.w1t"], out["G.vinf.b1"] = f("v_inference.0.weight").T, f("v_inference.0.bias")
     out["G.vinf.w2"], out["G.vinf.b2"] = f("v_inference.2.weight"), f("v_inference.2.bias")
+    for c, name in enumerate(("atom_mlp", "atom_mlp_1")):          # atom-count heads (diffusion.py:77-88)
+        out[f"G.cnt{c}.w1t"], out[f"G.cnt{c}.b1"] = f(name + ".0.weight").T, f(name + ".0.bias")
+        out[f"G.cnt{c}.w2"] = f(name + ".2.weight")[0]
+        out[f"G.cnt{c}.b2"] = np.concatenate([f(name + ".2.bias"), np.zeros(3)])
     out["G.binf.w1t"], out["G.binf.b1"] = f("bond_inference.0.weight").T, f("bond_inference.0.bias")
     out["G.binf.w2"] = f("bond_inference.2.weight")
     out["G.binf.b2"] = np.concatenate([f("bond_inference.2.bias"), np.zeros(2)])
@@ -138,6 +142,13 @@ def bf16_split(wt):
     return np.concatenate([hi.reshape(-1), lo.reshape(-1)]).view(np.float32)
 
 
+def f16_image(wt):
+    """k-major fp32 weight [128][N] -> fp32-typed carrier of [N][128] IEEE half values (K-major): the B operand of the
+    single-pass fp16 contraction the tensor-core attention kernels use for the key MLP's second Linear."""
+    w = np.ascontiguousarray(np.asarray(wt, dtype=np.float64).T, dtype=np.float32)
+    return w.astype(np.float16).view(np.uint16).reshape(-1).view(np.float32)
+
+
 def bf16_tiles64(wt):
     """k-major fp32 weight [128][N] -> the exact shared-memory images the tcgen05 GEMM bulk-copies: for every block of 64
     output columns a 32 KB image [hi|lo][K block 0|1][64 rows x 128 B], rows K-major with the 128-byte swizzle applied
@@ -160,7 +171,7 @@ def bf16_tiles64(wt):
 def build_blob(sd):
     """-> (fp32 numpy blob, int64 offsets in floats) following the library's own slot table."""
     packed = pack_state_dict(sd)
-    for name in [k for k in packed if k.endswith((".wt", "w2q_t", "wcat_t", "w1t")) and k != "G.ew.w1t"]:
+    for name in [k for k in packed if k.endswith((".wt", "w2q_t", "wcat_t", "w1t")) and k != "G.ew.w1t" and not k.startswith("G.cnt")]:
         packed[name + ".bf"] = bf16_tiles64(packed[name])
     # Tensor-core attention kernels: second Linear as bf16 hi/lo images.  Where every LayerNorm gain of the MLP is positive,
     # relu(g*xn + b) = g * relu(xn + b/g), so g is folded into the columns of W2 (fp64) and the kernel only needs b/g
@@ -176,6 +187,8 @@ def build_blob(sd):
             flags[i] = 1.0 if fold else 0.0
             packed[S + f"ln{kv}_bf"] = b / g if fold else b
             packed[S + f"w2{kv}.bf"] = bf16_split((w2 * g[None, :] if fold else w2).T)   # [out][in]; pos value head: 16 outputs
+            if kv == "k":
+                packed[S + "w2k.h"] = f16_image((w2 * g[None, :] if fold else w2).T)
         packed[S + "fold"] = flags
     for name in [k for k in packed if k.endswith((".nk.tab_k", ".nk.tab_v", ".pk.tab_k", ".pk.tab_v"))]:
         packed[name + ".bf"] = bf16_split(np.asarray(packed[name]).reshape(96, 128))   # [type*24 + feat][128] -> [hi|lo][128][96]

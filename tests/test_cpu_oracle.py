@@ -111,3 +111,80 @@ def test_oracle_matches_unmodified_reference_live(sd):
     got = O.phorediff_forward(sd, b["h_node"], b["pos"], b["batch_node"], b["h_edge"], b["edge_index"], b["batch_edge"], t, ph["x"], ph["pos"], ph["norm"], ph["batch"])
     for g_, w_ in zip(got[:3], want[:3]):
         assert_close(g_, w_, "forward", rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("case", ["n35", "n48"])
+def test_oracle_forward_matches_reference_golden_big_molecules(sd, case):
+    """The fixtures that pin the chunked-segment kernels (n - 2 > 32): the oracle agrees with the unmodified reference there too."""
+    f = load_golden("forward_big.pt")["cases"][case]
+    b = O.synthetic_batch(f["seed"], f["n_graphs"], n_atoms=f["n_atoms"], p_choices=f["p_choices"], pos_scale=f["pos_scale"])
+    ph = b["phore"]
+    v, pos, e, _ = O.phorediff_forward(sd, b["h_node"], b["pos"], b["batch_node"], b["h_edge"], b["edge_index"], b["batch_edge"],
+                                       torch.tensor(f["times"]), ph["x"], ph["pos"], ph["norm"], ph["batch"])
+    tight = dict(rtol=1e-5, atol=2e-5)
+    assert_close(v, f["pred_node"], "logits_node", **tight)
+    assert_close(pos, f["pred_pos"], "pos", **tight)
+    assert_close(e, f["pred_edge"], "logits_edge", **tight)
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference not mounted")
+def test_oracle_sampling_entry_pieces_match_unmodified_reference_live(sd):
+    """D2 / T4 / T5 pieces of PhoreDiff.sample: the atom-count interval of sample_nodes, sample_init under an injected
+    uniform draw, and the guidance gradient (autograd of the reference's energies) for a single pharmacophore."""
+    import yaml
+    from oracle.shims.install import EasyDict, install
+    install()
+    import models.common as rc
+    from models.diffusion import PhoreDiff
+    from utils.sample_utils import compute_batch_atom_prox_loss, compute_batch_center_prox_loss, make_edge_data
+    cfg = EasyDict(yaml.safe_load(open("/root/reference/configs/train_lig-phore.yml")))
+    cfg.model.phore_feat_dim += 2
+    ref = PhoreDiff(cfg.model, "zinc_300").eval()
+    ref.load_state_dict(sd, strict=True)
+    # ---- T4
+    g = torch.Generator().manual_seed(4)
+    for trans, K in ((ref.node_transition, 12), (ref.edge_transition, 6)):
+        u = torch.rand(50, K, generator=g)
+        orig = torch.rand_like
+        torch.rand_like = lambda x: u.to(x.dtype)
+        try:
+            cls, onehot, log_vt = trans.sample_init(50)
+        finally:
+            torch.rand_like = orig
+        got_cls, got_log = O.sample_init(trans.init_prob, u)
+        assert torch.equal(got_cls, cls) and torch.allclose(got_log, log_vt.float())
+    # ---- D2: interval of sample_nodes (diffusion.py:356-380) through the oracle's encoder + count heads
+    import numpy as np
+    x, pos, _ = O.synthetic_phore(np.random.default_rng(3), 7, 30)
+    x, pos = torch.from_numpy(x), torch.from_numpy(pos)
+    batch = torch.zeros(x.shape[0], dtype=torch.long)
+    cl, cu = O.predict_atom_count(sd, O.phore_encode(sd, x, pos, batch), batch, x, 1)
+    lo, hi = int((cl * 74 + 4).round()), int((cu * 74 + 4).round())
+    from oracle.shims.install import HeteroData
+    data = HeteroData()
+    data["phore"].x, data["phore"].pos = x, pos
+    seen = []
+    import utils.sample_utils as su
+    import models.diffusion as md
+    orig = md.sample_from_interval
+    md.sample_from_interval = lambda l, u_, bs, mode="uniform", scale=4.0: (seen.append((l, u_)), orig(l, u_, bs, mode=mode, scale=scale))[1]
+    try:
+        with torch.no_grad():
+            ref.sample_nodes(data, 8, "cpu")
+    finally:
+        md.sample_from_interval = orig
+    assert seen == [(lo, hi)]
+    # ---- T5: closed-form gradient against autograd of the reference's energies (sample_utils.py:135-165)
+    na = torch.tensor([5, 7, 4])
+    ei, eb = make_edge_data(na)
+    bn = torch.repeat_interleave(torch.arange(3), na)
+    g = torch.Generator().manual_seed(8)
+    xt = (torch.randn(int(na.sum()), 3, generator=g) * 1.5).requires_grad_(True)
+    onehot = F.one_hot(torch.randint(0, 6, (ei.shape[1],), generator=g), 6).float()
+    centre = torch.randn(3, generator=g)
+    e1 = compute_batch_atom_prox_loss(xt, bn, onehot, ei, eb, min_d=1.2, max_d=1.9)
+    e2 = compute_batch_center_prox_loss(xt, bn, centre)
+    want = torch.autograd.grad(e1, xt)[0] + torch.autograd.grad(e2, xt)[0]
+    got = O.guidance_grad(xt.detach(), bn, onehot.argmax(-1), ei, eb, [dict(type="atom_prox", min_d=1.2, max_d=1.9), dict(type="center_prox")], centre, 3)
+    assert_close(got, want, "guidance gradient", rtol=1e-5, atol=1e-6)

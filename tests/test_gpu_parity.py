@@ -364,7 +364,7 @@ def test_sampler_cuda_graph_equals_eager_and_is_deterministic(model, dev):
     x, pos, nrm = O.synthetic_phore(rng, 7)
     data = PhoreData(torch.from_numpy(x), torch.from_numpy(pos), torch.from_numpy(nrm), center=torch.tensor([1.0, 2.0, 3.0]))
     na = torch.tensor([9, 12, 10, 11])
-    kw = dict(ligand_num_atoms=na, seed=1234, num_steps=4)
+    kw = dict(ligand_num_atoms=na, seed=1234, num_steps=4, traj_layout="reference")
     r_graph = m.sample(data, 4, dev, use_cuda_graph=True, **kw)
     r_eager = m.sample(data, 4, dev, use_cuda_graph=False, **kw)
     r_again = m.sample(data, 4, dev, use_cuda_graph=True, **kw)
@@ -378,6 +378,16 @@ def test_sampler_cuda_graph_equals_eager_and_is_deterministic(model, dev):
     assert torch.equal(ei.cpu(), want_ei) and torch.equal(eb.cpu(), want_eb) and torch.equal(n_.cpu(), na)
     other = m.sample(data, 4, dev, ligand_num_atoms=na, seed=99, num_steps=4)
     assert not torch.equal(other["traj"][1][:5], pos_traj[:5])
+    # default layout: class-index trajectories that index like the reference's one-hot tensors (results.ClassTrajectory)
+    from phoregen_b200 import results as R
+    r_c = m.sample(data, 4, dev, use_cuda_graph=True, **{**kw, "traj_layout": "compact"})
+    assert isinstance(r_c["traj"][0], R.ClassTrajectory) and r_c["traj"][2].shape == edge_traj.shape
+    assert torch.equal(r_c["traj"][0].dense(), node_traj) and torch.equal(r_c["traj"][2].dense(), edge_traj)
+    host = {k: [v.cpu() for v in vals] for k, vals in r_c.items()}                     # sample_all.py:104
+    ref_host = {k: [v.cpu() for v in vals] for k, vals in r_graph.items()}
+    for mc, mr in zip(R.unbatch_data(host, 4), R.unbatch_data(ref_host, 4)):
+        for k in (0, 2):
+            assert torch.equal(mc["traj"][k][3], mr["traj"][k][3]) and len(mc["traj"][k]) == 1001  # sample_all.py:138-143
 
 
 def test_sampler_statistics_of_philox_draws(model, dev):
@@ -422,13 +432,13 @@ def test_sample_with_guidance_and_atom_count_head(model, dev):
     assert res["pred"][0].shape == (Nl, 12) and res["pred"][1].shape == (Nl, 3)
     assert all(bool(torch.isfinite(t).all()) for t in res["pred"])
     # guidance changes the position update and only that
-    res0 = m.sample(data, 3, dev, ligand_num_atoms=n_atoms, seed=11, num_steps=1)
-    res1 = m.sample(data, 3, dev, ligand_num_atoms=n_atoms, pos_guidance_opt=opts, seed=11, num_steps=1)
+    res0 = m.sample(data, 3, dev, ligand_num_atoms=n_atoms, seed=11, num_steps=1, traj_layout="reference")
+    res1 = m.sample(data, 3, dev, ligand_num_atoms=n_atoms, pos_guidance_opt=opts, seed=11, num_steps=1, traj_layout="reference")
     assert torch.equal(res0["traj"][0][:2], res1["traj"][0][:2]) and torch.equal(res0["traj"][2][:2], res1["traj"][2][:2])
     assert not torch.equal(res0["traj"][1][1], res1["traj"][1][1])
     # eager and graph replay agree with guidance on
-    r_e = m.sample(data, 3, dev, ligand_num_atoms=n_atoms, pos_guidance_opt=opts, seed=11, num_steps=3, use_cuda_graph=False)
-    r_g = m.sample(data, 3, dev, ligand_num_atoms=n_atoms, pos_guidance_opt=opts, seed=11, num_steps=3, use_cuda_graph=True)
+    r_e = m.sample(data, 3, dev, ligand_num_atoms=n_atoms, pos_guidance_opt=opts, seed=11, num_steps=3, use_cuda_graph=False, traj_layout="reference")
+    r_g = m.sample(data, 3, dev, ligand_num_atoms=n_atoms, pos_guidance_opt=opts, seed=11, num_steps=3, use_cuda_graph=True, traj_layout="reference")
     for a_, b_ in zip(r_e["traj"], r_g["traj"]):
         assert torch.equal(a_, b_)
 
@@ -611,3 +621,131 @@ def test_compute_loss_value_matches_oracle_forward(model, dev):
     assert not got_total.requires_grad
     for k in want:
         assert got[k] == pytest.approx(want[k], rel=2e-3, abs=2e-4), k
+
+
+# ---------------------------------------------------------------- D2 / O2: atom-count heads on the device
+def test_atom_count_intervals_match_oracle(model, dev):
+    """pg_atom_count against the oracle's predict_atom_count / sample_nodes interval (diffusion.py:148-163,356-380) for a
+    batch of pharmacophores of different sizes, with and without exclusion spheres: floats within tolerance, the integer
+    interval exact wherever the oracle's value is not within 1e-3 of a rounding boundary."""
+    m, sd = model
+    rng = np.random.default_rng(17)
+    xs, ps, bs = [], [], []
+    for g, (p, n_ex) in enumerate([(6, 0), (8, 40), (3, 94), (7, 0), (12, 5)]):
+        x, pos, _ = O.synthetic_phore(rng, p, n_ex)
+        xs.append(x); ps.append(pos); bs.append(np.full(x.shape[0], g))
+    x, pos, batch = torch.from_numpy(np.concatenate(xs)), torch.from_numpy(np.concatenate(ps)), torch.from_numpy(np.concatenate(bs))
+    lo, hi = m.atom_count_intervals(x, pos, batch.to(dev), 5, dev)
+    h_p = O.phore_encode(sd, x, pos, batch)
+    cl, cu = O.predict_atom_count(sd, h_p, batch, x, 5)
+    from phoregen_b200.engine import BatchPlan
+    plan = BatchPlan(np.full(5, 2, np.int32), torch.bincount(batch).numpy(), dev, edge_order=1)
+    pm = m.packed(dev)
+    got_l, got_u = plan.atom_count(pm, plan.phore_encode(pm, x.to(dev), pos.to(dev)), x.to(dev))
+    assert_close(got_l, cl, "count_l")
+    assert_close(got_u, cu, "count_u")
+    for got, want in ((lo, cl), (hi, cu)):
+        v = want[:, 0] * 74 + 4
+        safe = (v - v.floor() - 0.5).abs() > 1e-3
+        assert torch.equal(got.cpu()[safe].long(), v.round().long()[safe])
+    # the single-pharmacophore entry point of the reference (sample_nodes) sees the same interval
+    from phoregen_b200.testing import PhoreData
+    d0 = PhoreData(torch.from_numpy(xs[1]), torch.from_numpy(ps[1]), torch.zeros(len(xs[1]), 3))
+    assert m.sample_nodes(d0, 4, dev, return_interval=True) == (int(lo[1]), int(hi[1]))
+    n = m.sample_nodes(d0, 64, dev)
+    assert int(n.min()) >= int(lo[1]) and int(n.max()) <= int(hi[1])
+    # per-graph draws on the device stay inside their own interval, in both modes
+    for mode in ("uniform", "normal"):
+        n = m.sample_from_intervals(lo, hi, mode)
+        assert bool(((n >= lo) & (n <= hi)).all())
+
+
+def test_initial_state_matches_reference_sample_init_under_supplied_uniforms(model, dev):
+    """T4 (transition.py:65-69,331-339): the sampler's categorical initial state is arg-max(gumbel(u) + log init_prob); with
+    the uniforms it drew itself (same generator, same order) the oracle's sample_init gives the same classes."""
+    from phoregen_b200.diffusion import TrajectorySampler
+    m, sd = model
+    b = O.synthetic_batch(5, 3, n_atoms=(5, 9))
+    s = TrajectorySampler(m, None, 3, dev, ligand_num_atoms=b["num_atoms"], save_traj=False, seed=77, use_cuda_graph=False, phore_batch=b["phore"])
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(77)
+    Nl, Eb = s.plan.Nl, s.plan.Eb
+    z = torch.randn(Nl, 3, device=dev, generator=gen)
+    u_node = torch.rand(Nl, 12, device=dev, generator=gen)
+    u_edge = torch.rand(Eb, 6, device=dev, generator=gen)
+    for trans, u, cls, onehot, logp in ((m.node_transition, u_node, s.node_cls, s.h_node, s.log_node), (m.edge_transition, u_edge, s.edge_cls, s.h_edge, s.log_edge)):
+        want_cls, want_log = O.sample_init(trans.init_prob, u.cpu())
+        assert torch.equal(cls.cpu().long(), want_cls)
+        assert torch.equal(onehot.cpu().argmax(-1), want_cls) and torch.allclose(logp.cpu(), want_log)
+    assert torch.equal(s.pos, z)          # centre 0 for pharmacophore batches without centres
+
+
+# ---------------------------------------------------------------- multi-pharmacophore batches: guidance, centres, devices
+def test_guidance_per_graph_centres_match_oracle(model, dev):
+    """T5 with one pharmacophore per graph (what a configs[2] batch needs): atom_prox + center_prox with each graph's own
+    non-EX centre, accumulated over the list entries like diffusion.py:479-501, against the oracle's autograd."""
+    from phoregen_b200.engine import BatchPlan
+    g = torch.Generator().manual_seed(3)
+    na = np.array([6, 9, 4], dtype=np.int32)
+    plan = BatchPlan(na, np.array([5, 7, 3], dtype=np.int32), dev, edge_order=0)
+    ei, eb = O.make_edge_data(torch.tensor(na))
+    pos = torch.randn(int(na.sum()), 3, generator=g) * 1.5
+    cls = torch.randint(0, 6, (ei.shape[1],), generator=g)
+    centres = torch.randn(3, 3, generator=g)
+    batch_node = torch.repeat_interleave(torch.arange(3), torch.tensor(na).long())
+    opts = [dict(type="atom_prox", min_d=1.2, max_d=1.9), dict(type="center_prox"), dict(type="atom_prox", min_d=0.5, max_d=1.0)]
+    got = plan.guidance_grad(pos.to(dev), cls.int().to(dev), opts, centres.to(dev))
+    want = torch.zeros_like(pos)
+    for o in opts:
+        want += O.guidance_grad(pos, batch_node, cls, ei, eb, [o], centres, 3)
+    assert_close(got, want, "guidance gradient (per-graph centres, three entries)", rtol=1e-4, atol=1e-6)
+
+
+def test_sampler_on_explicit_device_and_per_graph_centres(model, dev):
+    """sample(..., device) launches on the plan's GPU whatever device is current (engine._on_device), and a pharmacophore
+    batch with per-graph centres returns positions in each graph's own frame."""
+    from phoregen_b200.diffusion import TrajectorySampler
+    m, _ = model
+    b = O.synthetic_batch(8, 3, n_atoms=(5, 8))
+    ph = dict(b["phore"])
+    s0 = TrajectorySampler(m, None, 3, dev, ligand_num_atoms=b["num_atoms"], save_traj=False, seed=5, use_cuda_graph=True, phore_batch=ph)
+    s0.run(3)
+    ph["center"] = torch.tensor([[1.0, 0.0, 0.0], [0.0, 2.0, 0.0], [0.0, 0.0, 3.0]])
+    s1 = TrajectorySampler(m, None, 3, dev, ligand_num_atoms=b["num_atoms"], save_traj=True, seed=5, use_cuda_graph=True, phore_batch=ph)
+    assert s1.run(3) == 3
+    shift = ph["center"].to(dev)[s1.batch_node]
+    # same draws: the centred-frame state differs only by the initial shift's propagation, the returned frame adds it back
+    r0, r1 = s0.results(), s1.results()
+    assert torch.allclose(r1["traj"][1][0], s1.traj_pos[0]) and r1["pred"][1].shape == r0["pred"][1].shape
+    assert torch.allclose(s1.traj_pos[3], s1.pos + shift, atol=1e-6)
+    with pytest.raises(ValueError):
+        TrajectorySampler(m, None, 3, dev, ligand_num_atoms=b["num_atoms"], phore_batch=dict(ph, batch=ph["batch"].flip(0)))
+    if torch.cuda.device_count() > 1:
+        m1 = build_model(torch.device("cuda:1"))[0]
+        out = m1.sample(None, 3, "cuda:1", ligand_num_atoms=b["num_atoms"], seed=5, num_steps=2, phore_batch=b["phore"], save_traj=False)
+        assert out["pred"][1].device == torch.device("cuda:1") and bool(torch.isfinite(out["pred"][1]).all())
+
+
+def test_plan_cache_distinguishes_batches_with_equal_sizes(model, dev):
+    """two batches with identical ligand topology and the same TOTAL number of pharmacophore nodes but different
+    per-graph counts ([5,7] vs [7,5]) must not share a cached plan."""
+    m, sd = model
+    rng = np.random.default_rng(2)
+    def batch(p0, p1):
+        b = O.synthetic_batch(41, 2, n_atoms=6)
+        xs, ps, ns, bs = [], [], [], []
+        r = np.random.default_rng(9)
+        for g, p in enumerate((p0, p1)):
+            x, pos, nrm = O.synthetic_phore(r, p)
+            xs.append(x); ps.append(pos); ns.append(nrm); bs.append(np.full(p, g))
+        b["phore"] = dict(x=torch.from_numpy(np.concatenate(xs)), pos=torch.from_numpy(np.concatenate(ps)),
+                          norm=torch.from_numpy(np.concatenate(ns)), batch=torch.from_numpy(np.concatenate(bs)))
+        return b
+    for p0, p1 in ((5, 7), (7, 5)):
+        b = batch(p0, p1)
+        ph = b["phore"]
+        want = O.phorediff_forward(sd, b["h_node"], b["pos"], b["batch_node"], b["h_edge"], b["edge_index"], b["batch_edge"],
+                                   torch.tensor([300, 20]), ph["x"], ph["pos"], ph["norm"], ph["batch"])
+        got = _forward(m, b, [300, 20], dev)          # same model object: the second call must rebuild the plan
+        for g_, w_, what in zip(got[:3], want[:3], ("logits_node", "pos", "logits_edge")):
+            assert_close(g_, w_, f"{what} with phore counts {(p0, p1)}", rtol=2e-3, atol=2e-4)

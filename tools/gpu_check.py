@@ -45,3 +45,27 @@ for name in ("forward_small.pt", "forward_n30.pt", "forward_ex.pt"):
         plan = BatchPlan(na, npn, dev, ref_edge_index=to(b["edge_index"]))
         hp = plan.phore_encode(pm, to(ph["x"]), to(ph["pos"]))
         print("  h_phore_emb", report(hp, f["h_phore_emb"]))
+
+big = load_golden("forward_big.pt")["cases"]
+for name, f in big.items():
+    b = O.synthetic_batch(f["seed"], f["n_graphs"], n_atoms=f["n_atoms"], p_choices=f["p_choices"], pos_scale=f["pos_scale"])
+    ph = b["phore"]
+    to = lambda t: t.to(dev)
+    out = model(to(b["h_node"]), to(b["pos"]), to(b["batch_node"]), to(b["h_edge"]), to(b["edge_index"]), to(b["batch_edge"]),
+                torch.tensor(f["times"], dtype=torch.long, device=dev), to(ph["x"]), to(ph["pos"]), to(ph["norm"]), to(ph["batch"]))
+    print("big", name, "| node", report(out[0], f["pred_node"]), "| pos", report(out[1], f["pred_pos"]), "| edge", report(out[2], f["pred_edge"]))
+
+# denoiser drop-in outputs (h, h_bond, x after the 6 layers) against the reference's hooked tensors
+f = load_golden("forward_small.pt")
+b = O.synthetic_batch(f["seed"], f["n_graphs"], n_atoms=f["n_atoms"])
+ph = b["phore"]
+stages = []
+O.phorediff_forward(sd, b["h_node"], b["pos"], b["batch_node"], b["h_edge"], b["edge_index"], b["batch_edge"], torch.tensor(f["times"]),
+                    ph["x"], ph["pos"], ph["norm"], ph["batch"], stages=stages)
+s0 = stages[0]
+to = lambda t: t.to(dev)
+out = model.denoiser(h=to(s0["h_all"]), x=to(s0["pos_all"]), group_idx=None, bond_index=to(s0["bond_index_in_all"]), h_bond=to(s0["h_edge"]),
+                     mask_ligand=to(s0["mask_ligand"]), mask_ligand_atom=to(s0["mask_ligand"]), batch=to(s0["batch_all"]),
+                     phore_norm=to(ph["norm"]), packed=pm)
+h5, hb5, x5 = f["layer5"]
+print("layer5 | h", report(out["h"], h5), "| h_bond", report(out["h_bond"], hb5), "| x", report(out["x"], x5))
