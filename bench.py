@@ -2,16 +2,22 @@
 """Benchmark of the PhoreGen sampling hot path (BASELINE.json metric: molecules/sec for a full 1000-step reverse
 trajectory; denoiser step ms).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config1|config2|config4|ragged|ex70]
 
 A "step" is one reverse-diffusion step (PhoreDiff.forward + categorical/Gaussian posterior update, the loop body of
-reference models/diffusion.py:432-517) over one batch of synthetic molecules.  Workload at N=1 is BASELINE.json
-configs[1]: 1024 molecules x 30 heavy atoms, 6-8 pharmacophore features each, random-init weights, seed 2032.
-Every step of a trajectory has identical shapes and executes identical work, so
+reference models/diffusion.py:432-517) over one batch of synthetic molecules.  Every step of a trajectory has identical
+shapes and executes identical work, so
     molecules/sec = molecules / (1000 * seconds_per_step)
 and K timed steps measure it without running all 1000 (``--full-trajectory`` runs them all).
-For N>1 (torchrun) each rank runs its own 1024 molecules (weak scaling, no collective inside the loop) and the
-sampled molecules are gathered to rank 0 once, inside the timed region.
+
+Workloads:
+  config1 (default)  BASELINE.json configs[1]: 1024 molecules/GPU x 30 heavy atoms, 6-8 pharmacophore features, seed 2032.
+                     N>1 (torchrun): every rank its own 1024 molecules (weak scaling), one final gather inside the timed region.
+  ragged             as config1 with n ~ round(N(30, 3)) clipped to [20, 40] (exercises the mixed single-/multi-chunk kernels)
+  ex70               as config1 plus 70 exclusion spheres per pharmacophore (the median of the shipped .phore files)
+  config4            BASELINE.json configs[4]: 80 heavy atoms, 12 pharmacophore features, molecules sized to --hbm-gb of work space
+  config2            BASELINE.json configs[2]: 256 pharmacophores x 100 samples = 25,600 molecules as ONE job, dealt to the ranks
+                     (strong scaling), ragged batches of <= 1024, final gather; a step = one reverse step of every batch.
 """
 import argparse
 import json
@@ -28,6 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 TRAJ_STEPS = 1000
+REF_ROOT = "/root/reference"
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -50,9 +57,9 @@ def f_ref_flops(n, p):
 def f_exec_trip_flops(n):
     """bf16 tensor FLOPs the tcgen05 triplet kernel actually issues per molecule-layer (DESIGN.md 'Triplet kernel'):
     per 128-row tile (4 segments x 32 lanes) 3 MMAs M128 N256 K16 (angle slice, bf16x3) + 2 x 24 MMAs M128 N128 K16
-    (second Linear of the key / value MLPs, bf16x3); ceil((n-1)/4) tiles per ligand atom.  Includes the padding rows and
-    the x3 of the hi/lo split, so it is the work the tensor pipe really performs."""
-    tiles = n * ((n - 1 + 3) // 4) * max((n - 2 + 31) // 32, 1)      # segments longer than 32 rows: one tile per 32-row chunk
+    (second Linear of the key / value MLPs, bf16x3); ceil((n-1)/4) segment groups per ligand atom, one tile per 32-row
+    chunk of a group.  Includes the padding rows and the x3 of the hi/lo split: the work the tensor pipe really performs."""
+    tiles = n * ((n - 1 + 3) // 4) * max((n - 2 + 31) // 32, 1)
     macs_per_tile = 3 * 128 * 256 * 16 + 48 * 128 * 128 * 16
     return 2.0 * tiles * macs_per_tile
 
@@ -104,65 +111,130 @@ def load_peaks():
     return {"bf16_tflops_sustained": 1400.0, "bf16_tflops": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
-def workload(seed, n_graphs, n_atoms):
-    from phoregen_b200.synthetic import synthetic_batch
-    return synthetic_batch(seed, n_graphs, n_atoms=n_atoms)
+WORKLOADS = {
+    # name: (description, atoms, p_choices, n_ex)
+    "config1": ("configs[1]: {G} molecules/GPU x 30 heavy atoms, 6-8 pharmacophore features", 30, (6, 7, 8), 0),
+    "ragged": ("configs[1] secondary: {G} molecules/GPU x round(N(30,3)) in [20,40] heavy atoms, 6-8 pharmacophore features", None, (6, 7, 8), 0),
+    "ex70": ("configs[1] realistic variant: {G} molecules/GPU x 30 heavy atoms, 6-8 pharmacophore features + 70 exclusion spheres", 30, (6, 7, 8), 70),
+    "config4": ("configs[4] stress: {G} molecules/GPU x 80 heavy atoms (full O(n^2) bond edges, 493k triplets each), 12 pharmacophore features", 80, (12,), 0),
+}
 
 
-# ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
-def cpu_reference_step_time(n_mol, n_atoms, steps, warmup, seed=2032):
-    """Times the reference formulation's reverse step on the host cores: the oracle port of
-    models/diffusion.py:432-517 (torch fp32, all host threads)."""
-    from oracle import phoregen_oracle as O
+def ragged_sizes(seed, G):
+    rng = np.random.default_rng(seed)
+    return np.clip(np.rint(rng.normal(30.0, 3.0, size=G)), 20, 40).astype(np.int64)
+
+
+def make_workload(name, seed, G, atoms=None):
+    """Seeded synthetic batch of the named shape (phoregen_b200.synthetic: pure numpy PCG64)."""
+    from phoregen_b200.synthetic import sampling_edges, synthetic_batch
+    _, n, p_choices, n_ex = WORKLOADS[name]
+    n = atoms or n
+    if name != "ragged":
+        return synthetic_batch(seed, G, n_atoms=n, p_choices=p_choices, n_ex=n_ex)
+    b = synthetic_batch(seed, G, n_atoms=30, p_choices=p_choices, n_ex=n_ex)          # pharmacophores of the seed; resize the ligands
+    na = ragged_sizes(seed, G)
+    rng = np.random.default_rng(seed + 1)
+    Nl = int(na.sum())
+    ei, eb = sampling_edges(na)
+    import torch.nn.functional as F
+    b.update(num_atoms=torch.from_numpy(na), batch_node=torch.from_numpy(np.repeat(np.arange(G), na).astype(np.int64)), edge_index=ei,
+             batch_edge=eb, h_node=F.one_hot(torch.from_numpy(rng.integers(0, 12, size=Nl)), 12).float(),
+             h_edge=F.one_hot(torch.from_numpy(rng.integers(0, 6, size=ei.shape[1])), 6).float(),
+             pos=torch.from_numpy(rng.normal(0.0, 1.0, size=(Nl, 3)).astype(np.float32)))
+    return b
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def _seeded_state_dict():
+    """The 641-key state_dict with the reproducible weights (numpy PCG64).  Importing the package does not map the CUDA
+    library (phoregen_b200._lib binds on first use), and nothing here calls into it."""
     from phoregen_b200.diffusion import PhoreDiff
     from phoregen_b200.testing import MODEL_CONFIG, random_state_dict
+    return random_state_dict(PhoreDiff(MODEL_CONFIG, "zinc_300"), 0)
+
+
+def cpu_reference_step_time(n_mol, workload, steps, warmup, seed=2032, atoms=None, prefer_reference=True):
+    """Times the reference's reverse step (models/diffusion.py:432-517) on the host cores, all threads, fp32.
+    With /root/reference present (the build container) the UNMODIFIED reference runs through oracle/shims
+    (kind "reference-via-shims"); on the GPU box, where the Python reference cannot travel, the oracle port of the same
+    loop body runs (kind "port").  -> (seconds per step, threads, kind)"""
     torch.set_num_threads(os.cpu_count())
-    sd = random_state_dict(PhoreDiff(MODEL_CONFIG, "zinc_300"), 0)
-    b = O.synthetic_batch(seed, n_mol, n_atoms=n_atoms)
+    sd = _seeded_state_dict()
+    b = make_workload(workload, seed, n_mol, atoms)
+    ph = b["phore"]
     g = torch.Generator().manual_seed(seed)
     Nl, Eb = b["h_node"].shape[0], b["h_edge"].shape[0]
     st = dict(h_node=b["h_node"], pos=b["pos"], h_edge=b["h_edge"], log_node=torch.log(b["h_node"].clamp(min=1e-30)),
               log_edge=torch.log(b["h_edge"].clamp(min=1e-30)))
-    topo = dict(batch_node=b["batch_node"], edge_index=b["edge_index"], batch_edge=b["batch_edge"], n_graphs=n_mol)
     times = []
+    use_ref = prefer_reference and os.path.isdir(os.path.join(REF_ROOT, "models"))
+    if use_ref:
+        import yaml
+        from oracle.shims.install import EasyDict, install
+        install()
+        import models.common as rc
+        from models.diffusion import PhoreDiff as RefPhoreDiff
+        cfg = EasyDict(yaml.safe_load(open(os.path.join(REF_ROOT, "configs/train_lig-phore.yml"))))
+        cfg.model.phore_feat_dim += 2
+        ref = RefPhoreDiff(cfg.model, "zinc_300").eval()
+        ref.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            for i in range(warmup + steps):
+                t = torch.full((n_mol,), 999 - i, dtype=torch.long)
+                t0 = time.perf_counter()
+                pn, pp, pe, _ = ref(st["h_node"], st["pos"], b["batch_node"], st["h_edge"], b["edge_index"], b["batch_edge"], t,
+                                    ph["x"], ph["pos"], ph["norm"], ph["batch"])
+                ln = ref.node_transition.q_v_posterior(torch.log_softmax(pn, -1), st["log_node"], t, b["batch_node"], v0_prob=True)
+                le = ref.edge_transition.q_v_posterior(torch.log_softmax(pe, -1), st["log_edge"], t, b["batch_edge"], v0_prob=True)
+                nc, ec = rc.log_sample_categorical(ln), rc.log_sample_categorical(le)
+                xp = ref.pos_transition.get_prev_from_recon(x_t=st["pos"], x_recon=pp, t=t, batch=b["batch_node"])
+                st = dict(h_node=ref.node_transition.onehot_encode(nc), pos=xp, h_edge=ref.edge_transition.onehot_encode(ec), log_node=ln, log_edge=le)
+                if i >= warmup:
+                    times.append(time.perf_counter() - t0)
+        return float(np.mean(times)), torch.get_num_threads(), "reference-via-shims"
+    from oracle import phoregen_oracle as O
+    topo = dict(batch_node=b["batch_node"], edge_index=b["edge_index"], batch_edge=b["batch_edge"], n_graphs=n_mol)
     with torch.no_grad():
         for i in range(warmup + steps):
             d = dict(u_node=torch.rand(Nl, 12, generator=g), u_edge=torch.rand(Eb, 6, generator=g), z_pos=torch.randn(Nl, 3, generator=g))
             t0 = time.perf_counter()
-            st, _ = O.reverse_step(sd, st, 999 - i, topo, b["phore"], d)
+            st, _ = O.reverse_step(sd, st, 999 - i, topo, ph, d)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
-    return float(np.mean(times)), torch.get_num_threads()
+    return float(np.mean(times)), torch.get_num_threads(), "port"
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    wl = args.workload if args.workload in WORKLOADS else "config1"
     n_mol = args.cpu_molecules
-    sec, cores = cpu_reference_step_time(n_mol, args.atoms, args.steps, args.warmup)
+    atoms = args.atoms or WORKLOADS[wl][1] or 30
+    sec, cores, kind = cpu_reference_step_time(n_mol, wl, args.steps, args.warmup, atoms=args.atoms)
     val = n_mol / (sec * TRAJ_STEPS)
-    sample = f"{n_mol} molecules x {args.atoms} atoms per step, {args.steps} timed steps of the 1000-step trajectory"
+    sample = f"{n_mol} molecules of the {wl} shape per step, {args.steps} timed steps of the 1000-step trajectory"
+    from phoregen_b200 import _lib
     line = {
         "impl": "reference", "metric": "molecules/sec (full 1000-step reverse trajectory)", "value": val, "unit": "molecules/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"configs[1]: {args.atoms}-atom molecules, 6-8 pharmacophore features, random-init weights, seed 2032",
-                   "trajectory_steps": TRAJ_STEPS, "note": "reference formulation (oracle port of models/diffusion.py loop body) on host cores"},
-        "cpu_baseline": {"value": val, "unit": "molecules/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOADS[wl][0].format(G=n_mol) + f", random-init weights, seed 2032 ({atoms} atoms)",
+                   "trajectory_steps": TRAJ_STEPS,
+                   "note": ("unmodified reference models/diffusion.py forward + transitions through oracle/shims" if kind == "reference-via-shims"
+                            else "oracle port of the reference loop body (models/diffusion.py:432-517); the Python reference is not on this box")
+                           + ", all host threads", "repo_cuda_library_mapped": bool(_lib.lib.loaded)},
+        "cpu_baseline": {"value": val, "unit": "molecules/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
 
 
-# ------------------------------------------------------------------------------------------------ our arm
-def run_ours(args):
+# ------------------------------------------------------------------------------------------------ our arm: common pieces
+def _setup():
     import torch.distributed as dist
-    from phoregen_b200.diffusion import PhoreDiff, TrajectorySampler
-    from phoregen_b200.distributed import gather_results, pack_results
-    from phoregen_b200.testing import MODEL_CONFIG, random_state_dict
-
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
@@ -172,57 +244,133 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    G = args.molecules
+    from phoregen_b200.diffusion import PhoreDiff
+    from phoregen_b200.testing import MODEL_CONFIG, random_state_dict
     model = PhoreDiff(MODEL_CONFIG, "zinc_300")
     model.load_state_dict(random_state_dict(model, 0), strict=True)
-    model = model.to(dev).eval()
-    b = workload(2032 + rank, G, args.atoms)
+    return rank, world, local_rank, dev, model.to(dev).eval()
+
+
+def _barrier(world, dev):
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+
+
+def _max_over_ranks(ms, world, dev):
+    import torch.distributed as dist
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def stage(msg, dev):                      # progress markers on stderr (PG_BENCH_TRACE=1): where a slow or stuck run is
+    if os.environ.get("PG_BENCH_TRACE"):
+        torch.cuda.synchronize(dev)
+        print(f"[bench] {msg}", file=sys.stderr, flush=True)
+
+
+def hbm_kernels(plan, smp, dev, peaks, reps=20):
+    """HBM-class kernels of the step (north_star: graph build, transition, guidance): CUDA-event time of `reps`
+    back-to-back launches, algorithmic bytes (every operand read / written once) / time, against the measured copy
+    bandwidth.  Together they are ~0.5 % of the step; the fractions say how far each is from the bandwidth roofline."""
+    pm = smp.pm
+    out = {}
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
+    Nl, Eb, N, Ek, G = plan.Nl, plan.Eb, plan.N, plan.Ek, plan.G
+    ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+    log_e, log_n = smp.log_edge.clone(), smp.log_node.clone()
+    oh_e, oh_n = torch.empty_like(smp.h_edge), torch.empty_like(smp.h_node)
+    cl_e, cl_n = torch.empty_like(smp.edge_cls), torch.empty_like(smp.node_cls)
+    xo, gr = torch.empty_like(smp.pos), torch.empty_like(smp.pos)
+    xctx = torch.randn(N, 3, device=dev)
+    cen = torch.zeros(G, 3, device=dev)
+    opts = [dict(type="atom_prox", min_d=1.2, max_d=1.9), dict(type="center_prox")]
+    cases = {
+        # bytes: pred + log_vt read, log_vt + onehot written (K f32 each), class int32 written, row->graph int32 read
+        "categorical_step_kernel<6> (edges)": (lambda: plan.categorical_step(pm, "edge", smp.pred[2], log_e, smp.time_step, seed=1, step_counter=ctr,
+                                                                             onehot=oh_e, cls=cl_e), Eb * (4 * 6 * 4 + 8)),
+        "categorical_step_kernel<12> (atoms)": (lambda: plan.categorical_step(pm, "node", smp.pred[0], log_n, smp.time_step, seed=1, step_counter=ctr,
+                                                                              onehot=oh_n, cls=cl_n), Nl * (4 * 12 * 4 + 8)),
+        # x_t, x_recon read, x_prev written (3 f32 each), row->graph read
+        "position_step_kernel": (lambda: plan.position_step(pm, smp.pos, smp.pred[1], smp.time_step, seed=1, step_counter=ctr, out=xo), Nl * (3 * 12 + 4)),
+        # coordinates read once, one int64 pair per kNN edge written by the exporting entry point (pg_knn_graph)
+        "knn_kernel<0> (k=32 joint graph, exporting entry point)": (lambda: plan.knn_graph(xctx, 0), N * 12 + Ek * 16),
+        # positions + sampled edge classes (through the edge permutation) read, gradient written; two launches (one per drift entry)
+        "guidance_kernel x2 (atom_prox + center_prox)": (lambda: plan.guidance_grad(smp.pos, smp.edge_cls, opts, cen, out=gr), 2 * Nl * 24 + Eb * 8),
+    }
+    for name, (fn, nbytes) in cases.items():
+        ms = timed(fn)
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out[name] = {"ms": ms, "algorithmic_bytes": int(nbytes), "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]}
+    return {"bound": "hbm", "peak": peaks["hbm_gbs"], "unit": "GB/s", "peak_source": peaks["source"] + ", copy bandwidth", "kernels": out,
+            "note": "timed through the Python wrappers (allocation of small outputs included for knn_graph); kernels of 10-60 us on <= 100 MB are "
+                    "launch-latency bound, none is more than 0.3 % of the step"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm: one batch per GPU
+def run_ours(args):
+    import torch.distributed as dist
+    from phoregen_b200.diffusion import TrajectorySampler
+    from phoregen_b200.distributed import gather_results, pack_results
+    rank, world, local_rank, dev, model = _setup()
+    wl = args.workload
+    desc, n_fixed, _, n_ex = WORKLOADS[wl]
+    n_fixed = args.atoms or n_fixed
+    G = args.molecules
+    if wl == "config4" and not args.molecules_set:
+        # size the batch so that the plan's work space is about --hbm-gb (~40 MB of fp32 work space per 80-atom molecule)
+        import ctypes
+        from phoregen_b200._lib import lib
+        one_n, one_p = (ctypes.c_int32 * 1)(n_fixed), (ctypes.c_int32 * 1)(12)
+        per = int(lib.pg_plan_workspace_bytes(1, one_n, one_p))
+        G = max(1, int(args.hbm_gb * 2 ** 30 // per))
+    b = make_workload(wl, 2032 + rank, G, args.atoms)
     ph = b["phore"]
+    n_mean = float(b["num_atoms"].float().mean())
     smp = TrajectorySampler(model, None, G, dev, ligand_num_atoms=b["num_atoms"], save_traj=False, seed=2032 + rank,
                             use_cuda_graph=True, phore_batch=ph)
     plan = smp.plan
     p_mean = plan.P / G
-    K, W = args.steps, args.warmup
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def stage(msg):                      # progress markers on stderr (PG_BENCH_TRACE=1): where a slow or stuck run is
-        if os.environ.get("PG_BENCH_TRACE"):
-            torch.cuda.synchronize(dev)
-            print(f"[bench] {msg}", file=sys.stderr, flush=True)
+    K, W = args.steps, max(args.warmup, 3)
 
     # ---- warm-up (also captures the CUDA graph of the step)
-    stage("sampler built")
-    smp.run(max(W, 3))
-    stage("warm-up + graph capture done")
-    launches_per_step = None
-    barrier()
+    stage("sampler built", dev)
+    smp.run(W)
+    stage("warm-up + graph capture done", dev)
+    _barrier(world, dev)
     # ---- timed region: device-resident state, CUDA-graph replay of the whole step
     clocks = ClockSampler(local_rank)
     clocks.start()
-    l0 = plan.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    _barrier(world, dev)
     ev0.record()
     K = smp.run(K)            # steps actually executed (the sampler stops at the end of the 1000-step trajectory)
     if K <= 0:
         raise SystemExit("bench.py: --warmup + --steps exceed the 1000-step trajectory")
     gathered = None
     if world > 1:
-        local = pack_results(smp.pos + smp.center, smp.node_cls, smp.edge_cls, smp.num_atoms)
+        local = pack_results(smp.pos + smp.center_rows, smp.node_cls, smp.edge_cls, smp.num_atoms)
         gathered = gather_results(local, dst=0)
     ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
+    _barrier(world, dev)
+    ms = _max_over_ranks(ev0.elapsed_time(ev1), world, dev)
     clk = clocks.stop()
-    stage("timed region done")
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    stage("timed region done", dev)
     ms_per_step = ms / K
     value = world * G / (ms_per_step * 1e-3 * TRAJ_STEPS)
 
@@ -230,7 +378,7 @@ def run_ours(args):
     eager = TrajectorySampler(model, None, G, dev, ligand_num_atoms=b["num_atoms"], save_traj=False, seed=1, use_cuda_graph=False,
                               phore_batch=ph)
     eager.run(2)
-    stage("eager sampler ran")
+    stage("eager sampler ran", dev)
     c0 = eager.plan.launches
     eager.plan.timing(True)
     n_prof = 3
@@ -238,10 +386,11 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     timing = eager.plan.read_timing()
     eager.plan.timing(False)
-    stage("per-class timing pass done")
+    stage("per-class timing pass done", dev)
     launches_per_step = (eager.plan.launches - c0) // n_prof + 3          # + node/edge categorical + position kernels
     trip_ms, trip_n = timing["trip"]
     class_ms = {k: v[0] / n_prof for k, v in timing.items()}
+    del eager
 
     # ---- end to end through the public forward() with HOST buffers: pinned H2D of the step's inputs, D2H of its result
     pin = lambda t: t.contiguous().pin_memory()
@@ -269,58 +418,62 @@ def run_ours(args):
 
     for _ in range(3):
         e2e_step()
-    barrier()
-    stage("e2e warm-up done")
+    _barrier(world, dev)
+    stage("e2e warm-up done", dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_e2e = max(3, min(K, 10))
     e0.record()
     for _ in range(n_e2e):
         e2e_step()
     e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1) / n_e2e
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    _barrier(world, dev)
+    e2e_ms = _max_over_ranks(e0.elapsed_time(e1) / n_e2e, world, dev)
     e2e_value = world * G / (e2e_ms * 1e-3 * TRAJ_STEPS)
 
     if rank == 0:
         peaks = load_peaks()
-        n = args.atoms
-        f_ref, f_trip_layer = f_ref_flops(n, p_mean)
-        trip_launch_ms = trip_ms / max(trip_n, 1)
-        achieved = f_trip_layer * G / (trip_launch_ms * 1e-3) / 1e12
-        exec_tf = f_exec_trip_flops(n) * G / (trip_launch_ms * 1e-3) / 1e12
+        na = b["num_atoms"].numpy()
+        sizes, counts = np.unique(na, return_counts=True)
+        f_ref = float(sum(c * f_ref_flops(int(n), p_mean)[0] for n, c in zip(sizes, counts)))
+        f_trip_layer = float(sum(c * f_ref_flops(int(n), p_mean)[1] for n, c in zip(sizes, counts)))
+        f_exec = float(sum(c * f_exec_trip_flops(int(n)) for n, c in zip(sizes, counts)))
+        # a mixed batch launches the single-chunk and the chunked triplet kernel: the layer's time is the sum of both launches
+        trip_layer_ms = trip_ms / (n_prof * 6)
+        achieved = f_trip_layer / (trip_layer_ms * 1e-3) / 1e12
+        exec_tf = f_exec / (trip_layer_ms * 1e-3) / 1e12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "trip_tc_traffic.json")      # dram bytes of one launch from the committed ncu --set full capture
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            if tj.get("molecules") == G and tj.get("atoms") == n:
+            if tj.get("molecules") == G and tj.get("atoms") == n_fixed and tj.get("workload", "config1") == wl:
                 traffic = tj["dram_bytes_per_launch"]
         roof = {"bound": "tensor", "kernel": "trip_tc_kernel (BondUpdateLayer, uni_denoiser.py:123-165)",
                 "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
                 "traffic": traffic, "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                "launch_ms": trip_launch_ms, "launches_timed": trip_n,
-                "algorithmic_flops_per_launch": f_trip_layer * G, "executed_flops_per_launch": f_exec_trip_flops(n) * G,
-                "achieved_executed": exec_tf,
+                "launch_ms": trip_layer_ms, "launches_timed": trip_n,
+                "algorithmic_flops_per_launch": f_trip_layer, "executed_flops_per_launch": f_exec,
+                "achieved_executed": exec_tf, "frac_executed": exec_tf / peaks["bf16_tflops_sustained"],
                 "note": "achieved = reference-formulation FLOPs of the triplet layer (SURVEY.md §8(d) term C: per-triplet 437->128->128 k/v MLPs and "
-                        "256->128->128 q MLP) / measured launch time of trip_tc_kernel; the kernel evaluates the exactly factorised form "
-                        "(first Linear split over its concatenated input, q per edge) with tcgen05 bf16x3 MMAs; `achieved_executed` counts "
-                        "the bf16 tensor FLOPs actually issued (hi/lo x3 and padding rows included)",
+                        "256->128->128 q MLP) / measured time of the layer's trip_tc_kernel launch(es); the kernel evaluates the exactly factorised form "
+                        "(first Linear split over its concatenated input, q per edge) with tcgen05 bf16x3 MMAs, so `achieved` can exceed the peak: "
+                        "`achieved_executed` / `frac_executed` count the bf16 tensor FLOPs actually issued (hi/lo x3 and padding rows included)",
                 "step_share": trip_ms / n_prof / max(sum(class_ms.values()), 1e-9), "ms_per_step_by_kernel_class": class_ms,
-                "whole_step_f_ref_tflops": f_ref * G / (ms_per_step * 1e-3) / 1e12}
+                "whole_step_f_ref_tflops": f_ref / (ms_per_step * 1e-3) / 1e12}
         line = {
             "metric": "molecules/sec (full 1000-step reverse trajectory)", "value": value, "unit": "molecules/s", "n_gpus": world,
-            "steps": K, "warmup": max(W, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3 tensor-core contractions (bf16 hi/lo split operands, fp32 accumulate) + f32 elsewhere", "data": "synthetic",
-            "config": {"workload": f"configs[1]: {G} molecules/GPU x {n} heavy atoms, 6-8 pharmacophore features (mean {p_mean:.2f}), "
-                                   "random-init weights, seed 2032", "molecules_per_gpu": G, "atoms": n, "trajectory_steps": TRAJ_STEPS,
-                       "step": "PhoreDiff.forward + categorical/Gaussian posterior update (diffusion.py:432-517), whole step replayed as one CUDA graph",
+            "config": {"workload": desc.format(G=G) + f" (mean {p_mean:.2f} nodes), random-init weights, seed 2032", "workload_name": wl,
+                       "molecules_per_gpu": G, "atoms": n_fixed if wl != "ragged" else f"mean {n_mean:.1f}, range {int(na.min())}-{int(na.max())}",
+                       "trajectory_steps": TRAJ_STEPS, "save_traj": False,
+                       "step": "PhoreDiff.forward + categorical/Gaussian posterior update (diffusion.py:432-517), whole step replayed as one CUDA graph; "
+                               "trajectory logging off (save_traj=False: only the final state is kept, which is all sample_all.py reads at its default save_traj_prob=0)",
                        "value_formula": "n_gpus * molecules_per_gpu / (1000 * seconds_per_step)",
                        "l2": f"per-step working set {plan.workspace_bytes / 2**30:.1f} GiB >> 126 MB L2 (inputs larger than L2; no flush needed)",
-                       "parallelism": f"molecule-sharded x{world}, final gather only"},
+                       "parallelism": f"molecule-sharded x{world}, final gather only",
+                       "key_precision": os.environ.get("PG_KEY", "bf16x3 (default)")},
             "roofline": roof,
+            "roofline_hbm": hbm_kernels(plan, smp, dev, peaks),
             "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                     "call": "PhoreDiff.forward(host tensors) + pg_categorical_step/pg_position_step, pinned H2D and D2H inside the timed region"},
             "gpu_launches": int(launches_per_step * K),
@@ -329,11 +482,85 @@ def run_ours(args):
             "denoiser_step_ms": ms_per_step,
         }
         if not args.no_cpu_baseline and world == 1:
-            sec, cores = cpu_reference_step_time(args.cpu_molecules, n, 2, 1)
-            line["cpu_baseline"] = {"value": args.cpu_molecules / (sec * TRAJ_STEPS), "unit": "molecules/s", "cores": cores, "kind": "port",
-                                    "sample": f"{args.cpu_molecules} molecules x {n} atoms, 1 warm-up + 2 timed reverse steps ({sec:.2f} s/step), extrapolated x1000"}
+            sec, cores, kind = cpu_reference_step_time(args.cpu_molecules, wl, 2, 1, atoms=args.atoms)
+            line["cpu_baseline"] = {"value": args.cpu_molecules / (sec * TRAJ_STEPS), "unit": "molecules/s", "cores": cores, "kind": kind,
+                                    "sample": f"{args.cpu_molecules} molecules of the {wl} shape, 1 warm-up + 2 timed reverse steps ({sec:.2f} s/step), extrapolated x1000"}
         if gathered is not None:
             line["config"]["gathered_molecules"] = int(gathered["num_atoms"].numel())
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ our arm: configs[2]
+def run_config2(args):
+    """256 synthetic pharmacophores x 100 samples = 25,600 molecules as one molecule-sharded job (runner.SamplingJob):
+    static size-balanced deal over the ranks, batches of <= 1024 molecules, per-molecule random streams, one final gather.
+    Ligand sizes ~ round(N(30,3)) in [20,40] (random-init count heads give arbitrary counts).  A step =
+    one reverse step of EVERY batch of the rank; batches run one after the other (work space of one batch at a time), K timed
+    steps each after W warm-up steps, CUDA events per batch summed, max over ranks."""
+    import torch.distributed as dist
+    from phoregen_b200.distributed import pack_results
+    from phoregen_b200.runner import SamplingJob, gather_job
+    from phoregen_b200.synthetic import synthetic_phore
+    from phoregen_b200.testing import PhoreData
+    rank, world, local_rank, dev, model = _setup()
+    P, S = args.pharmacophores, args.samples
+    rng = np.random.default_rng(2032)
+    phores = []
+    for i in range(P):
+        x, pos, nrm = synthetic_phore(rng, int(rng.choice((6, 7, 8))))
+        phores.append(PhoreData(torch.from_numpy(x), torch.from_numpy(pos), torch.from_numpy(nrm), name=f"synthetic{i}"))
+    na = ragged_sizes(2032, P * S)
+    job = SamplingJob(model, phores, S, dev, seed=2032, batch_size=args.molecules, ligand_num_atoms=na, rank=rank, world_size=world)
+    K, W = args.steps, max(args.warmup, 3)
+    clocks = ClockSampler(local_rank)
+    _barrier(world, dev)
+    clocks.start()
+    total_ms, parts = 0.0, []
+    for items in job.batches:
+        s = job.sampler(items, use_cuda_graph=True)
+        s.run(W)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        k = s.run(K)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        total_ms += e0.elapsed_time(e1) * (K / max(k, 1))
+        rec = pack_results(s.pos + s.center_rows, s.node_cls, s.edge_cls, s.num_atoms)
+        rec["item"] = torch.from_numpy(items).to(dev)
+        parts.append(rec)
+        del s
+    local = {k: torch.cat([p[k] for p in parts]) for k in parts[0]}
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _barrier(world, dev)
+    g0.record()
+    got = gather_job(local, dst=0)
+    g1.record()
+    _barrier(world, dev)
+    gather_ms = _max_over_ranks(g0.elapsed_time(g1), world, dev)
+    clk = clocks.stop()
+    ms_per_step = _max_over_ranks(total_ms / K, world, dev)
+    job_s = ms_per_step * 1e-3 * TRAJ_STEPS + gather_ms * 1e-3          # whole job: 1000 steps of every batch + the one gather
+    if rank == 0:
+        line = {
+            "metric": "molecules/sec (full 1000-step reverse trajectory)", "value": P * S / job_s, "unit": "molecules/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16x3 tensor-core contractions (bf16 hi/lo split operands, fp32 accumulate) + f32 elsewhere", "data": "synthetic",
+            "config": {"workload": f"configs[2]: {P} synthetic pharmacophores (6-8 features) x {S} samples = {P * S} molecules in one job, "
+                                   f"round(N(30,3)) in [20,40] heavy atoms, batches of <= {args.molecules}, size-balanced deal over {world} rank(s), final gather",
+                       "workload_name": "config2", "molecules_total": P * S, "batches_rank0": len(job.batches),
+                       "molecules_rank0": int(len(job.items)), "trajectory_steps": TRAJ_STEPS, "save_traj": False,
+                       "step": "one reverse step of every batch of the rank (batches run one after the other, each a CUDA-graph replay)",
+                       "value_formula": "molecules_total / (1000 * seconds_per_step + gather_seconds)", "gather_ms": gather_ms,
+                       "gathered_molecules": int(got["num_atoms"].numel()),
+                       "gathered_in_item_order": bool((got["item"].cpu() == torch.arange(P * S)).all()),
+                       "parallelism": f"molecule-sharded x{world} (runner.SamplingJob), no collective inside the loop"},
+            "e2e": {"value": P * S / job_s, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "job-level number: pharmacophores are uploaded once per job and the results gathered once; the config1 line carries the per-step host<->device form"},
+            "gpu_launches": None, "clocks": clk, "denoiser_step_ms": ms_per_step,
+        }
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -354,12 +581,19 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--molecules", type=int, default=1024, help="molecules per GPU")
-    ap.add_argument("--atoms", type=int, default=30)
+    ap.add_argument("--workload", default="config1", choices=list(WORKLOADS) + ["config2"])
+    ap.add_argument("--molecules", type=int, default=None, help="molecules per GPU (config2: molecules per batch)")
+    ap.add_argument("--atoms", type=int, default=None, help="heavy atoms per molecule (overrides the workload's)")
+    ap.add_argument("--hbm-gb", type=float, default=120.0, help="config4: work-space budget that sizes the batch")
+    ap.add_argument("--pharmacophores", type=int, default=256, help="config2")
+    ap.add_argument("--samples", type=int, default=100, help="config2: samples per pharmacophore")
     ap.add_argument("--cpu-molecules", type=int, default=4, help="bounded CPU sample size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--full-trajectory", action="store_true", help="time all 1000 steps")
     args = ap.parse_args()
+    args.molecules_set = args.molecules is not None
+    if args.molecules is None:
+        args.molecules = 1024
     if args.full_trajectory:
         args.steps = TRAJ_STEPS - max(args.warmup, 3)
     # The contract is ONE JSON line on stdout.  Native libraries print there too (NCCL announces its version on stdout when
@@ -371,6 +605,8 @@ def main():
     os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "config2":
+        run_config2(args)
     else:
         run_ours(args)
 

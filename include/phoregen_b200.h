@@ -121,20 +121,40 @@ int pg_phorediff_forward(const PgModel* m, PgPlan* p, const float* d_h_node, con
 int pg_categorical_step(int rows, int K, const float* d_pred, float* d_log_vt, const float* d_q_mats,
                         const float* d_tq_onestep, const int64_t* d_time_step, const int32_t* d_row_graph,
                         const float* d_uniform, uint64_t seed, uint32_t stream_id, const int64_t* d_step_counter,
-                        float* d_onehot, int32_t* d_cls, uint8_t* d_traj_cls /*[T+1,rows] or NULL*/, void* stream);
+                        float* d_onehot, int32_t* d_cls, uint8_t* d_traj_cls /*[T+1,rows] or NULL*/,
+                        const uint64_t* d_graph_seed /*[G] or NULL*/, const int64_t* d_graph_row0 /*[G] or NULL*/, void* stream);
+/* Random-stream addressing of the Philox draws (all entry points below): with d_graph_seed == NULL the counter is the batch
+ * row under `seed`; with d_graph_seed [G] (one 64-bit seed per molecule) and d_graph_row0 [G] (first row of each graph)
+ * the counter is the row's index inside its own molecule under that molecule's seed, so a molecule draws the same numbers
+ * in any batch and on any rank (molecule-sharded sampling reproduces a single-GPU run bit for bit). */
 /* x_prev = coef_x0[t] x_recon + coef_xt[t] x_t - grad (+ std[t] z unless t == 0); d_normal NULL -> Philox. */
 int pg_position_step(int rows, const float* d_x_t, const float* d_x_recon, const float* d_energy_grad,
                      const float* d_coef_x0, const float* d_coef_xt, const float* d_std,
                      const int64_t* d_time_step, const int32_t* d_row_graph, const float* d_normal, uint64_t seed,
                      uint32_t stream_id, const int64_t* d_step_counter, float* d_x_prev,
                      float* d_traj_pos /*[T+1,rows,3] or NULL*/, const float* d_center /*[3], [G,3] or NULL*/,
-                     int center_per_graph /*1: d_center holds one centre per graph (multi-pharmacophore batches)*/, void* stream);
+                     int center_per_graph /*1: d_center holds one centre per graph (multi-pharmacophore batches)*/,
+                     const uint64_t* d_graph_seed, const int64_t* d_graph_row0, void* stream);
+/* T4: initial state of the reverse trajectory (reference models/transition.py:65-69,331-339 `sample_init`;
+ * models/diffusion.py:406-408).  Categorical: class = argmax(gumbel(u) + d_log_prior[K]) per row, one-hot f32, int32 class
+ * and log one-hot (log(clamp(onehot, 1e-30))) written; d_uniform [rows,K] supplies the draws, NULL -> Philox.
+ * Positions: d_pos = z - centre, z standard normal (d_normal [rows,3] or Philox). */
+int pg_sample_init(int rows, int K, const float* d_log_prior, const int32_t* d_row_graph, const float* d_uniform, uint64_t seed,
+                   uint32_t stream_id, float* d_onehot, int32_t* d_cls, float* d_log_vt, const uint64_t* d_graph_seed,
+                   const int64_t* d_graph_row0, void* stream);
+int pg_position_init(int rows, const int32_t* d_row_graph, const float* d_normal, uint64_t seed, uint32_t stream_id,
+                     const float* d_center, int center_per_graph, float* d_pos, const uint64_t* d_graph_seed,
+                     const int64_t* d_graph_row0, void* stream);
 /* T5: closed-form gradient of the guidance energies (utils/sample_utils.py:135-165; diffusion.py:476-502).
  * flags bit0 = atom_prox(min_d,max_d), bit1 = center_prox(d_phore_center), bit2 = add onto d_grad instead of overwriting
  * it (the reference sums one gradient per pos_guidance_opt entry: diffusion.py:479-501), bit3 = d_phore_center is [G,3]
  * (one pharmacophore per graph) instead of [3].  d_edge_cls: sampled classes, reference edge order.  Output d_grad [Nl,3]. */
 int pg_guidance_grad(const PgPlan* p, const float* d_pos, const int32_t* d_edge_cls, int flags, float min_d,
-                     float max_d, const float* d_phore_center, float* d_grad, void* stream);
+                     float max_d, const float* d_phore_center, float* d_grad,
+                     int norm_graphs /*the energies are means over the call's n_graphs (sample_utils.py:155,165); 0 = this
+                                       plan's G like the reference, > 0 = a job-wide constant so that the drift of a molecule
+                                       does not depend on how a sharded job is batched*/,
+                     void* stream);
 
 /* O2 / D2: atom-count heads (reference models/diffusion.py:148-163 `predict_atom_count`, and the interval of
  * `sample_nodes` :374-380).  d_h_phore_emb [P,128] is pg_phore_encode's output, d_h_phore [P,18] the raw features

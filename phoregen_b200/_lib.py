@@ -23,7 +23,33 @@ def _load():
     return ctypes.CDLL(LIB_PATH)
 
 
-lib = _load()
+class _Library:
+    """The shared library, mapped on first use.  Importing the package (e.g. to enumerate a PhoreDiff state_dict, as
+    bench.py's CPU reference arm does) does not map the CUDA library into the process; the first call of any entry point
+    does, binds every signature below, and raises loudly if the library or a symbol is missing."""
+
+    def __init__(self):
+        self._cdll = None
+
+    def _bind(self):
+        if self._cdll is None:
+            cdll = _load()
+            for name, (res, args) in _SIGS.items():
+                fn = getattr(cdll, name)          # AttributeError here = header/library drift; never silently ignored
+                fn.restype = res
+                fn.argtypes = args
+            self._cdll = cdll
+        return self._cdll
+
+    @property
+    def loaded(self):
+        return self._cdll is not None
+
+    def __getattr__(self, name):
+        return getattr(self._bind(), name)
+
+
+lib = _Library()
 
 _P = c_void_p
 _SIGS = {
@@ -48,10 +74,12 @@ _SIGS = {
     "pg_denoiser_forward": (c_int, [_P] * 10),
     "pg_phore_encode": (c_int, [_P] * 6),
     "pg_phorediff_forward": (c_int, [_P] * 13),
-    "pg_categorical_step": (c_int, [c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_uint64, c_uint32, _P, _P, _P, _P, _P]),
-    "pg_position_step": (c_int, [c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_uint64, c_uint32, _P, _P, _P, _P, c_int, _P]),
+    "pg_categorical_step": (c_int, [c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_uint64, c_uint32, _P, _P, _P, _P, _P, _P, _P]),
+    "pg_position_step": (c_int, [c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_uint64, c_uint32, _P, _P, _P, _P, c_int, _P, _P, _P]),
+    "pg_sample_init": (c_int, [c_int, c_int, _P, _P, _P, c_uint64, c_uint32, _P, _P, _P, _P, _P, _P]),
+    "pg_position_init": (c_int, [c_int, _P, _P, c_uint64, c_uint32, _P, c_int, _P, _P, _P, _P]),
     "pg_atom_count": (c_int, [_P, _P, _P, _P, c_int, c_float, c_float, _P, _P, _P, _P, _P]),
-    "pg_guidance_grad": (c_int, [_P, _P, _P, c_int, c_float, c_float, _P, _P, _P]),
+    "pg_guidance_grad": (c_int, [_P, _P, _P, c_int, c_float, c_float, _P, _P, c_int, _P]),
     "pg_gemm_k128": (c_int, [c_int, c_int, c_int64, _P, c_int64, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, c_int, _P]),
     "pg_plan_ligand_graph": (_P, [_P]),
     "pg_plan_edge_graph": (_P, [_P]),
@@ -59,11 +87,6 @@ _SIGS = {
     "pg_plan_timing_enable": (c_int, [_P, c_int]),
     "pg_plan_timing_read": (c_int, [_P, c_int, POINTER(ctypes.c_double), POINTER(c_int64)]),
 }
-for _name, (_res, _args) in _SIGS.items():
-    _fn = getattr(lib, _name)          # AttributeError here = header/library drift; never silently ignored
-    _fn.restype = _res
-    _fn.argtypes = _args
-
 EXPORTED_SYMBOLS = tuple(_SIGS)
 
 

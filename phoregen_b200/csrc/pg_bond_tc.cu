@@ -475,17 +475,19 @@ int pg_launch_bond_tc(const BondTcArgs& a, int pos, int num_sms, cudaStream_t s)
 #undef PG_BOND_ATTR
         init = true;
     }
-    // every segment fits one lane quarter (n-1 <= 32): atoms packed four to a tile across the batch; otherwise the
-    // per-graph tile table with 4/C atoms per tile
-    const bool multi = a.d.max_n - 1 > PG_BOND_TC_SINGLE_CHUNK_ROWS;
-    const long long ntiles = multi ? a.d.nbt : (a.d.Nl + 3) / 4;
-    const unsigned grid = (unsigned)std::min<long long>(ntiles, num_sms);
+    // Which instantiation an atom runs on depends on its molecule alone (n-1 <= 32: atoms packed four to a tile across the
+    // batch; longer segments: the per-graph tile table, which lists only those molecules), so results do not depend on
+    // the batch composition.  A mixed batch launches both.
+    const bool have_single = a.d.min_n - 1 <= PG_BOND_TC_SINGLE_CHUNK_ROWS, have_multi = a.d.nbt > 0;
 #define PG_BOND_GO(P, M, K) bond_tc_kernel<P, M, K><<<grid, NTHREADS, SM_TOTAL, s>>>(a)
-    if (a.key_bf16x3) {
-        if (!multi) { if (pos == 0) PG_BOND_GO(0, false, false); else PG_BOND_GO(1, false, false); }
-        else { if (pos == 0) PG_BOND_GO(0, true, false); else PG_BOND_GO(1, true, false); }
-    } else {
-        if (!multi) { if (pos == 0) PG_BOND_GO(0, false, true); else PG_BOND_GO(1, false, true); }
+    if (have_single) {
+        const unsigned grid = (unsigned)std::min<long long>((a.d.Nl + 3) / 4, num_sms);
+        if (a.key_bf16x3) { if (pos == 0) PG_BOND_GO(0, false, false); else PG_BOND_GO(1, false, false); }
+        else { if (pos == 0) PG_BOND_GO(0, false, true); else PG_BOND_GO(1, false, true); }
+    }
+    if (have_multi) {
+        const unsigned grid = (unsigned)std::min<long long>(a.d.nbt, num_sms);
+        if (a.key_bf16x3) { if (pos == 0) PG_BOND_GO(0, true, false); else PG_BOND_GO(1, true, false); }
         else { if (pos == 0) PG_BOND_GO(0, true, true); else PG_BOND_GO(1, true, true); }
     }
 #undef PG_BOND_GO

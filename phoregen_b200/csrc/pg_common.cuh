@@ -41,8 +41,9 @@ struct PlanDev {
     const int* edge_graph;  // [Eb] reference-order edge -> graph
     const int* esrc_node;   // [Eb] internal edge -> context node of src (j)
     const int* edst_node;   // [Eb] internal edge -> context node of dst (i)
-    // bond-graph attention tiles when some segment is longer than one 32-row TMEM lane quarter (pg_bond_tc.cu): a graph
-    // whose segments take C = ceil((n-1)/32) quarters places 4/C atoms in a tile, ceil(n / (4/C)) tiles per graph
+    // bond-graph attention tiles of the molecules whose segments are longer than one 32-row TMEM lane quarter
+    // (pg_bond_tc.cu): a graph whose segments take C = ceil((n-1)/32) > 1 quarters places 4/C atoms in a tile,
+    // ceil(n / (4/C)) tiles per graph; molecules with n-1 <= 32 have no entry (they run on the packed instantiation)
     int nbt;                // number of such tiles in the batch
     const int* btile_off;   // [G+1] first tile of graph g
     const int* btile_graph; // [nbt] tile -> graph

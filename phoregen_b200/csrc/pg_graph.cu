@@ -163,7 +163,7 @@ extern "C" int pg_plan_create(PgPlan** out, int G, const int32_t* na, const int3
     std::vector<int> btile_off(G + 1, 0), btile_graph;
     for (int g = 0; g < G; g++) {
         const int apt = std::max(pg_bond_atoms_per_tile(na[g]), 1);
-        const int nt = (na[g] + apt - 1) / apt;
+        const int nt = na[g] - 1 > 32 ? (na[g] + apt - 1) / apt : 0;     // single-quarter molecules take the packed kernel
         btile_off[g + 1] = btile_off[g] + nt;
         btile_graph.insert(btile_graph.end(), nt, g);
     }

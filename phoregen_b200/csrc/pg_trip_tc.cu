@@ -79,7 +79,7 @@ __device__ __forceinline__ void iter_load_unit(const PlanDev& d, TileIter& it) {
     while (it.u < d.Nl) {
         const int g = d.lig_graph[it.u];
         const int n = d.g_n[g];
-        if (n >= 3 && (MULTI || n - 2 <= 32)) {
+        if (n >= 3 && (MULTI ? n - 2 > 32 : n - 2 <= 32)) {       // each instantiation takes its own molecules (see the launcher)
             it.n = n; it.jl = it.u - d.lig_off[g]; it.ctx0 = d.ctx_off[g] + d.g_p[g]; it.eoff = d.eoff[g];
             it.nchunk = MULTI ? (n - 2 + 31) >> 5 : 1;
             it.ntile = ((n - 1 + 3) >> 2) * it.nchunk; it.tile = 0; it.chunk = 0; it.grp = 0; it.stage++; it.valid = true;
@@ -718,11 +718,17 @@ int pg_launch_trip_tc(const TripTcArgs& a, int num_sms, cudaStream_t s) {
         cur = smem;
     }
     const unsigned grid = (unsigned)std::min<long long>(a.d.Nl, num_sms);
-    // segments of every molecule fit one 32-row chunk (n - 2 <= 32): the single-chunk kernel; otherwise the chunked one
-    // serves the whole batch (molecules of either kind)
-    const bool multi = a.maxn > PG_TRIP_TC_SINGLE_CHUNK_ATOMS;
-    if (a.flags & 2) { if (multi) trip_tc_kernel<true, false><<<grid, NTHREADS, smem, s>>>(a); else trip_tc_kernel<false, false><<<grid, NTHREADS, smem, s>>>(a); }
-    else { if (multi) trip_tc_kernel<true, true><<<grid, NTHREADS, smem, s>>>(a); else trip_tc_kernel<false, true><<<grid, NTHREADS, smem, s>>>(a); }
+    // The kernel a molecule runs on depends on the molecule alone (n - 2 <= 32: single-chunk instantiation, else the chunked
+    // one), never on the batch it is in: results are bit-identical however a job is batched or sharded.  A mixed batch
+    // launches both; each walks the unit list and skips the other's molecules.
+    const bool have_single = a.d.min_n <= PG_TRIP_TC_SINGLE_CHUNK_ATOMS, have_multi = a.maxn > PG_TRIP_TC_SINGLE_CHUNK_ATOMS;
+    if (a.flags & 2) {
+        if (have_single) trip_tc_kernel<false, false><<<grid, NTHREADS, smem, s>>>(a);
+        if (have_multi) trip_tc_kernel<true, false><<<grid, NTHREADS, smem, s>>>(a);
+    } else {
+        if (have_single) trip_tc_kernel<false, true><<<grid, NTHREADS, smem, s>>>(a);
+        if (have_multi) trip_tc_kernel<true, true><<<grid, NTHREADS, smem, s>>>(a);
+    }
     PG_LAUNCH_CHECK();
     return PG_OK;
 }

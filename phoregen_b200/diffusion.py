@@ -248,6 +248,19 @@ class PhoreDiff(nn.Module):
         return sampler.results(traj_layout)
 
 
+def non_ex_centers(x, pos, num_phore, ex_col):
+    """diffusion.py:493-497 per graph: mean position of the features that are not exclusion spheres, [G,3].  Computed graph by
+    graph on the host (a device scatter-add would make the centre depend on atomics' order and on the batch composition;
+    the sharded job needs it to depend on the pharmacophore alone).  nan for a graph without such features, like the
+    reference's mean over an empty selection."""
+    out, o = [], 0
+    for p in np.asarray(num_phore).tolist():
+        xs, ps = x[o:o + p], pos[o:o + p]
+        out.append(ps[xs[:, ex_col] != 1].mean(0))
+        o += p
+    return torch.stack(out).float().contiguous()
+
+
 class TrajectorySampler:
     """State + one captured CUDA graph of a reverse step (forward + categorical/Gaussian posterior update).
 
@@ -256,10 +269,14 @@ class TrajectorySampler:
     so the whole step is captured once and replayed `num_timesteps` times."""
 
     def __init__(self, model, data, n_graphs, device, ligand_num_atoms=None, sample_mode="uniform", normal_scale=4.0,
-                 guidance=None, save_traj=True, seed=None, use_cuda_graph=True, phore_batch=None):
+                 guidance=None, save_traj=True, seed=None, use_cuda_graph=True, phore_batch=None, graph_uid=None,
+                 guidance_n_graphs=0):
         """`data` is one pharmacophore replicated `n_graphs` times (the reference's sample()); alternatively
         `phore_batch` = dict(x [P,18], pos [P,3], norm [P,3], batch [P]) supplies a different pharmacophore per
-        molecule (something the reference's sample() cannot do: sample_all.py:69-94 handles one at a time)."""
+        molecule (something the reference's sample() cannot do: sample_all.py:69-94 handles one at a time).
+        Every random draw of molecule g (initial state, Gumbel noise, position noise) comes from its own Philox stream
+        keyed by (seed, graph_uid[g]) - default uid = g - so a molecule's trajectory does not depend on the batch it is in
+        (engine.BatchPlan.molecule_streams); a sharded job passes job-wide ids."""
         self.m, self.device, self.G = model, device, n_graphs
         self.T = model.num_timesteps
         pm = self.pm = model.packed(device)
@@ -304,31 +321,29 @@ class TrajectorySampler:
         self.edge_index, self.edge_batch = plan.bond_edges()                # G1 on device
         Nl, Eb = plan.Nl, plan.Eb
         self.seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if seed is None else int(seed)
-        gen = torch.Generator(device=device)
-        gen.manual_seed(self.seed)
-        # initial state (diffusion.py:406-408; transition.py:65-69,331-339)
+        self.streams = plan.molecule_streams(self.seed, graph_uid)
+        # initial state (diffusion.py:406-408; transition.py:65-69,331-339) from the init kernels (pg_position_init / pg_sample_init)
         self.center_rows = self.center[self.batch_node] if self.center.dim() == 2 else self.center     # [Nl,3] or [3]
-        self.pos = (torch.randn(Nl, 3, device=device, generator=gen) - self.center_rows).contiguous()
-        self.log_node = torch.empty(Nl, 12, device=device)
-        self.log_edge = torch.empty(Eb, 6, device=device)
-        self.h_node, self.node_cls = self._init_categorical(model.node_transition, Nl, self.log_node, gen)
-        self.h_edge, self.edge_cls = self._init_categorical(model.edge_transition, Eb, self.log_edge, gen)
+        self.pos = plan.position_init(center=self.center, seed=self.seed, streams=self.streams)
+        self.h_node, self.node_cls, self.log_node = plan.sample_init("node", model.node_transition.init_log_prob(), seed=self.seed, streams=self.streams)
+        self.h_edge, self.edge_cls, self.log_edge = plan.sample_init("edge", model.edge_transition.init_log_prob(), seed=self.seed, streams=self.streams)
         self.pred = (torch.empty(Nl, 12, device=device), torch.empty(Nl, 3, device=device), torch.empty(Eb, 6, device=device))
         self.time_step = torch.full((n_graphs,), self.T - 1, dtype=torch.int64, device=device)
         self.step_counter = torch.zeros(1, dtype=torch.int64, device=device)
         self.guidance = guidance
+        # the guidance energies are means over the call's n_graphs (reference quirk: the drift scales with 1 / batch size,
+        # sample_utils.py:155,165); 0 keeps that, a sharded job passes one constant for all its batches
+        self.guidance_n_graphs = int(guidance_n_graphs)
         self.grad = torch.zeros(Nl, 3, device=device) if guidance else None
         self.phore_center = None
         if guidance:
             col = model._ex_col
             if single_x is not None:
                 self.phore_center = single_pos[single_x[:, col] != 1].mean(0).contiguous()   # diffusion.py:493-497
-            else:   # one pharmacophore per graph: centre of each graph's non-EX features (segment mean, once per batch)
-                keep = (self.px[:, col] != 1).float().unsqueeze(1)
-                pbatch = phore_batch["batch"].to(device)
-                s = torch.zeros(n_graphs, 3, device=device).index_add_(0, pbatch, self.ppos * keep)
-                c = torch.zeros(n_graphs, 1, device=device).index_add_(0, pbatch, keep)
-                self.phore_center = (s / c).contiguous()          # 0/0 = nan for a graph without non-EX features, as torch.mean of an empty set
+            elif phore_batch.get("guidance_center") is not None:     # precomputed per pharmacophore (runner.PhoreSet)
+                self.phore_center = phore_batch["guidance_center"].to(device).float().contiguous()
+            else:   # one pharmacophore per graph: centre of each graph's non-EX features, once per batch
+                self.phore_center = non_ex_centers(self.px.cpu(), self.ppos.cpu(), num_phore, col).to(device)
         self.save_traj = save_traj
         if save_traj:
             try:
@@ -344,28 +359,19 @@ class TrajectorySampler:
         self.graph = None
         self.steps_done = 0
 
-    def _init_categorical(self, trans, rows, log_out, gen):
-        K = trans.num_classes
-        logits = trans.init_log_prob().to(self.device).unsqueeze(0).expand(rows, K)
-        u = torch.rand(rows, K, device=self.device, generator=gen)
-        cls = (-torch.log(-torch.log(u + 1e-30) + 1e-30) + logits).argmax(-1)
-        onehot = F.one_hot(cls, K).float().contiguous()
-        log_out.copy_(torch.log(onehot.clamp(min=1e-30)))                    # index_to_log_onehot (common.py:398-402)
-        return onehot, cls.to(torch.int32).contiguous()
-
     def _step(self):
         """Loop body of diffusion.py:432-517."""
         plan, pm = self.plan, self.pm
         plan.phorediff_forward(pm, self.h_node, self.pos, self.h_edge, self.time_step, self.h_phore_emb, self.ppos,
                                self.pnorm, out=self.pred)
-        plan.categorical_step(pm, "node", self.pred[0], self.log_node, self.time_step, seed=self.seed,
-                              step_counter=self.step_counter, onehot=self.h_node, cls=self.node_cls, traj=self.traj_node)
-        plan.categorical_step(pm, "edge", self.pred[2], self.log_edge, self.time_step, seed=self.seed,
-                              step_counter=self.step_counter, onehot=self.h_edge, cls=self.edge_cls, traj=self.traj_edge)
+        plan.categorical_step(pm, "node", self.pred[0], self.log_node, self.time_step, seed=self.seed, step_counter=self.step_counter,
+                              onehot=self.h_node, cls=self.node_cls, traj=self.traj_node, streams=self.streams)
+        plan.categorical_step(pm, "edge", self.pred[2], self.log_edge, self.time_step, seed=self.seed, step_counter=self.step_counter,
+                              onehot=self.h_edge, cls=self.edge_cls, traj=self.traj_edge, streams=self.streams)
         if self.guidance:
-            plan.guidance_grad(self.pos, self.edge_cls, self.guidance, self.phore_center, out=self.grad)
+            plan.guidance_grad(self.pos, self.edge_cls, self.guidance, self.phore_center, out=self.grad, norm_graphs=self.guidance_n_graphs)
         plan.position_step(pm, self.pos, self.pred[1], self.time_step, energy_grad=self.grad, seed=self.seed,
-                           step_counter=self.step_counter, out=self.pos, traj=self.traj_pos, center=self.center)
+                           step_counter=self.step_counter, out=self.pos, traj=self.traj_pos, center=self.center, streams=self.streams)
         self.time_step.sub_(1)
         self.step_counter.add_(1)
 

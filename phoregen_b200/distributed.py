@@ -34,8 +34,9 @@ def pack_results(pos, node_cls, edge_cls, num_atoms):
                 edge_cls=edge_cls.to(torch.uint8).contiguous(), num_atoms=num_atoms.to(torch.int32).contiguous())
 
 
-def gather_results(local, dst=0, group=None):
+def gather_results(local, dst=0, group=None, extra=()):
     """Final gather to rank `dst`: sizes first, then one padded all_gather per field (ragged across ranks).
+    `extra`: names of additional per-molecule fields of `local` (e.g. the job-wide item ids of runner.SamplingJob).
     Returns the concatenated dict on `dst` (None elsewhere)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
@@ -45,7 +46,7 @@ def gather_results(local, dst=0, group=None):
     dist.all_gather(all_sizes, sizes, group=group)
     all_sizes = torch.stack(all_sizes).cpu()
     out = {}
-    for key, col, tail in (("num_atoms", 0, ()), ("pos", 1, (3,)), ("node_cls", 1, ()), ("edge_cls", 2, ())):
+    for key, col, tail in (("num_atoms", 0, ()), ("pos", 1, (3,)), ("node_cls", 1, ()), ("edge_cls", 2, ())) + tuple((k, 0, ()) for k in extra):
         mx = int(all_sizes[:, col].max())
         buf = torch.zeros((mx,) + tail, dtype=local[key].dtype, device=dev)
         buf[: local[key].shape[0]] = local[key]

@@ -218,10 +218,61 @@ class BatchPlan:
                                 _ptr(cl), _ptr(cu), _ptr(lo), _ptr(hi), _stream(self.device)), "pg_atom_count")
         return (cl, cu, lo, hi) if intervals else (cl, cu)
 
+    # ---- per-molecule random streams ---------------------------------------------------------
+    def molecule_streams(self, seed, graph_uid=None):
+        """Per-molecule Philox addressing (see include/phoregen_b200.h, "Random-stream addressing"): molecule g draws from
+        the key splitmix64(seed, uid_g) with its LOCAL row as counter, so its trajectory does not depend on the batch it
+        is in or on the rank that runs it.  `graph_uid` [G] int: job-wide molecule ids (default: 0..G-1).
+        -> dict(seed [G] int64 bit patterns, node_row0 [G] int64, edge_row0 [G] int64) on the plan's device."""
+        uid = np.arange(self.G, dtype=np.uint64) if graph_uid is None else np.asarray(graph_uid).astype(np.uint64)
+        assert uid.shape == (self.G,)
+        with np.errstate(over="ignore"):
+            z = (np.uint64(int(seed) & 0xFFFFFFFFFFFFFFFF) + (uid + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15))
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            z = z ^ (z >> np.uint64(31))
+        na = self.num_atoms.astype(np.int64)
+        node0 = np.concatenate([[0], np.cumsum(na)[:-1]])
+        edge0 = np.concatenate([[0], np.cumsum(na * (na - 1))[:-1]])
+        dev = self.device
+        return dict(seed=torch.from_numpy(z.view(np.int64)).to(dev), node_row0=torch.from_numpy(node0).to(dev),
+                    edge_row0=torch.from_numpy(edge0).to(dev))
+
+    @staticmethod
+    def _stream_args(streams, kind):
+        if streams is None:
+            return None, None
+        return _ptr(streams["seed"]), _ptr(streams["node_row0" if kind == "node" else "edge_row0"])
+
+    # ---- initial state (T4) --------------------------------------------------------------------
+    @_on_device
+    def sample_init(self, kind, log_prior, uniform=None, seed=0, streams=None):
+        """transition.py:331-339: -> (onehot [rows,K] f32, cls [rows] int32, log_vt [rows,K] f32)."""
+        K = 12 if kind == "node" else 6
+        rows = self.Nl if kind == "node" else self.Eb
+        log_prior = _f32(log_prior.to(self.device))
+        assert log_prior.shape == (K,)
+        onehot, cls = _alloc((rows, K), torch.float32, self.device), _alloc((rows,), torch.int32, self.device)
+        log_vt = _alloc((rows, K), torch.float32, self.device)
+        rg = self._lig_graph_ptr if kind == "node" else self._edge_graph_ptr
+        gs, r0 = self._stream_args(streams, kind)
+        check(lib.pg_sample_init(rows, K, _ptr(log_prior), ctypes.c_void_p(rg), _ptr(uniform), seed, 4 if kind == "node" else 5,
+                                 _ptr(onehot), _ptr(cls), _ptr(log_vt), gs, r0, _stream(self.device)), "pg_sample_init")
+        return onehot, cls, log_vt
+
+    @_on_device
+    def position_init(self, center=None, normal=None, seed=0, streams=None):
+        """diffusion.py:406: standard normal minus the centre ([3] or one per graph [G,3])."""
+        pos = _alloc((self.Nl, 3), torch.float32, self.device)
+        gs, r0 = self._stream_args(streams, "node")
+        check(lib.pg_position_init(self.Nl, ctypes.c_void_p(self._lig_graph_ptr), _ptr(normal), seed, 6, _ptr(center),
+                                   int(center is not None and center.dim() == 2), _ptr(pos), gs, r0, _stream(self.device)), "pg_position_init")
+        return pos
+
     # ---- transitions -----------------------------------------------------------------------
     @_on_device
     def categorical_step(self, model, kind, pred, log_vt, time_step, uniform=None, seed=0, step_counter=None,
-                         onehot=None, cls=None, traj=None):
+                         onehot=None, cls=None, traj=None, streams=None):
         K = 12 if kind == "node" else 6
         rows = self.Nl if kind == "node" else self.Eb
         assert pred.shape == (rows, K) and log_vt.shape == (rows, K) and pred.is_contiguous() and log_vt.is_contiguous()
@@ -234,12 +285,13 @@ class BatchPlan:
             cls = _alloc((rows,), torch.int32, self.device)
         check(lib.pg_categorical_step(rows, K, _ptr(pred), _ptr(log_vt), _ptr(qm), _ptr(tq), _ptr(time_step),
                                       ctypes.c_void_p(rg), _ptr(uniform), seed, 1 if kind == "node" else 2,
-                                      _ptr(step_counter), _ptr(onehot), _ptr(cls), _ptr(traj), _stream(self.device)), "pg_categorical_step")
+                                      _ptr(step_counter), _ptr(onehot), _ptr(cls), _ptr(traj), *self._stream_args(streams, kind),
+                                      _stream(self.device)), "pg_categorical_step")
         return onehot, cls
 
     @_on_device
     def position_step(self, model, x_t, x_recon, time_step, normal=None, energy_grad=None, seed=0, step_counter=None,
-                      out=None, traj=None, center=None):
+                      out=None, traj=None, center=None, streams=None):
         assert x_t.shape == (self.Nl, 3) and x_recon.shape == (self.Nl, 3)
         if out is None:
             out = torch.empty_like(x_t)
@@ -248,11 +300,11 @@ class BatchPlan:
                                    _ptr(t["pos_transition.coef_xt"]), _ptr(t["pos_transition.std"]), _ptr(time_step),
                                    ctypes.c_void_p(self._lig_graph_ptr), _ptr(normal), seed, 3, _ptr(step_counter),
                                    _ptr(out), _ptr(traj), _ptr(center), int(center is not None and center.dim() == 2),
-                                   _stream(self.device)), "pg_position_step")
+                                   *self._stream_args(streams, "node"), _stream(self.device)), "pg_position_step")
         return out
 
     @_on_device
-    def guidance_grad(self, pos, edge_cls, opts, phore_center, out=None):
+    def guidance_grad(self, pos, edge_cls, opts, phore_center, out=None, norm_graphs=0):
         """Sum of the drift gradients of every entry of `pos_guidance_opt` (diffusion.py:479-501 adds one gradient per
         list entry; unknown types contribute nothing there and are rejected here).  `phore_center`: [3] (one
         pharmacophore for the whole batch) or [G,3] (one per graph)."""
@@ -270,7 +322,7 @@ class BatchPlan:
             else:
                 raise NotImplementedError(f"pos_guidance_opt type {o['type']!r}")
             check(lib.pg_guidance_grad(self.handle, _ptr(pos), _ptr(edge_cls), flags | (0 if first else 4) | (8 * per_graph),
-                                       min_d, max_d, _ptr(phore_center), _ptr(out), _stream(self.device)), "pg_guidance_grad")
+                                       min_d, max_d, _ptr(phore_center), _ptr(out), int(norm_graphs), _stream(self.device)), "pg_guidance_grad")
             first = False
         if first:
             out.zero_()

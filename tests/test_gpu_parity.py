@@ -172,9 +172,9 @@ def test_forward_big_molecules_match_reference_golden(model, dev, case):
 
 
 def test_forward_mixed_chunk_batch_equals_single_molecule_runs(model, dev):
-    """A batch mixing 1-, 2- and 3-chunk molecules takes the chunked kernels for every molecule; each molecule's outputs
-    must equal (bit for bit: per-molecule arithmetic is batch-independent) the ones it gets alone, where the small ones
-    run on the single-chunk kernels only up to the softmax normalisation order -> tolerance for those."""
+    """A batch mixing 1-, 2- and 3-chunk molecules: the kernel instantiation a molecule runs on depends on the molecule
+    alone, so each molecule's outputs equal BIT FOR BIT the ones it gets in a batch of its own (what makes a sharded job
+    reproduce a single-GPU run)."""
     m, _ = model
     b = O.synthetic_batch(311, 4, n_atoms=(12, 70), p_choices=(6, 9), pos_scale=2.0)
     na = b["num_atoms"].tolist()
@@ -194,9 +194,7 @@ def test_forward_mixed_chunk_batch_equals_single_molecule_runs(model, dev):
                    batch_edge=torch.zeros(na[g] * (na[g] - 1), dtype=torch.long),
                    phore=dict(x=ph["x"][pm], pos=ph["pos"][pm], norm=ph["norm"][pm], batch=torch.zeros(int(pm.sum()), dtype=torch.long)))
         alone = _forward(m, one, [times[g]], dev)
-        assert_close(got[0][sel_a], alone[0], f"molecule {g} logits_node", rtol=2e-4, atol=2e-5)
-        assert_close(got[1][sel_a], alone[1], f"molecule {g} pos", rtol=2e-4, atol=2e-5)
-        assert_close(got[2][sel_e], alone[2], f"molecule {g} logits_edge", rtol=2e-4, atol=2e-5)
+        assert torch.equal(got[0][sel_a], alone[0]) and torch.equal(got[1][sel_a], alone[1]) and torch.equal(got[2][sel_e], alone[2]), g
 
 
 def test_forward_training_edge_order(model, dev):
@@ -244,7 +242,7 @@ def test_transition_matches_reference_golden(model, dev):
     pred_d, uni_d = e["pred"].to(dev), e["uniform"].to(dev)      # keep the device tensors alive across the launch
     check(lib.pg_categorical_step(rows, 6, P(pred_d), P(log_vt), P(pm.tables["edge_transition.q_mats"]),
                                   P(pm.tables["edge_transition.transpopse_q_onestep_mats"]), P(t), P(rg), P(uni_d),
-                                  0, 2, None, P(oh), P(cl), None, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "cat")
+                                  0, 2, None, P(oh), P(cl), None, None, None, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "cat")
     assert_close(log_vt, e["post"], "edge posterior", rtol=1e-5, atol=1e-5)
     safe = e["margin"] > 1e-4
     assert torch.equal(cl.cpu().long()[safe], e["cls"][safe])
@@ -660,24 +658,48 @@ def test_atom_count_intervals_match_oracle(model, dev):
         assert bool(((n >= lo) & (n <= hi)).all())
 
 
-def test_initial_state_matches_reference_sample_init_under_supplied_uniforms(model, dev):
-    """T4 (transition.py:65-69,331-339): the sampler's categorical initial state is arg-max(gumbel(u) + log init_prob); with
-    the uniforms it drew itself (same generator, same order) the oracle's sample_init gives the same classes."""
+def test_initial_state_matches_reference_sample_init(model, dev):
+    """T4 (transition.py:65-69,331-339): pg_sample_init under supplied uniforms against the oracle's sample_init (pinned to
+    the unmodified reference in tests/test_cpu_oracle.py); pg_position_init under supplied normals; and the Philox path:
+    class frequencies follow the prior, and a molecule's initial state does not depend on the batch it is drawn in."""
     from phoregen_b200.diffusion import TrajectorySampler
+    from phoregen_b200.engine import BatchPlan
     m, sd = model
+    na = np.array([5, 9, 7], dtype=np.int32)
+    plan = BatchPlan(na, np.array([4, 6, 5], dtype=np.int32), dev, edge_order=0)
+    g = torch.Generator().manual_seed(12)
+    for kind, trans, K, rows in (("node", m.node_transition, 12, plan.Nl), ("edge", m.edge_transition, 6, plan.Eb)):
+        u = torch.rand(rows, K, generator=g)
+        onehot, cls, log_vt = plan.sample_init(kind, trans.init_log_prob(), uniform=u.to(dev))
+        want_cls, want_log = O.sample_init(trans.init_prob, u)
+        assert torch.equal(cls.cpu().long(), want_cls) and torch.equal(onehot.cpu().argmax(-1), want_cls)
+        assert torch.allclose(log_vt.cpu(), want_log)
+    z = torch.randn(plan.Nl, 3, generator=g)
+    c = torch.tensor([0.5, -1.0, 2.0])
+    assert torch.equal(plan.position_init(center=c.to(dev), normal=z.to(dev)).cpu(), z - c)     # diffusion.py:406
+    # Philox path: prior frequencies (tomask: last atom class ~ 0.989; absorb: bond class 0 ~ 0.952), unit normal positions
+    big = BatchPlan(np.full(400, 30, np.int32), np.full(400, 7, np.int32), dev, edge_order=0)
+    st = big.molecule_streams(2032)
+    _, ncls, _ = big.sample_init("node", m.node_transition.init_log_prob(), seed=2032, streams=st)
+    _, ecls, _ = big.sample_init("edge", m.edge_transition.init_log_prob(), seed=2032, streams=st)
+    assert abs(float((ncls == 11).float().mean()) - float(m.node_transition.init_prob[-1])) < 0.01
+    assert abs(float((ecls == 0).float().mean()) - float(m.edge_transition.init_prob[0])) < 0.005
+    pos = big.position_init(seed=2032, streams=st)
+    assert abs(float(pos.std()) - 1.0) < 0.02 and abs(float(pos.mean())) < 0.02
+    # batch independence: molecule uid 7 alone == molecule uid 7 inside a batch of other molecules
     b = O.synthetic_batch(5, 3, n_atoms=(5, 9))
-    s = TrajectorySampler(m, None, 3, dev, ligand_num_atoms=b["num_atoms"], save_traj=False, seed=77, use_cuda_graph=False, phore_batch=b["phore"])
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(77)
-    Nl, Eb = s.plan.Nl, s.plan.Eb
-    z = torch.randn(Nl, 3, device=dev, generator=gen)
-    u_node = torch.rand(Nl, 12, device=dev, generator=gen)
-    u_edge = torch.rand(Eb, 6, device=dev, generator=gen)
-    for trans, u, cls, onehot, logp in ((m.node_transition, u_node, s.node_cls, s.h_node, s.log_node), (m.edge_transition, u_edge, s.edge_cls, s.h_edge, s.log_edge)):
-        want_cls, want_log = O.sample_init(trans.init_prob, u.cpu())
-        assert torch.equal(cls.cpu().long(), want_cls)
-        assert torch.equal(onehot.cpu().argmax(-1), want_cls) and torch.allclose(logp.cpu(), want_log)
-    assert torch.equal(s.pos, z)          # centre 0 for pharmacophore batches without centres
+    s_all = TrajectorySampler(m, None, 3, dev, ligand_num_atoms=b["num_atoms"], save_traj=False, seed=77, use_cuda_graph=False,
+                              phore_batch=b["phore"], graph_uid=[3, 7, 11])
+    n1 = int(b["num_atoms"][1]); a0 = int(b["num_atoms"][0]); e0 = a0 * (a0 - 1)
+    pm_ = b["phore"]["batch"] == 1
+    one = dict(x=b["phore"]["x"][pm_], pos=b["phore"]["pos"][pm_], norm=b["phore"]["norm"][pm_], batch=torch.zeros(int(pm_.sum()), dtype=torch.long))
+    s_one = TrajectorySampler(m, None, 1, dev, ligand_num_atoms=b["num_atoms"][1:2], save_traj=False, seed=77, use_cuda_graph=False,
+                              phore_batch=one, graph_uid=[7])
+    assert torch.equal(s_all.pos[a0:a0 + n1], s_one.pos) and torch.equal(s_all.node_cls[a0:a0 + n1], s_one.node_cls)
+    assert torch.equal(s_all.edge_cls[e0:e0 + n1 * (n1 - 1)], s_one.edge_cls)
+    s_all.run(3); s_one.run(3)
+    assert torch.equal(s_all.pos[a0:a0 + n1], s_one.pos) and torch.equal(s_all.node_cls[a0:a0 + n1], s_one.node_cls)
+    assert torch.equal(s_all.edge_cls[e0:e0 + n1 * (n1 - 1)], s_one.edge_cls)
 
 
 # ---------------------------------------------------------------- multi-pharmacophore batches: guidance, centres, devices
@@ -749,3 +771,41 @@ def test_plan_cache_distinguishes_batches_with_equal_sizes(model, dev):
         got = _forward(m, b, [300, 20], dev)          # same model object: the second call must rebuild the plan
         for g_, w_, what in zip(got[:3], want[:3], ("logits_node", "pos", "logits_edge")):
             assert_close(g_, w_, f"{what} with phore counts {(p0, p1)}", rtol=2e-3, atol=2e-4)
+
+
+# ---------------------------------------------------------------- configs[2]: many pharmacophores x many samples, sharded
+def test_sharded_job_is_bit_identical_to_single_rank_job(model, dev):
+    """runner.SamplingJob (sample_all.py:69-94 as one molecule-sharded job): 5 pharmacophores x 6 samples, atom counts from
+    the device count heads, guidance on (per-graph phore centres).  The records of rank 0 + rank 1 of a 2-rank job, and of
+    a 1-rank job with another batch size, are bit-identical molecule by molecule (per-molecule kernels and Philox streams)."""
+    from phoregen_b200.runner import SamplingJob, order_by_item
+    from phoregen_b200.testing import PhoreData
+    m, _ = model
+    rng = np.random.default_rng(23)
+    phores = []
+    for i, (p, n_ex) in enumerate([(6, 0), (7, 30), (8, 0), (5, 50), (6, 10)]):
+        x, pos, nrm = O.synthetic_phore(rng, p, n_ex)
+        phores.append(PhoreData(torch.from_numpy(x), torch.from_numpy(pos), torch.from_numpy(nrm), center=torch.tensor([float(i), 0.0, -1.0]), name=f"ph{i}"))
+    opts = [dict(type="atom_prox", min_d=1.2, max_d=1.9), dict(type="center_prox")]
+    kw = dict(seed=99, guidance=opts)
+    single = SamplingJob(m, phores, 6, dev, batch_size=1024, **kw)
+    assert single.num_atoms.shape == (30,) and single.intervals is not None
+    lo, hi = single.intervals
+    assert bool(((single.num_atoms >= np.repeat(lo, 6)) & (single.num_atoms <= np.repeat(hi, 6))).all())
+    ref = order_by_item(single.run(num_steps=4))
+    assert ref["item"].tolist() == list(range(30))
+    parts = []
+    for rank in (0, 1):
+        job = SamplingJob(m, phores, 6, dev, batch_size=4, rank=rank, world_size=2, **kw)      # several ragged batches per rank
+        assert np.array_equal(job.num_atoms, single.num_atoms) and len(job.batches) >= 3
+        parts.append(job.run(num_steps=4))
+    merged = order_by_item({k: torch.cat([p[k] for p in parts]) for k in parts[0]})
+    for k in ref:
+        assert torch.equal(merged[k], ref[k]), k
+    assert bool(torch.isfinite(ref["pos"]).all())
+    # explicit atom counts (the synthetic benchmarks bypass the count heads), mixed single- and multi-chunk molecules
+    na = np.array([12, 40, 33, 36, 9, 50] * 5)
+    a = order_by_item(SamplingJob(m, phores, 6, dev, ligand_num_atoms=na, batch_size=7, seed=5).run(num_steps=2))
+    b = order_by_item(SamplingJob(m, phores, 6, dev, ligand_num_atoms=na, batch_size=30, seed=5).run(num_steps=2, use_cuda_graph=False))
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
