@@ -88,6 +88,24 @@ def big_main():
         torch.save(dict(state_dict_digest=state_dict_digest(sd), cases=cases), os.path.join(GOLD, "forward_big.pt"))
 
 
+def train_main():
+    """python -m oracle.make_golden train -> tests/golden/train_grads.pt: loss and a per-tensor fingerprint of the gradients of
+    the unmodified reference's compute_loss (models/diffusion.py:249-352) + autograd, for the training-tier parity tests."""
+    from phoregen_b200.testing import grad_digest, training_batch_from_synthetic
+    ref, sd, _ = reference_model(0)
+    ref.train()
+    seed, n_graphs, n_atoms, torch_seed = 92, 4, (6, 12), 5
+    data = training_batch_from_synthetic(O.synthetic_batch(seed, n_graphs, n_atoms=n_atoms, edge_order="training"))
+    torch.manual_seed(torch_seed)
+    loss, terms = ref.compute_loss(data)
+    loss.backward()
+    grads = {k: p.grad for k, p in ref.named_parameters() if p.requires_grad and p.grad is not None}
+    fix = dict(seed=seed, n_graphs=n_graphs, n_atoms=list(n_atoms), torch_seed=torch_seed, loss=float(loss), terms=terms,
+               digest=grad_digest(grads), n_params=sum(g.numel() for g in grads.values()), state_dict_digest=state_dict_digest(sd))
+    torch.save(fix, os.path.join(GOLD, "train_grads.pt"))
+    print("train_grads.pt: loss", float(loss), "tensors", len(grads), "params", fix["n_params"])
+
+
 def forward_fixture(ref, seed, n_graphs, n_atoms, times, n_ex=0, stages=True, sd=None):
     seed, margin = well_conditioned_seed(sd, seed, n_graphs, n_atoms, times, n_ex)
     b = O.synthetic_batch(seed, n_graphs, n_atoms=n_atoms, n_ex=n_ex)
@@ -244,4 +262,4 @@ def main():
 
 
 if __name__ == "__main__":
-    big_main() if "big" in sys.argv[1:] else main()
+    big_main() if "big" in sys.argv[1:] else train_main() if "train" in sys.argv[1:] else main()

@@ -177,10 +177,14 @@ class PhoreDiff(nn.Module):
         cnt = self.predict_atom_count(h_phore_emb, batch_phore, h_phore, n_graphs, plan=plan)
         return v, pos, b, cnt
 
-    def compute_loss(self, data, rng_device=None):
-        """Value of the training objective (diffusion.py:249-352) -> (loss_total, loss_dict), forward only: what the
-        reference's validation loop evaluates under no_grad.  The backward pass is not built, so
-        `loss_total` has no autograd graph and `.backward()` on it fails loudly."""
+    def compute_loss(self, data, rng_device=None, provider=None):
+        """The training objective (diffusion.py:249-352) -> (loss_total, loss_dict).
+        With gradients enabled the loss carries an autograd graph over every trainable parameter (training.py: the
+        reference formulation on torch operators, graph artefacts from the CUDA graph kernels).  Under `torch.no_grad()`
+        - the reference's validation loop - the forward runs on the CUDA kernels (losses.py)."""
+        if torch.is_grad_enabled():
+            from . import training
+            return training.compute_loss_with_grad(self, data, provider=provider, rng_device=rng_device)
         from . import losses
         return losses.compute_loss(self, data, rng_device=rng_device)
 

@@ -37,6 +37,17 @@ def state_dict_digest(sd):
     return h.hexdigest()
 
 
+def grad_digest(named_grads, seed=7):
+    """Per-tensor (L2 norm, projection on a seeded direction): a compact fingerprint of the 5.2 M gradient values of one
+    backward pass, small enough to commit as a fixture (tests/golden/train_grads.pt)."""
+    out = {}
+    for k in sorted(named_grads):
+        g = named_grads[k].detach().double().cpu().reshape(-1)
+        r = torch.from_numpy(np.random.default_rng(seed + g.numel()).standard_normal(g.numel()))
+        out[k] = (float(g.norm()), float((g * r).sum()))
+    return out
+
+
 MODEL_CONFIG = {   # `model:` section of reference configs/train_lig-phore.yml with phore_feat_dim += 2 (sample_all.py:41-43)
     "name": "diffusion", "num_atom_classes": 12, "num_bond_classes": 6, "lig_feat_dim": 12, "phore_feat_dim": 18,
     "hidden_dim": 128, "bond_diffusion": True, "bond_net_type": "lin", "bond_len_loss": False,

@@ -615,7 +615,8 @@ def test_compute_loss_value_matches_oracle_forward(model, dev):
             break
         seed += 1000
     torch.manual_seed(9)
-    got_total, got = m.compute_loss(training_batch_from_synthetic(b).to(dev), rng_device="cpu")
+    with torch.no_grad():                              # the validation loop's form: forward on the CUDA kernels, no autograd graph
+        got_total, got = m.compute_loss(training_batch_from_synthetic(b).to(dev), rng_device="cpu")
     assert not got_total.requires_grad
     for k in want:
         assert got[k] == pytest.approx(want[k], rel=2e-3, abs=2e-4), k
@@ -809,3 +810,48 @@ def test_sharded_job_is_bit_identical_to_single_rank_job(model, dev):
     b = order_by_item(SamplingJob(m, phores, 6, dev, ligand_num_atoms=na, batch_size=30, seed=5).run(num_steps=2, use_cuda_graph=False))
     for k in a:
         assert torch.equal(a[k], b[k]), k
+
+
+# ---------------------------------------------------------------- training tier (configs[3])
+def test_training_forward_value_matches_cuda_forward_and_gradients_match_reference_fixture(model, dev):
+    """training.forward_with_grad (torch operators, index artefacts from the CUDA graph kernels) against (a) the CUDA forward on
+    the same perturbed inputs and (b) the fingerprint of the unmodified reference's gradients (tests/golden/train_grads.pt,
+    oracle/make_golden.py train): loss to 1e-5, per-tensor gradient norms / projections to 1e-3, all 5,201,785 parameters."""
+    from phoregen_b200 import losses, training
+    from phoregen_b200.engine import BatchPlan
+    from phoregen_b200.testing import grad_digest, training_batch_from_synthetic
+    from test_cpu_training import check_digest
+    m, sd = model
+    f = load_golden("train_grads.pt")
+    data = training_batch_from_synthetic(O.synthetic_batch(f["seed"], f["n_graphs"], n_atoms=tuple(f["n_atoms"]), edge_order="training")).to(dev)
+    m.train()
+    try:
+        for p in m.parameters():
+            p.grad = None
+        torch.manual_seed(f["torch_seed"])
+        loss, terms = m.compute_loss(data, rng_device="cpu")                   # the fixture's draws were made on the CPU
+        assert loss.requires_grad and float(loss) == pytest.approx(f["loss"], rel=2e-5)
+        loss.backward()
+        grads = {k: p.grad for k, p in m.named_parameters() if p.requires_grad and p.grad is not None}
+        assert sum(g.numel() for g in grads.values()) == f["n_params"] == 5201785
+        check_digest(grad_digest(grads), f["digest"])
+        # (a) same perturbed inputs through the CUDA kernels
+        lig, ll, ph = data["ligand"], data["ligand", "ligand"], data["phore"]
+        torch.manual_seed(f["torch_seed"])
+        pert = losses.perturb(m, lig.pos, lig.x, lig.batch, ll.f_edge_attr, ll.f_edge_attr_batch, f["n_graphs"], "cpu")
+        na = (lig.ptr[1:] - lig.ptr[:-1]).cpu().numpy()
+        plan = BatchPlan(na, torch.bincount(ph.batch).cpu().numpy(), dev, ref_edge_index=ll.f_edge_index)
+        topo = training.Topology(plan, na, torch.bincount(ph.batch).cpu().numpy(), ll.f_edge_index, dev)
+        args = (pert["h_node_pert"], pert["pos_pert"], lig.batch, pert["h_edge_pert"], ll.f_edge_index, ll.f_edge_attr_batch, pert["time_step"],
+                ph.x.float(), ph.pos.float(), ph.norm.float(), ph.batch)
+        with torch.no_grad():
+            want = training.forward_with_grad(m, topo, *args)
+            got = m(*args)
+        for g_, w_, what in zip(got[:3], want[:3], ("logits_node", "pos", "logits_edge")):
+            assert_close(g_, w_, what)
+        assert_close(got[3][0], want[3][0], "count_l")
+        assert_close(got[3][1], want[3][1], "count_u")
+    finally:
+        m.eval()
+        for p in m.parameters():
+            p.grad = None
