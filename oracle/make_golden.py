@@ -106,6 +106,50 @@ def train_main():
     print("train_grads.pt: loss", float(loss), "tensors", len(grads), "params", fix["n_params"])
 
 
+def phores_main():
+    """python -m oracle.make_golden phores -> tests/golden/forward_phores.pt: forward outputs of the unmodified reference on each
+    of its 10 shipped sampling pharmacophores (data/phores_for_sampling, 44-99 nodes of which 40-94 exclusion spheres; read by
+    the reference's own PhoreData_New), two 14- / 17-atom ligands per pharmacophore, plus the sample_nodes interval."""
+    import json
+    from datasets.get_phore_data import PhoreData_New
+    ref, sd, _ = reference_model(0)
+    index = json.load(open("/root/reference/data/phores_for_sampling/file_index.json"))
+    files = [os.path.join("/root/reference", p.lstrip("./")) for p in index]
+    ds = PhoreData_New(files, center="phore", data_name="zinc_300")
+    cases = {}
+    for i, path in enumerate(files):
+        d = ds.get(i)
+        px, ppos, pnorm = d["phore"].x, d["phore"].pos, d["phore"].norm
+        P = px.shape[0]
+        seed = 400 + i
+        while True:
+            b = O.synthetic_batch(seed, 2, n_atoms=(14, 17), pos_scale=2.0)
+            ph = dict(x=px.repeat(2, 1), pos=ppos.repeat(2, 1), norm=pnorm.repeat(2, 1), batch=torch.repeat_interleave(torch.arange(2), P))
+            t = torch.tensor([650, 40])
+            stages = []
+            O.phorediff_forward(sd, b["h_node"], b["pos"], b["batch_node"], b["h_edge"], b["edge_index"], b["batch_edge"], t,
+                                ph["x"], ph["pos"], ph["norm"], ph["batch"], stages=stages)
+            margin = O.forward_knn_margin(stages)
+            if margin >= 5e-4:
+                break
+            print(f"  {os.path.basename(path)} seed {seed}: kNN margin {margin:.2e} too small, next", flush=True)
+            seed += 50
+        with torch.no_grad():
+            out = ref(b["h_node"], b["pos"], b["batch_node"], b["h_edge"], b["edge_index"], b["batch_edge"], t, ph["x"], ph["pos"], ph["norm"], ph["batch"])
+            seen = []
+            import models.diffusion as md
+            orig = md.sample_from_interval
+            md.sample_from_interval = lambda l, u_, bs, mode="uniform", scale=4.0: (seen.append((l, u_)), orig(l, u_, bs, mode=mode, scale=scale))[1]
+            try:
+                ref.sample_nodes(d, 4, "cpu")
+            finally:
+                md.sample_from_interval = orig
+        cases[os.path.basename(path)] = dict(seed=seed, knn_margin=margin, n_phore=P, times=[650, 40], pred_node=out[0], pred_pos=out[1], pred_edge=out[2],
+                                             count_l=out[3][0], count_u=out[3][1], interval=seen[0])
+        print(os.path.basename(path), "nodes", P, "seed", seed, "margin", margin, "interval", seen[0], flush=True)
+    torch.save(dict(state_dict_digest=state_dict_digest(sd), cases=cases), os.path.join(GOLD, "forward_phores.pt"))
+
+
 def forward_fixture(ref, seed, n_graphs, n_atoms, times, n_ex=0, stages=True, sd=None):
     seed, margin = well_conditioned_seed(sd, seed, n_graphs, n_atoms, times, n_ex)
     b = O.synthetic_batch(seed, n_graphs, n_atoms=n_atoms, n_ex=n_ex)
@@ -262,4 +306,5 @@ def main():
 
 
 if __name__ == "__main__":
-    big_main() if "big" in sys.argv[1:] else train_main() if "train" in sys.argv[1:] else main()
+    a = sys.argv[1:]
+    big_main() if "big" in a else train_main() if "train" in a else phores_main() if "phores" in a else main()

@@ -82,3 +82,46 @@ def test_collate_phores(tmp_path):
     b = phore_io.collate_phores([d, d], copies=[2, 1])
     assert b["x"].shape == (15, 18) and b["batch"].tolist() == [0] * 5 + [1] * 5 + [2] * 5
     assert b["center"].shape == (3, 3) and b["names"] == ["m3"] * 3
+
+
+# ---------------------------------------------------------------- the reference's own sampling inputs (configs[0])
+PHORE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "phores")
+
+
+def shipped_phore_files():
+    """The 10 files of reference data/phores_for_sampling (file_index.json order), kept as input fixtures."""
+    import json
+    index = json.load(open(os.path.join(PHORE_DIR, "file_index.json")))
+    return [os.path.join(PHORE_DIR, os.path.basename(p)) for p in index]
+
+
+def test_shipped_phore_files_parse_to_the_surveyed_shapes():
+    files = shipped_phore_files()
+    assert len(files) == 10
+    sizes = []
+    for f in files:
+        d = phore_io.parse_phore_file(f)
+        ph = d["phore"]
+        n, n_ex = ph["x"].shape[0], int((ph["x"][:, 12] == 1).sum())
+        sizes.append((n, n_ex))
+        assert ph["x"].shape == (n, 18) and torch.all(ph["x"][:, :13].sum(-1) == 1) and torch.all(ph["x"][:, 16:18].sum(-1) == 1)
+        assert torch.allclose(ph["pos"].mean(0), torch.zeros(3), atol=1e-4) and 3 <= n - n_ex <= 7
+    assert min(s[0] for s in sizes) == 44 and max(s[0] for s in sizes) == 99          # SURVEY.md §8(d) config[0]
+    assert min(s[1] for s in sizes) == 40 and max(s[1] for s in sizes) == 94
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference not mounted")
+def test_shipped_phore_files_match_the_unmodified_reference_reader():
+    from oracle.shims.install import install
+    install()
+    from datasets.get_phore_data import PhoreData_New
+    files = shipped_phore_files()
+    ref_files = [os.path.join("/root/reference/data/phores_for_sampling", os.path.basename(f)) for f in files]
+    ds = PhoreData_New(ref_files, center="phore", data_name="zinc_300")
+    for i, f in enumerate(files):
+        assert open(f, "rb").read() == open(ref_files[i], "rb").read()               # the fixture IS the reference's input
+        want, got = ds.get(i), phore_io.parse_phore_file(f)
+        for key in ("x", "pos", "norm"):
+            assert torch.equal(got["phore"][key], getattr(want["phore"], key)), (f, key)
+        assert torch.equal(got.center, want.center) and got.name == want.name

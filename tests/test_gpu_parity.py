@@ -855,3 +855,43 @@ def test_training_forward_value_matches_cuda_forward_and_gradients_match_referen
         m.eval()
         for p in m.parameters():
             p.grad = None
+
+
+# ---------------------------------------------------------------- configs[0]: the reference's own sampling inputs
+def test_shipped_pharmacophores_forward_interval_and_sample(model, dev):
+    """The 10 files of reference data/phores_for_sampling (44-99 nodes, 40-94 exclusion spheres; input fixtures under
+    tests/golden/phores): parsed by phore_io, forwarded with two ligands each against the unmodified reference's outputs
+    (oracle/make_golden.py phores), the atom-count interval of sample_nodes exact, and one guided sample() call per file
+    through the reference's entry point (sample_all.py:69-94 with sample.sh's guidance options)."""
+    from phoregen_b200 import phore_io, results as R
+    from test_cpu_phore_io import shipped_phore_files
+    m, _ = model
+    fix = load_golden("forward_phores.pt")["cases"]
+    opts = [dict(type="atom_prox", min_d=1.2, max_d=1.9), dict(type="center_prox")]
+    for path in shipped_phore_files():
+        name = path.split("/")[-1]
+        f = fix[name]
+        d = phore_io.parse_phore_file(path)
+        ph = d["phore"]
+        P = ph["x"].shape[0]
+        assert P == f["n_phore"]
+        b = O.synthetic_batch(f["seed"], 2, n_atoms=(14, 17), pos_scale=2.0)
+        b["phore"] = dict(x=ph["x"].repeat(2, 1), pos=ph["pos"].repeat(2, 1), norm=ph["norm"].repeat(2, 1), batch=torch.repeat_interleave(torch.arange(2), P))
+        got = _forward(m, b, f["times"], dev)
+        assert_close(got[0], f["pred_node"], f"{name} logits_node")
+        assert_close(got[1], f["pred_pos"], f"{name} pos")
+        assert_close(got[2], f["pred_edge"], f"{name} logits_edge")
+        assert_close(got[3][0], f["count_l"], f"{name} count_l")
+        assert_close(got[3][1], f["count_u"], f"{name} count_u")
+        assert m.sample_nodes(d, 4, dev, return_interval=True) == tuple(f["interval"]), name
+    # one guided sampling call on the largest pharmacophore, atom counts from the count heads (32-46 atoms: chunked kernels too)
+    d = phore_io.parse_phore_file([p for p in shipped_phore_files() if "P43254" in p][0])
+    torch.manual_seed(0)
+    res = m.sample(d, 4, dev, pos_guidance_opt=opts, seed=3, num_steps=3)
+    lo, hi = fix["P43254_merge.phore"]["interval"]
+    n_atoms = res["lig_info"][0]
+    assert bool(((n_atoms >= lo) & (n_atoms <= hi)).all())
+    host = {k: [v.cpu() for v in vals] for k, vals in res.items()}               # sample_all.py:104
+    mols = R.unbatch_data(host, 4)
+    assert [len(x["pred"][0]) for x in mols] == n_atoms.tolist() and all(bool(torch.isfinite(x["pred"][1]).all()) for x in mols)
+    assert len(mols[0]["traj"][2]) == 1001 and mols[0]["traj"][2][2].shape == (int(n_atoms[0]) * (int(n_atoms[0]) - 1), 6)
