@@ -98,7 +98,7 @@ struct TripTcArgs {
     const float* H; long long ldh; int hk_k, hj_k, hk_v, hj_v;
     const float* q;                        // [Eb,128]
     float* R;                              // [Eb,256] work space: smear(d_e) @ Wrji
-    float* P;                              // [Eb,256] work space: per-edge partial of the first Linear (k->j role)
+    float* P;                              // [2][Eb,132] work space: per-edge partial of the first Linear (k->j role), key | value halves, padded rows
     const float *wrkj, *wrji;              // [20][256] fp32
     const uint16_t *w2k_bf, *w2v_bf;       // [hi|lo][128][128] bf16, K-major
     const uint16_t* w2k_h;                 // [128][128] fp16, K-major: the key MLP's second Linear at single precision-16
@@ -109,6 +109,7 @@ struct TripTcArgs {
     float* hb;
     int maxn;
 };
+constexpr int PG_TRIP_P_STRIDE = 132;                 // floats per row of one half of P (128 channels + 16 bytes: shared-memory staging layout)
 constexpr int PG_TRIP_TC_SINGLE_CHUNK_ATOMS = 34;   // n - 2 <= 32: the single-chunk instantiation serves the batch
 int pg_launch_trip_pr(const TripTcArgs& a, cudaStream_t s);               // per-edge partials P, R (elementwise, HBM-bound)
 int pg_launch_trip_tc(const TripTcArgs& a, int num_sms, cudaStream_t s);  // the tcgen05 triplet kernel proper

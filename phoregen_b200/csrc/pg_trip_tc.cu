@@ -40,7 +40,11 @@ extern "C" int pg_debug_trip_trace(long long* h_out) { return cudaMemcpyFromSymb
 #endif
 
 namespace {
-constexpr int PS_LD = 260;                 // padded row stride of the staged P rows (conflict-free LDS.128 across rows)
+// Staged P rows.  trip_pr_kernel writes the key and the value halves of P to two arrays [Eb][132]: 128 channels + 4 floats of
+// padding per row, i.e. already in the shared-memory layout.  The rows of a unit (or of one 32-row chunk of it) are then ONE
+// contiguous block per half, staged by a single bulk copy instead of one per row, and a warp's row-per-lane LDS.128 (row
+// stride 528 B = 33 x 16 B) touches every bank exactly once per 8 lanes.
+constexpr int PS_HALF = PG_TRIP_P_STRIDE;  // floats per row of one half (132)
 // staged P rows: all n-1 rows of a unit while a segment is one chunk (n-1 <= 33), else the 33 rows of one chunk
 __host__ __device__ constexpr int ps_rows(int maxn) { return maxn - 1 < 33 ? maxn - 1 : 33; }
 constexpr int W_TILE = 32768;              // one [128 x 128] bf16 matrix in two 128B-swizzled K blocks
@@ -173,8 +177,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
     float* sB2 = sLn + 4 * 128;                     // b2k, b2v
     uint64_t* bars = (uint64_t*)(sB2 + 2 * 128);
     uint32_t* tmem_slot = (uint32_t*)(bars + B_COUNT);
-    float* sPs = (float*)(smem + SM_FIXED);         // [min(maxn-1, 33)][260]
-    float* sX = sPs + (size_t)ps_rows(a.maxn) * PS_LD; // [2][maxn][4] ligand coordinates of the current / next unit
+    float* sPs = (float*)(smem + SM_FIXED);         // [k|v][min(maxn-1, 33)][132] (see PS_HALF)
+    const int psr = ps_rows(a.maxn);
+    float* sX = sPs + (size_t)2 * psr * PS_HALF;    // [2][maxn][4] ligand coordinates of the current / next unit
     const PlanDev& d = a.d;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wq = warp & 3;
@@ -251,10 +256,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             uint64_t* bar = &bars[mlp == 0 ? B_PSK : B_PSV];
             // rows k -> j of chunk c: segment rows [32c, 32c+32) map to unit rows [32c, 32c+33) (the row k = i is skipped)
             const int r0 = t.chunk * 32, nr = min(33, t.n - 1 - r0);
-            if (lane == 0) tc::mbar_arrive_expect_tx(bar, (uint32_t)nr * 512u);
+            if (lane == 0) tc::mbar_arrive_expect_tx(bar, (uint32_t)nr * (PS_HALF * 4u));
             __syncwarp();
-            const float* src = a.P + (size_t)(t.eoff + (long long)t.jl * (t.n - 1) + r0) * 256 + mlp * 128;
-            for (int r = lane; r < nr; r += 32) tc::bulk_copy_g2s(sPs + (size_t)r * PS_LD + mlp * 128, src + (size_t)r * 256, 512u, bar);
+            const float* src = a.P + (size_t)mlp * a.d.Eb * PS_HALF + (size_t)(t.eoff + (long long)t.jl * (t.n - 1) + r0) * PS_HALF;
+            if (lane == 0) tc::bulk_copy_g2s(sPs + (size_t)mlp * psr * PS_HALF, src, (uint32_t)nr * (PS_HALF * 4u), bar);   // one copy per half
         };
         // angle slice of the first Linear for one MLP of tile `tl` (operand buffer tl & 1) -> pre-activation columns `dcol`
         auto feat_mma = [&](int tl, int mlp, uint32_t dcol, uint64_t* bar) {
@@ -416,7 +421,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
                 for (int i = 0; i < 16; i++) x2[i] = make_float2(__uint_as_float(xu[2 * i]), __uint_as_float(xu[2 * i + 1]));
             }
             float2 s1 = make_float2(0.f, 0.f), s2 = s1, s1b = s1, s2b = s1;
-            const float* prow = sPs + trow * PS_LD + c0;
+            const float* prow = sPs + ((size_t)mlp * psr + trow) * PS_HALF + cq * 32;
             const float* rrow = sR + wq * 256 + c0;
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
@@ -690,8 +695,9 @@ __global__ void __launch_bounds__(256, 2) trip_pr_kernel(TripTcArgs a) {
         if (e >= d.Eb) break;
         st4(a.R + (size_t)e * 256 + lane * 4, f4(acc[k][0], acc[k][1]));
         st4(a.R + (size_t)e * 256 + 128 + lane * 4, f4(acc[k][2], acc[k][3]));
-        st4(a.P + (size_t)e * 256 + lane * 4, f4(acc[k][4], acc[k][5]));
-        st4(a.P + (size_t)e * 256 + 128 + lane * 4, f4(acc[k][6], acc[k][7]));
+        // P: key / value halves in separate arrays of padded rows (the staging layout of trip_tc_kernel)
+        st4(a.P + (size_t)e * PS_HALF + lane * 4, f4(acc[k][4], acc[k][5]));
+        st4(a.P + (size_t)d.Eb * PS_HALF + (size_t)e * PS_HALF + lane * 4, f4(acc[k][6], acc[k][7]));
     }
 }
 }  // namespace
@@ -703,7 +709,7 @@ int pg_launch_trip_pr(const TripTcArgs& a, cudaStream_t s) {
     return PG_OK;
 }
 
-size_t pg_trip_tc_smem(int maxn) { return (size_t)SM_FIXED + ((size_t)ps_rows(maxn) * PS_LD + 2 * (size_t)maxn * 4) * sizeof(float) + 1024; }
+size_t pg_trip_tc_smem(int maxn) { return (size_t)SM_FIXED + ((size_t)2 * ps_rows(maxn) * PS_HALF + 2 * (size_t)maxn * 4) * sizeof(float) + 1024; }
 
 int pg_launch_trip_tc(const TripTcArgs& a, int num_sms, cudaStream_t s) {
     if (a.d.Nl <= 0) return PG_OK;

@@ -188,3 +188,44 @@ def test_oracle_sampling_entry_pieces_match_unmodified_reference_live(sd):
     want = torch.autograd.grad(e1, xt)[0] + torch.autograd.grad(e2, xt)[0]
     got = O.guidance_grad(xt.detach(), bn, onehot.argmax(-1), ei, eb, [dict(type="atom_prox", min_d=1.2, max_d=1.9), dict(type="center_prox")], centre, 3)
     assert_close(got, want, "guidance gradient", rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference not mounted")
+def test_reference_side_caller_code_runs_on_the_mirror():
+    """Reference-side caller code against the drop-in's module tree: `freeze_parameters` (utils/training_utils.py:18-26)
+    walks denoiser.num_layers / base_block[i].pos_layer_with_edge|bond, `get_parameter_number` (:12-15) counts the
+    parameters, and the reference's own PhoreDiff constructs with OUR get_denoiser_net / get_phore_encoder swapped in
+     and still loads the 641-key checkpoint strictly."""
+    import yaml
+    from oracle.shims.install import EasyDict, install
+    install()
+    # utils/training_utils.py imports the whole dataset stack (lmdb, rdkit, PyG transforms) at module level: run the two
+    # functions' own source, taken from the reference file at test time, without the module's imports
+    import ast
+    src = open("/root/reference/utils/training_utils.py").read()
+    fns = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name in ("freeze_parameters", "get_parameter_number")]
+    ns = {}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), "/root/reference/utils/training_utils.py", "exec"), ns)
+    freeze_parameters, get_parameter_number = ns["freeze_parameters"], ns["get_parameter_number"]
+    mirror, sd = build_model()
+    assert "5.5688 M" in get_parameter_number(mirror) and "5.2018 M" in get_parameter_number(mirror)
+    frozen = freeze_parameters(mirror, EasyDict(freeze_pos=True))
+    pos = [p for l in frozen.denoiser.base_block for m_ in (l.pos_layer_with_edge, l.pos_layer_with_bond) for p in m_.parameters()]
+    assert len(pos) == 6 * 2 * 18 and not any(p.requires_grad for p in pos)
+    assert all(p.requires_grad for p in frozen.denoiser.base_block[0].bond_layer.parameters())
+    # the reference's PhoreDiff with our factories
+    import models
+    import models.diffusion as md
+    from phoregen_b200 import modules as ours
+    cfg = EasyDict(yaml.safe_load(open("/root/reference/configs/train_lig-phore.yml")))
+    cfg.model.phore_feat_dim += 2
+    orig = (md.get_denoiser_net, md.get_phore_encoder)
+    md.get_denoiser_net, md.get_phore_encoder = ours.get_denoiser_net, ours.get_phore_encoder
+    try:
+        hybrid = md.PhoreDiff(cfg.model, "zinc_300")
+    finally:
+        md.get_denoiser_net, md.get_phore_encoder = orig
+    assert isinstance(hybrid.denoiser, ours.UniTransformerO2TwoUpdateGeneralBond)
+    hybrid.load_state_dict(sd, strict=True)
+    assert len(hybrid.state_dict()) == 641
