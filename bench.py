@@ -57,12 +57,16 @@ def f_ref_flops(n, p):
 
 def f_exec_trip_flops(n):
     """bf16 tensor FLOPs the tcgen05 triplet kernel actually issues per molecule-layer (DESIGN.md 'Triplet kernel'):
-    per 128-row tile (4 segments x 32 lanes) 3 MMAs M128 N256 K16 (angle slice, bf16x3) + 2 x 24 MMAs M128 N128 K16
-    (second Linear of the key / value MLPs, bf16x3); ceil((n-1)/4) segment groups per ligand atom, one tile per 32-row
-    chunk of a group.  Includes the padding rows and the x3 of the hi/lo split: the work the tensor pipe really performs."""
-    tiles = n * ((n - 1 + 3) // 4) * max((n - 2 + 31) // 32, 1)
-    macs_per_tile = 3 * 128 * 256 * 16 + 48 * 128 * 128 * 16
-    return 2.0 * tiles * macs_per_tile
+    per 128-row tile (4 segments x 32 lanes) and per MLP: 3 MMAs M128 N128 K16 (angle + R slab, bf16x3), 2 per K16 slab
+    of staged P rows (one-hot x hi / lo image; ceil(rows/16) slabs) and 24 MMAs M128 N128 K16 (second Linear, bf16x3);
+    ceil((n-1)/4) segment groups per ligand atom, one tile per 32-row chunk of the unit's n-1 rows.  Includes the
+    padding rows and the x3 of the hi/lo split: the work the tensor pipe really performs."""
+    groups = (n - 1 + 3) // 4
+    mmas = 0
+    for c in range(max((n - 1 + 31) // 32, 1)):
+        rows = min(32, n - 1 - 32 * c)
+        mmas += 2 * (3 + 2 * ((rows + 15) // 16) + 24)
+    return 2.0 * n * groups * mmas * 128 * 128 * 16
 
 
 class ClockSampler:

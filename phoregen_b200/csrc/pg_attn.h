@@ -97,20 +97,19 @@ struct TripTcArgs {
     const float* T; long long ldt; int t_k, t_v;
     const float* H; long long ldh; int hk_k, hj_k, hk_v, hj_v;
     const float* q;                        // [Eb,128]
-    float* R;                              // [Eb,256] work space: smear(d_e) @ Wrji
-    float* P;                              // [2][Eb,132] work space: per-edge partial of the first Linear (k->j role), key | value halves, padded rows
+    float* R;                              // [2][Eb,128] work space: smear(d_e) @ Wrji as bf16 hi/lo operand images (key | value), indexed by the source atom's unit
+    float* P;                              // [2][Eb,128] work space: per-edge partial of the first Linear (k->j role) as bf16 hi/lo operand images (key | value)
     const float *wrkj, *wrji;              // [20][256] fp32
     const uint16_t *w2k_bf, *w2v_bf;       // [hi|lo][128][128] bf16, K-major
     const uint16_t* w2k_h;                 // [128][128] fp16, K-major: the key MLP's second Linear at single precision-16
-    const uint16_t* wa_bf;                 // [hi|lo][256][16] bf16 (angle slice, 13 used)
+    const uint16_t* wa_bf;                 // angle slab image [mlp][hi|lo][half][16][64] bf16, MN-major SW128 (weights.angle_slab_image)
     int flags;                             // switches (PG_TRIP_FLAGS): bit 0 = shuffle-butterfly softmax instead of REDUX; bit 1 = key MLP in bf16x3
     const float *lnk_g, *lnk_b, *lnv_g, *lnv_b, *b2k, *b2v;
     const float *lnk_bf, *lnv_bf, *fold;   // beta (/ gamma where folded into the W2 images), fold flags (see AttnW)
     float* hb;
     int maxn;
 };
-constexpr int PG_TRIP_P_STRIDE = 132;                 // floats per row of one half of P (128 channels + 16 bytes: shared-memory staging layout)
-constexpr int PG_TRIP_TC_SINGLE_CHUNK_ATOMS = 34;   // n - 2 <= 32: the single-chunk instantiation serves the batch
+constexpr int PG_TRIP_TC_SINGLE_CHUNK_ATOMS = 33;   // n - 1 <= 32 staged rows: the single-chunk instantiation serves the molecule
 int pg_launch_trip_pr(const TripTcArgs& a, cudaStream_t s);               // per-edge partials P, R (elementwise, HBM-bound)
 int pg_launch_trip_tc(const TripTcArgs& a, int num_sms, cudaStream_t s);  // the tcgen05 triplet kernel proper
 size_t pg_trip_tc_smem(int maxn);

@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
     uint32_t* tmem_slot = (uint32_t*)(bars + B_COUNT);
     volatile int* sProg = (volatile int*)(tmem_slot + 1);   // tiles whose value LayerNorm is done (pacing of the prefetch warps)
     const PlanDev& d = a.d;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // provably warp-uniform: the role branches and the MMA issuer's descriptor arithmetic stay on the uniform datapath
     const int wq = warp & 3;
     constexpr int NV = POS ? 16 : 128;              // outputs of the value MLP's second Linear
 
@@ -139,15 +140,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
                 for (int mlp = 0; mlp < 2; mlp++) {
                     tc::mbar_wait_wd(&bars[mlp == 0 ? B_HIDK : B_HIDV], ph);
                     tc::tc_fence_after();
-                    if (lane == 0 && KF16 && mlp == 0) {
+                    // warp-collective issue (pg_tc.cuh): descriptor arithmetic on the uniform datapath, one elected lane issues
+                    if (KF16 && mlp == 0) {
                         constexpr uint32_t idesc16 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // A, B = F16
 #pragma unroll
                         for (int ks = 0; ks < 8; ks++) {
                             const uint64_t bd = tc::umma_desc_sw128(sW_u32 + (ks >> 2) * 16384 + (ks & 3) * 32);
-                            tc::umma_bf16_ts(tmem + C_OUTK, tmem + C_HIDK + ks * 8, bd, idesc16, ks > 0);
+                            tc::umma_bf16_ts_w(tmem + C_OUTK, tmem + C_HIDK + ks * 8, bd, idesc16, ks > 0);
                         }
-                        tc::umma_commit(&bars[B_OUTK]);
-                    } else if (lane == 0) {
+                        tc::umma_commit_w(&bars[B_OUTK]);
+                    } else {
                         const uint32_t hid = tmem + (mlp == 0 ? C_HIDK : C_HIDV);
                         const uint32_t dcol = tmem + (mlp == 0 ? C_OUTK : C_OUTV);
                         uint32_t acc = 0;
@@ -158,11 +160,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
 #pragma unroll
                             for (int ks = 0; ks < 8; ks++) {
                                 const uint64_t bd = tc::umma_desc_sw128(bbase + (ks >> 2) * 16384 + (ks & 3) * 32);
-                                tc::umma_bf16_ts(dcol, abase + ks * 8, bd, mlp == 0 ? idesc_k : idesc_v, acc);
+                                tc::umma_bf16_ts_w(dcol, abase + ks * 8, bd, mlp == 0 ? idesc_k : idesc_v, acc);
                                 acc = 1;
                             }
                         }
-                        tc::umma_commit(&bars[mlp == 0 ? B_OUTK : B_OUTV]);
+                        tc::umma_commit_w(&bars[mlp == 0 ? B_OUTK : B_OUTV]);
                     }
                     __syncwarp();
                 }

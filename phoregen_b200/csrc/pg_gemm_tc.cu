@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(GemmArgs a) {
     float* sEpi = (float*)(sB + NB * B_BUF);
     uint64_t* bars = (uint64_t*)(sB + NB * B_BUF + EPI_BYTES);
     uint32_t* tmem_slot = (uint32_t*)(bars + NBARS);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // provably warp-uniform: the role branches and the MMA issuer's descriptor arithmetic stay on the uniform datapath
     const long long n_mtiles = (a.M + TM - 1) / TM;
 
     if (warp == MMA_WARP) tc::tmem_alloc<2 * TN>(tmem_slot);
@@ -210,28 +211,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(GemmArgs a) {
                 tc::mbar_wait_wd(&bars[B_FULL + s], (cnt / NB) & 1);
                 tc::mbar_wait_wd(&bars[ACC_EMPTY + ab], ((cnt >> 1) & 1) ^ 1);
                 tc::tc_fence_after();
-                if (lane == 0) {
-                    uint32_t acc = 0;
+                // warp-collective issue (pg_tc.cuh): descriptor arithmetic on the uniform datapath, one elected lane issues
+                uint32_t acc = 0;
 #pragma unroll
-                    for (int combo = 0; combo < 3; combo++) {       // hi*hi, hi*lo, lo*hi
-                        const uint32_t abase = sA_u32 + buf * A_BUF + (combo == 2 ? 2 * A_KBLK : 0);
-                        const uint32_t bbase = sB_u32 + s * B_BUF + (combo == 1 ? 2 * B_KBLK : 0);
+                for (int combo = 0; combo < 3; combo++) {       // hi*hi, hi*lo, lo*hi
+                    const uint32_t abase = sA_u32 + buf * A_BUF + (combo == 2 ? 2 * A_KBLK : 0);
+                    const uint32_t bbase = sB_u32 + s * B_BUF + (combo == 1 ? 2 * B_KBLK : 0);
 #pragma unroll
-                        for (int kb = 0; kb < 2; kb++) {
+                    for (int kb = 0; kb < 2; kb++) {
 #pragma unroll
-                            for (int k = 0; k < 4; k++) {           // 4 x K=16 slices (32 B) inside the 128-byte swizzle row
-                                const uint64_t ad = tc::umma_desc_sw128(abase + kb * A_KBLK + k * 32);
-                                const uint64_t bd = tc::umma_desc_sw128(bbase + kb * B_KBLK + k * 32);
-                                tc::umma_bf16(tmem_base + ab * TN, ad, bd, idesc, acc);
-                                acc = 1;
-                            }
+                        for (int k = 0; k < 4; k++) {           // 4 x K=16 slices (32 B) inside the 128-byte swizzle row
+                            const uint64_t ad = tc::umma_desc_sw128(abase + kb * A_KBLK + k * 32);
+                            const uint64_t bd = tc::umma_desc_sw128(bbase + kb * B_KBLK + k * 32);
+                            tc::umma_bf16_w(tmem_base + ab * TN, ad, bd, idesc, acc);
+                            acc = 1;
                         }
                     }
-                    tc::umma_commit(&bars[ACC_FULL + ab]);          // accumulator ready for the epilogue
-                    tc::umma_commit(&bars[B_EMPTY + s]);            // weight stage may be refilled
-                    if (nt == a.ntiles - 1) tc::umma_commit(&bars[A_EMPTY + buf]);
                 }
-                __syncwarp();
+                tc::umma_commit_w(&bars[ACC_FULL + ab]);          // accumulator ready for the epilogue
+                tc::umma_commit_w(&bars[B_EMPTY + s]);            // weight stage may be refilled
+                if (nt == a.ntiles - 1) tc::umma_commit_w(&bars[A_EMPTY + buf]);
             }
         }
     }

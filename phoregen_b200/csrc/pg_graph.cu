@@ -72,7 +72,7 @@ void carve(Carver& c, const Sizes& s, int G, PgPlan* pl) {
     float* dx1 = F(s.N * 3 + 4); float* dx2 = F(s.N * 3 + 4);
     float* ebuf = F(s.Eb * 640);
     float* qt = F(s.Eb * 128);
-    float* rbuf = F(s.Eb * 256); float* pbuf2 = F(s.Eb * 264 + 64); float* abuf = F(s.Ek * 16 + s.N * 16);
+    float* rbuf = F(s.Eb * 256); float* pbuf2 = F(s.Eb * 256 + 64); float* abuf = F(s.Ek * 16 + s.N * 16);
     float* ew = F(s.Ek); float* comb = F(s.N * 3 + 4);
     int* knn_src = I(s.Ek);
     float* pbuf = F(s.P * 640); float* pq = F(s.P * 128); float* pemb = F(s.P * 128);

@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
     uint64_t* bars = (uint64_t*)(sB2 + 128);
     uint32_t* tmem_slot = (uint32_t*)(bars + B_COUNT);
     const PlanDev& d = a.d;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // provably warp-uniform: the role branches and the MMA issuer's descriptor arithmetic stay on the uniform datapath
     const int wq = warp & 3;
     constexpr int NOUT = (PASS == 1 && POS) ? 16 : 128;     // outputs of this pass's second Linear
 
@@ -191,20 +192,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
         constexpr uint32_t idesc_w = tc::umma_idesc_bf16(128, NOUT);
         const uint32_t sW_u32 = tc::smem_u32(sW), sTab_u32 = tc::smem_u32(sTab), sFeat_u32 = tc::smem_u32(sFeat);
         auto table_mma = [&]() {                                // MMA warp only
-            if (lane == 0) {
-                uint32_t acc = 0;
+            // warp-collective issue (pg_tc.cuh): descriptor arithmetic on the uniform datapath, one elected lane issues
+            uint32_t acc = 0;
 #pragma unroll
-                for (int combo = 0; combo < 3; combo++) {       // hi*hi, hi*lo, lo*hi
-                    const uint32_t fb = sFeat_u32 + (combo == 2 ? FEAT_PART : 0), wb = sTab_u32 + (combo == 1 ? TAB_PART : 0);
+            for (int combo = 0; combo < 3; combo++) {       // hi*hi, hi*lo, lo*hi
+                const uint32_t fb = sFeat_u32 + (combo == 2 ? FEAT_PART : 0), wb = sTab_u32 + (combo == 1 ? TAB_PART : 0);
 #pragma unroll
-                    for (int ks = 0; ks < KF / 16; ks++) {
-                        tc::umma_bf16(tmem + C_PRE, tc::umma_desc_k16_noswizzle(fb + ks * 4096), tc::umma_desc_k16_noswizzle(wb + ks * 4096), idesc_t, acc);
-                        acc = 1;
-                    }
+                for (int ks = 0; ks < KF / 16; ks++) {
+                    tc::umma_bf16_w(tmem + C_PRE, tc::umma_desc_k16_noswizzle(fb + ks * 4096), tc::umma_desc_k16_noswizzle(wb + ks * 4096), idesc_t, acc);
+                    acc = 1;
                 }
-                tc::umma_commit(&bars[B_PRE]);
             }
-            __syncwarp();
+            tc::umma_commit_w(&bars[B_PRE]);
         };
         int s_cur = row_src(blockIdx.x);
         int s_nxt = row_src(blockIdx.x + gridDim.x);
@@ -233,15 +232,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
                 tc::mbar_wait_wd(&bars[B_HID], ph);
                 KTRACE(1, 3);
                 tc::tc_fence_after();
-                if (lane == 0 && KF16) {
+                if (KF16) {
                     constexpr uint32_t idesc16 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // A, B = F16
 #pragma unroll
                     for (int ks = 0; ks < 8; ks++) {
                         const uint64_t bd = tc::umma_desc_sw128(sW_u32 + (ks >> 2) * 16384 + (ks & 3) * 32);
-                        tc::umma_bf16_ts(tmem + C_OUT + ph * 128, tmem + C_HID + ks * 8, bd, idesc16, ks > 0);
+                        tc::umma_bf16_ts_w(tmem + C_OUT + ph * 128, tmem + C_HID + ks * 8, bd, idesc16, ks > 0);
                     }
-                    tc::umma_commit(&bars[B_OUT]);
-                } else if (lane == 0) {
+                    tc::umma_commit_w(&bars[B_OUT]);
+                } else {
                     const uint32_t dcol = tmem + C_OUT + ph * 128;
                     uint32_t acc = 0;
 #pragma unroll
@@ -251,13 +250,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
 #pragma unroll
                         for (int ks = 0; ks < 8; ks++) {
                             const uint64_t bd = tc::umma_desc_sw128(bbase + (ks >> 2) * 16384 + (ks & 3) * 32);
-                            tc::umma_bf16_ts(dcol, abase + ks * 8, bd, idesc_w, acc);
+                            tc::umma_bf16_ts_w(dcol, abase + ks * 8, bd, idesc_w, acc);
                             acc = 1;
                         }
                     }
-                    tc::umma_commit(&bars[B_OUT]);
+                    tc::umma_commit_w(&bars[B_OUT]);
                 }
-                __syncwarp();
                 KTRACE(1, 4);
                 if (more) {
                     tc::mbar_wait_wd(&bars[B_FEAT], ph ^ 1);   // features of the next tile (pre columns are free: HID(t) has fired)

@@ -18,8 +18,8 @@ struct PgPlan {
     float* ebuf;                  // [Eb,640] edge GEMM outputs
     float* qt;                    // [Eb,128] per-edge triplet queries / head hidden
     float* abuf;                  // [Ek,16] + [N,16] attention weights of the tcgen05 kNN attention (key pass -> value pass)
-    float* rbuf;                  // [Eb,256] r_ji slice of the triplet MLPs (tcgen05 triplet kernel)
-    float* pbuf2;                 // [2][Eb,132] per-edge first-Linear partials P[k->j], key | value halves with padded rows (tcgen05 triplet kernel)
+    float* rbuf;                  // [2][Eb,128] r_ji slice of the triplet MLPs as bf16 hi/lo operand images (tcgen05 triplet kernel)
+    float* pbuf2;                 // [2][Eb,128] per-edge first-Linear partials P[k->j] as bf16 hi/lo operand images (tcgen05 triplet kernel)
     float *ew, *comb;             // [Ek], [N,3]
     int* knn_src;                 // [Ek]
     float *pbuf, *pq, *pemb;      // phore encoder: [P,640], [P,128], [P,128]

@@ -151,6 +151,14 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);
 }
+// MN-major operand tile (element (n, k): n contiguous), 128-byte swizzle: rows of 64 bf16 along N (128 B) per k, 8 k-rows per
+// 1024-byte swizzle atom (16-byte chunk j of row k stored at chunk j ^ (k % 8)); LBO = byte stride between 64-element
+// blocks along N, SBO = byte stride between 8-row groups along K (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in
+// 16-byte units, CUTLASS cute/atom/mma_traits_sm100.hpp).  Needs the instruction descriptor's major bit of that operand.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes = 1024) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
 // kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, shape M x N (x 16).
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -181,6 +189,41 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Warp-collective forms of the three calls above: EVERY lane of the converged issuer warp calls them with identical
+// operands and one elected lane issues the instruction.  Branching on `lane == 0` around the issue code instead puts the
+// descriptor arithmetic into a divergent region, where ptxas cannot use the uniform datapath and feeds every UTCHMMA
+// through an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop (~100 cycles per MMA: the tensor pipe then idles behind
+// the issuer; measured on the triplet kernel).  elect.sync always picks the same lane while the mask is unchanged, so the
+// MMAs and their commit are issued by one thread, as tcgen05.commit requires.
+__device__ __forceinline__ void umma_bf16_w(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(smem_u32(bar))
         : "memory");
 }
 // all previously issued MMAs of this thread arrive on the mbarrier when complete (implies fence::before_thread_sync)

@@ -1,17 +1,23 @@
 // BondUpdateLayer (uni_denoiser.py:123-165) on the 5th-gen tensor cores.
 //
 // One persistent CTA per SM (640 threads) walks the ligand atoms j ("units").  For a unit the per-edge partials
-// P[k->j] (n-1 rows x 256 channels, k|v; written by trip_pr_kernel below) are staged once in shared memory by bulk copies;
-// the n-1 segments (j->i) are processed four at a time as a 128-row tile: TMEM lane = triplet row (32 lanes per segment,
-// rows k ascending).
+// P[k->j] (n-1 rows x 256 channels, k|v; written by trip_pr_kernel below as bf16 hi/lo operand images) are staged once in
+// shared memory by bulk copies; the n-1 segments (j->i) are processed four at a time as a 128-row tile: TMEM lane =
+// triplet row, lane l of every segment <-> staged row l (the edge k->j with the l-th k); the lane with k = i is masked
+// out of the softmax.  The whole first Linear is assembled by the tensor pipe: pre-activation = [angle features | segment
+// indicator] x [Wa ; R rows of the tile] + one-hot(l) x P rows, so the row warps never touch P or R.
 //
 // Roles: 16 row warps, thread = (row, 32-channel quarter), warp w -> lane quarter w & 3, channel quarter w >> 2 (four row
 //        warps per scheduler); warp 16 issues every MMA and the cp.async / bulk copies; warps 17-19 compute the angular
 //        features of the tiles ahead.  setmaxnreg moves registers from the auxiliary warpgroup to the row warps (104 / 64).
 //
-//   1. angular encoding (13 values per triplet) -> bf16 hi/lo A tile in smem (double buffered); per MLP three
-//      tcgen05.mma (M128 N128 K16, bf16x3) against the angle slice of the first Linear -> pre-activation columns in TMEM.
-//   2. every thread reads its 32-channel slice (tcgen05.ld), adds P[k->j] (smem) and R[j->i] (per segment), applies
+//   1. angular encoding (11 distinct values per triplet; sin/cos of the angle itself occur twice in the reference's encoding
+//      and their weight rows are summed at pack time) + a 1.0 in column 11 + segment slot -> bf16 hi/lo A tile in smem
+//      (double buffered); per MLP three tcgen05.mma (M128 N128 K16, bf16x3) against [angle slice of the first Linear ;
+//      R[j->i] rows of the tile's 4 segments] (B operand MN-major, rows 11..14 refilled per tile by bulk copies), then
+//      two K16 slabs of a constant one-hot A operand against the staged P rows (hi and lo images: 4 MMAs)
+//      -> pre-activation columns in TMEM.
+//   2. every thread reads its 32-channel slice (tcgen05.ld), applies
 //      LayerNorm + ReLU in registers with packed fp32x2 math (the four quarter statistics of a row meet in shared memory),
 //      splits to bf16 hi/lo with the ReLU fused into the conversions and writes the A operand of the second Linear back to
 //      TMEM (tcgen05.st).  Positive LayerNorm gains are folded into W2 at pack time (weights.py), so only beta/gamma is added.
@@ -40,38 +46,40 @@ extern "C" int pg_debug_trip_trace(long long* h_out) { return cudaMemcpyFromSymb
 #endif
 
 namespace {
-// Staged P rows.  trip_pr_kernel writes the key and the value halves of P to two arrays [Eb][132]: 128 channels + 4 floats of
-// padding per row, i.e. already in the shared-memory layout.  The rows of a unit (or of one 32-row chunk of it) are then ONE
-// contiguous block per half, staged by a single bulk copy instead of one per row, and a warp's row-per-lane LDS.128 (row
-// stride 528 B = 33 x 16 B) touches every bank exactly once per 8 lanes.
-constexpr int PS_HALF = PG_TRIP_P_STRIDE;  // floats per row of one half (132)
-// staged P rows: all n-1 rows of a unit while a segment is one chunk (n-1 <= 33), else the 33 rows of one chunk
-__host__ __device__ constexpr int ps_rows(int maxn) { return maxn - 1 < 33 ? maxn - 1 : 33; }
+// Operand images of the first Linear's per-edge parts (written by trip_pr_kernel, bulk-copied verbatim into shared memory):
+//   P[k->j], per MLP: for every unit a block [hi|lo][channel half][n-1 rows][64 bf16 = 128 B], the 16-byte chunks of a row
+//   XOR-swizzled with (row & 7): the MN-major / 128-byte-swizzle canonical layout of a UMMA B operand (K = staged row,
+//   N = channel), so rows 16s..16s+15 of the staged block are the B operand of K16 slab s.
+//   R[j->i], per MLP: same block shape, indexed by the SOURCE atom's unit and the segment index of i, swizzled for rows
+//   11 + (segment & 3) of the angle slab: the 4 segments of a tile are one contiguous 512-byte piece per (hi|lo, half).
 constexpr int W_TILE = 32768;              // one [128 x 128] bf16 matrix in two 128B-swizzled K blocks
 constexpr int SM_W = 4 * W_TILE;           // (k,v) x (hi,lo)
-constexpr int SM_WA = 2 * 8192;            // angle slice of the first Linear: (hi,lo) x [256 x 16] bf16, no swizzle
+constexpr int SM_WA = 2 * 2 * 4096;        // angle slab B operand [mlp][hi|lo][half][16 rows][128 B], MN-major SW128: rows 0..10 weights, 11..14 R
+constexpr int SM_P = 2 * 2 * 8192;         // staged P rows [mlp][hi|lo][half][32 rows][128 B], MN-major SW128
+constexpr int SM_ONE = 2 * 4096;           // constant one-hot A operand: two K16 slabs [128 x 16] bf16, no swizzle
 constexpr int SM_FEAT1 = 2 * 4096;         // (hi,lo) x [128 x 16] bf16, no swizzle
 constexpr int SM_FEAT = 2 * SM_FEAT1;      // double-buffered: the feature warps run up to two tiles ahead
-constexpr int SM_QR = 2 * (4 * 128 + 4 * 256) * 4;   // double-buffered query rows + r_ji rows of a tile's 4 segments
-constexpr int SM_ALPHA = 128 * 16 * 4;     // attention weights of the tile [row][head]
-constexpr int SM_FIXED = SM_W + SM_WA + SM_FEAT + SM_QR + SM_ALPHA + 6 * 128 * 4 /*ln + b2*/ + 128 /*barriers*/;
+constexpr int SM_Q = 2 * 4 * 128 * 4;      // double-buffered query rows of a tile's 4 segments
+constexpr int SM_STAT = 128 * 16 * 4;      // LayerNorm partial sums [mlp][quarter][row][2]
+constexpr int SM_FIXED = SM_W + SM_WA + SM_P + SM_ONE + SM_FEAT + SM_Q + SM_STAT + 6 * 128 * 4 /*ln + b2*/ + 256 /*barriers*/;
 constexpr float kInvSqrtD = 0.35355339059327373f;
 constexpr int ROW_WARPS = 16;               // 4 warps per TMEM lane quarter, each owning a 32-channel slice of the row
 constexpr int MMA_WARP = ROW_WARPS;         // MMA issue + q/R/P loaders; the 3 warps after it compute angular features
 constexpr int NTHREADS = (ROW_WARPS + 4) * 32;
 constexpr int ROW_THREADS = ROW_WARPS * 32;
+constexpr int R_ROW0 = 11;                  // angle slab: K columns 0..10 features, 11..14 segment indicator, 15 zero
 
 // mbarrier slots
 // A parity wait is only safe while the barrier cannot complete a second time before the waiter looks at it.  B_PREV has
 // two kinds of waiters (row warps and the feature warps, which run ahead on their own clock), so it alternates between
 // two barriers by tile parity, like B_FEAT.
-enum { B_FEAT0 = 0, B_FEAT1, B_PREK, B_PREV0, B_PREV1, B_HIDK, B_HIDV, B_OUTK, B_OUTV, B_PSK, B_PSV, B_COUNT };
+enum { B_FEAT0 = 0, B_FEAT1, B_PREK, B_PREV0, B_PREV1, B_HIDK, B_HIDV, B_OUTK, B_OUTV, B_PSK, B_PSV, B_RK, B_RV, B_COUNT };
 
 // the sequence of (unit, tile) a CTA walks; every role steps through it redundantly
-// MULTI: a segment longer than 32 rows is cut into chunks of 32 rows; a tile is then (group of 4 segments) x (chunk c),
+// MULTI: a unit with more than 32 rows k -> j is cut into chunks of 32 rows; a tile is then (group of 4 segments) x (chunk c),
 // the chunks of a group on consecutive tiles (chunk-inner order), and the softmax runs on-line across them.
-// `stage` counts the refills of the staged P rows: once per unit when a segment is a single chunk (all n-1 rows of the
-// unit stay resident), once per tile otherwise (the 33 rows k -> j of chunk c).
+// `stage` counts the refills of the staged P rows: once per unit when the unit is a single chunk (all n-1 rows stay
+// resident), once per tile otherwise (the rows of chunk c).
 struct TileIter {
     int u, tile, ntile, n, jl, ctx0, nchunk, chunk, grp, stage;
     long long eoff;
@@ -83,9 +91,9 @@ __device__ __forceinline__ void iter_load_unit(const PlanDev& d, TileIter& it) {
     while (it.u < d.Nl) {
         const int g = d.lig_graph[it.u];
         const int n = d.g_n[g];
-        if (n >= 3 && (MULTI ? n - 2 > 32 : n - 2 <= 32)) {       // each instantiation takes its own molecules (see the launcher)
+        if (n >= 3 && (MULTI ? n - 1 > 32 : n - 1 <= 32)) {       // each instantiation takes its own molecules (see the launcher)
             it.n = n; it.jl = it.u - d.lig_off[g]; it.ctx0 = d.ctx_off[g] + d.g_p[g]; it.eoff = d.eoff[g];
-            it.nchunk = MULTI ? (n - 2 + 31) >> 5 : 1;
+            it.nchunk = MULTI ? (n - 1 + 31) >> 5 : 1;
             it.ntile = ((n - 1 + 3) >> 2) * it.nchunk; it.tile = 0; it.chunk = 0; it.grp = 0; it.stage++; it.valid = true;
             return;
         }
@@ -120,17 +128,19 @@ __device__ __forceinline__ Seg seg_of(const TileIter& it, int wq) {
 
 // angular encoding of this thread's triplet row -> bf16 hi/lo A tile (common.py:67-87; uni_denoiser.py:131-135)
 // xs: coordinates of the molecule's ligand atoms, [n][4] floats (shared memory copy)
-// `wq` = segment slot of the tile (0..3), `row` = row inside the segment (0..31)
+// `wq` = segment slot of the tile (0..3), `row` = row inside the chunk (0..31) = staged row of the edge k -> j
+// K columns: 0 theta, 1..3 sin(theta * {1,2,3}), 4..5 sin(theta / {2,3}), 6..8 cos(theta * {1,2,3}), 9..10 cos(theta / {2,3})
+// (sin theta and cos theta occur twice in the reference's 13 values: weights.py adds their weight rows), 11 + wq = 1
+// (selects the tile's R[j->i] row in the B operand).
 __device__ __forceinline__ void write_features(const float* xs, const TileIter& it, int wq, int row, uint8_t* sFeat) {
     const int lane = row;
     const Seg sg = seg_of(it, wq);
     float f[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) f[i] = 0.f;
-    const int srow = it.chunk * 32 + lane;          // row inside the segment
-    if (sg.valid && srow < it.n - 2) {
-        const int trow = srow + (srow >= sg.ti);
-        const float4 xj = ld4(xs + it.jl * 4), xi = ld4(xs + sg.il * 4), xk = ld4(xs + (trow + (trow >= it.jl)) * 4);
+    const int srow = it.chunk * 32 + lane;          // row of the unit: k is the srow-th atom other than j
+    if (sg.valid && srow < it.n - 1 && srow != sg.ti) {
+        const float4 xj = ld4(xs + it.jl * 4), xi = ld4(xs + sg.il * 4), xk = ld4(xs + (srow + (srow >= it.jl)) * 4);
         const float xi0 = xi.x, xi1 = xi.y, xi2 = xi.z;
         const float pj0 = xj.x - xi0, pj1 = xj.y - xi1, pj2 = xj.z - xi2;
         const float pk0 = xk.x - xi0, pk1 = xk.y - xi1, pk2 = xk.z - xi2;
@@ -142,9 +152,10 @@ __device__ __forceinline__ void write_features(const float* xs, const TileIter& 
         __sincosf(th, &s1, &k1); __sincosf(th * 0.5f, &sh, &kh); __sincosf(th * (1.0f / 3.0f), &st, &kt);
         const float s2 = 2.0f * s1 * k1, k2 = fmaf(-2.0f * s1, s1, 1.0f);
         const float s3 = s1 * fmaf(-4.0f * s1, s1, 3.0f), k3 = k1 * fmaf(4.0f * k1, k1, -3.0f);
-        f[0] = th; f[1] = s1; f[2] = s2; f[3] = s3; f[4] = s1; f[5] = sh; f[6] = st;
-        f[7] = k1; f[8] = k2; f[9] = k3; f[10] = k1; f[11] = kh; f[12] = kt;
+        f[0] = th; f[1] = s1; f[2] = s2; f[3] = s3; f[4] = sh; f[5] = st;
+        f[6] = k1; f[7] = k2; f[8] = k3; f[9] = kh; f[10] = kt;
     }
+    f[11] = wq == 0 ? 1.f : 0.f; f[12] = wq == 1 ? 1.f : 0.f; f[13] = wq == 2 ? 1.f : 0.f; f[14] = wq == 3 ? 1.f : 0.f;
     uint32_t hi[8], lo[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) tc::split_pair_trunc(f[2 * i], f[2 * i + 1], hi[i], lo[i]);
@@ -169,19 +180,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
     // offset arithmetic on the __shared__ array (not a uintptr_t round trip) so the compiler keeps emitting LDS/STS
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sW = smem;
-    uint8_t* sWa = sW + SM_W;
-    uint8_t* sFeat = sWa + SM_WA;
-    float* sQR = (float*)(sFeat + SM_FEAT);         // [2][ q: 4x128 | R: 4x256 ]
-    float* sStat = sQR + SM_QR / 4;                 // [2 mlp][4 quarters][128 rows][2]  partial LayerNorm sums (quarter-major: conflict-free)
-    float* sLn = sStat + SM_ALPHA / 4;              // gk, bk, gv, bv
+    uint8_t* sWa = sW + SM_W;                       // 1024-aligned (swizzled operand)
+    uint8_t* sP = sWa + SM_WA;                      // 1024-aligned (swizzled operand)
+    uint8_t* sOne = sP + SM_P;
+    uint8_t* sFeat = sOne + SM_ONE;
+    float* sQ0 = (float*)(sFeat + SM_FEAT);         // [2][4 x 128] query rows
+    float* sStat = sQ0 + SM_Q / 4;                  // [2 mlp][4 quarters][128 rows][2]  partial LayerNorm sums (quarter-major: conflict-free)
+    float* sLn = sStat + SM_STAT / 4;               // gk, bk, gv, bv
     float* sB2 = sLn + 4 * 128;                     // b2k, b2v
     uint64_t* bars = (uint64_t*)(sB2 + 2 * 128);
     uint32_t* tmem_slot = (uint32_t*)(bars + B_COUNT);
-    float* sPs = (float*)(smem + SM_FIXED);         // [k|v][min(maxn-1, 33)][132] (see PS_HALF)
-    const int psr = ps_rows(a.maxn);
-    float* sX = sPs + (size_t)2 * psr * PS_HALF;    // [2][maxn][4] ligand coordinates of the current / next unit
+    float* sX = (float*)(smem + SM_FIXED);          // [2][maxn][4] ligand coordinates of the current / next unit
     const PlanDev& d = a.d;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // provably warp-uniform: the role branches and the MMA issuer's descriptor arithmetic stay on the uniform datapath
     const int wq = warp & 3;
 
     if (warp == MMA_WARP) tc::tmem_alloc<512>(tmem_slot);
@@ -191,6 +203,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
         tc::mbar_init(&bars[B_HIDK], ROW_THREADS); tc::mbar_init(&bars[B_HIDV], ROW_THREADS);
         tc::mbar_init(&bars[B_OUTK], 1); tc::mbar_init(&bars[B_OUTV], 1);
         tc::mbar_init(&bars[B_PSK], 1); tc::mbar_init(&bars[B_PSV], 1);
+        tc::mbar_init(&bars[B_RK], 1); tc::mbar_init(&bars[B_RV], 1);
         tc::fence_barrier_init();
     }
     // ---- resident weights
@@ -201,13 +214,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
         const uint32_t dst = tc::smem_u32(sW) + mat * W_TILE + (c >> 3) * 16384 + tc::sw128_chunk(n, c & 7);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
     }
-    for (int idx = tid; idx < 2 * 256 * 2; idx += NTHREADS) {      // [part 2][n 256][kc 2]
-        const int part = idx >> 9, n = (idx >> 1) & 255, kc = idx & 1;
-        const uint16_t* src = a.wa_bf + ((size_t)part * 256 + n) * 16 + kc * 8;
-        const uint32_t dst = tc::smem_u32(sWa) + part * 8192 + (n >> 3) * 256 + kc * 128 + (n & 7) * 16;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-    }
+    // angle slab image (weights.py: already in the shared-memory layout, R rows and row 15 zero)
+    for (int idx = tid; idx < SM_WA / 16; idx += NTHREADS)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(sWa) + idx * 16), "l"(a.wa_bf + idx * 8) : "memory");
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    // staged P rows start as zeros (rows beyond n-1 are selected by padding lanes: finite garbage is harmless, NaN is not)
+    for (int idx = tid; idx < SM_P / 16; idx += NTHREADS) *reinterpret_cast<uint4*>(sP + idx * 16) = make_uint4(0u, 0u, 0u, 0u);
+    // constant one-hot A operand: row r selects staged row (r & 31); slab s covers K columns 16 s .. 16 s + 15
+    for (int idx = tid; idx < 2 * 128 * 2; idx += NTHREADS) {     // [slab][row][k chunk of 8]
+        const int sl = idx >> 8, r = (idx >> 1) & 127, kc = idx & 1;
+        const int one = (r & 31) - sl * 16 - kc * 8;                // position of the 1.0 inside this 8-element chunk, if any
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (one >= 0 && one < 8) w[one >> 1] = (one & 1) ? 0x3F800000u : 0x00003F80u;
+        *reinterpret_cast<uint4*>(sOne + sl * 4096 + (r >> 3) * 256 + kc * 128 + (r & 7) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
     if (tid < 128) {
         sLn[tid] = a.lnk_g[tid]; sLn[128 + tid] = a.lnk_bf[tid]; sLn[256 + tid] = a.lnv_g[tid]; sLn[384 + tid] = a.lnv_bf[tid];
         sB2[tid] = a.b2k[tid]; sB2[128 + tid] = a.b2v[tid];
@@ -232,89 +252,113 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
         // registers move from this warpgroup to the four row warpgroups
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
       if (warp == MMA_WARP) {
-        // ================= MMA issue + loaders (query / r_ji rows via cp.async, P rows via bulk copy) =================
+        // ================= MMA issue + loaders (query rows via cp.async, P / R rows via bulk copies) =================
         constexpr uint32_t idesc = tc::umma_idesc_bf16(128, 128);
+        constexpr uint32_t idesc_bmn = idesc | (1u << 16);          // B operand MN-major (staged P rows, angle slab)
         const uint32_t sW_u32 = tc::smem_u32(sW), sWa_u32 = tc::smem_u32(sWa), sFeat_u32 = tc::smem_u32(sFeat);
-        auto load_qr = [&](const TileIter& t, int buf) {
-            const uint32_t q = tc::smem_u32(sQR + buf * (SM_QR / 8));
-            const uint32_t r = q + 4 * 128 * 4;
+        const uint32_t sP_u32 = tc::smem_u32(sP), sOne_u32 = tc::smem_u32(sOne);
+        const size_t mlp_stride = (size_t)a.d.Eb * 128;           // floats per MLP in the P and R images (512 B per edge)
+        auto load_q = [&](const TileIter& t, int buf) {
+            const uint32_t q = tc::smem_u32(sQ0 + buf * (SM_Q / 8));
 #pragma unroll
             for (int s4 = 0; s4 < 4; s4++) {
                 const Seg sg = seg_of(t, s4);
                 const float* qs = a.q + (size_t)sg.eji * 128 + lane * 4;
-                const float* rs = a.R + (size_t)sg.eji * 256 + lane * 4;
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(q + (s4 * 128 + lane * 4) * 4), "l"(qs) : "memory");
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(r + (s4 * 256 + lane * 4) * 4), "l"(rs) : "memory");
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(r + (s4 * 256 + 128 + lane * 4) * 4), "l"(rs + 128) : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        // P rows of the edges k -> j of a unit (n-1 contiguous 1 KB rows) -> padded smem rows.  The key and value halves
-        // travel separately (one mbarrier transaction each): each half is dead as soon as its LayerNorm pass of the
-        // unit's last tile is done, so the next unit's half is requested a whole phase before it is needed.
+        // P rows of the edges k -> j of a unit (or of one 32-row chunk of it): four contiguous pieces per MLP, (hi|lo) x
+        // (channel half), each nr x 128 B.  The key and value images travel separately (one mbarrier transaction each): an
+        // image is dead as soon as the first-Linear MMAs of the unit's last tile have completed, which the issuer knows
+        // when the row warps hand back that tile's activations (HIDK / HIDV).
         auto load_ps = [&](const TileIter& t, int mlp) {
             uint64_t* bar = &bars[mlp == 0 ? B_PSK : B_PSV];
-            // rows k -> j of chunk c: segment rows [32c, 32c+32) map to unit rows [32c, 32c+33) (the row k = i is skipped)
-            const int r0 = t.chunk * 32, nr = min(33, t.n - 1 - r0);
-            if (lane == 0) tc::mbar_arrive_expect_tx(bar, (uint32_t)nr * (PS_HALF * 4u));
-            __syncwarp();
-            const float* src = a.P + (size_t)mlp * a.d.Eb * PS_HALF + (size_t)(t.eoff + (long long)t.jl * (t.n - 1) + r0) * PS_HALF;
-            if (lane == 0) tc::bulk_copy_g2s(sPs + (size_t)mlp * psr * PS_HALF, src, (uint32_t)nr * (PS_HALF * 4u), bar);   // one copy per half
-        };
-        // angle slice of the first Linear for one MLP of tile `tl` (operand buffer tl & 1) -> pre-activation columns `dcol`
-        auto feat_mma = [&](int tl, int mlp, uint32_t dcol, uint64_t* bar) {
+            const int r0 = t.chunk * 32, nr = min(32, t.n - 1 - r0);
             if (lane == 0) {
-                const uint32_t fb = sFeat_u32 + (tl & 1) * SM_FEAT1;
-                const uint64_t fh = tc::umma_desc_k16_noswizzle(fb), fl = tc::umma_desc_k16_noswizzle(fb + 4096);
-                const uint64_t wh = tc::umma_desc_k16_noswizzle(sWa_u32 + mlp * 4096), wl = tc::umma_desc_k16_noswizzle(sWa_u32 + 8192 + mlp * 4096);
-                tc::umma_bf16(dcol, fh, wh, idesc, 0);
-                tc::umma_bf16(dcol, fh, wl, idesc, 1);
-                tc::umma_bf16(dcol, fl, wh, idesc, 1);
-                tc::umma_commit(bar);
+                tc::mbar_arrive_expect_tx(bar, (uint32_t)nr * 512u);
+                const uint8_t* src = (const uint8_t*)(a.P + (size_t)mlp * mlp_stride) + (size_t)(t.eoff + (long long)t.jl * (t.n - 1)) * 512;
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                    tc::bulk_copy_g2s(sP + (mlp * 4 + b) * 4096, src + ((size_t)b * (t.n - 1) + r0) * 128, (uint32_t)nr * 128u, bar);
             }
             __syncwarp();
         };
+        // R rows of the tile's 4 segments (j -> i), contiguous in the source-major R image -> rows 11..14 of the angle slab
+        auto load_r = [&](const TileIter& t, int mlp) {
+            uint64_t* bar = &bars[mlp == 0 ? B_RK : B_RV];
+            const int s0 = t.grp * 4, nr = min(4, t.n - 1 - s0);
+            if (lane == 0) {
+                tc::mbar_arrive_expect_tx(bar, (uint32_t)nr * 512u);
+                const uint8_t* src = (const uint8_t*)(a.R + (size_t)mlp * mlp_stride) + (size_t)(t.eoff + (long long)t.jl * (t.n - 1)) * 512;
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                    tc::bulk_copy_g2s(sWa + (mlp * 4 + b) * 2048 + 1024 + (R_ROW0 - 8) * 128, src + ((size_t)b * (t.n - 1) + s0) * 128,
+                                      (uint32_t)nr * 128u, bar);
+            }
+            __syncwarp();
+        };
+        // first Linear of one MLP for tile `tl` (feature operand buffer tl & 1) -> pre-activation columns `dcol`:
+        // [angle | indicator] x [Wa ; R] in bf16x3, then one-hot x staged P rows (hi and lo images), `nslab` K16 slabs
+        // (warp-collective issue: all lanes run the descriptor arithmetic on the uniform datapath, one elected lane issues)
+        auto feat_mma = [&](int tl, int mlp, int nslab, uint32_t dcol, uint64_t* bar) {
+            const uint32_t fb = sFeat_u32 + (tl & 1) * SM_FEAT1;
+            const uint64_t fh = tc::umma_desc_k16_noswizzle(fb), fl = tc::umma_desc_k16_noswizzle(fb + 4096);
+            const uint64_t wh = tc::umma_desc_mn_sw128(sWa_u32 + (mlp * 2) * 4096, 2048), wl = tc::umma_desc_mn_sw128(sWa_u32 + (mlp * 2 + 1) * 4096, 2048);
+            tc::umma_bf16_w(dcol, fh, wh, idesc_bmn, 0);
+            tc::umma_bf16_w(dcol, fh, wl, idesc_bmn, 1);
+            tc::umma_bf16_w(dcol, fl, wh, idesc_bmn, 1);
+            for (int sl = 0; sl < nslab; sl++) {
+                const uint64_t oh = tc::umma_desc_k16_noswizzle(sOne_u32 + sl * 4096);
+                tc::umma_bf16_w(dcol, oh, tc::umma_desc_mn_sw128(sP_u32 + (mlp * 2) * 8192 + sl * 2048, 4096), idesc_bmn, 1);
+                tc::umma_bf16_w(dcol, oh, tc::umma_desc_mn_sw128(sP_u32 + (mlp * 2 + 1) * 8192 + sl * 2048, 4096), idesc_bmn, 1);
+            }
+            tc::umma_commit_w(bar);
+        };
+        auto slabs_of = [](const TileIter& t) { return (min(32, t.n - 1 - t.chunk * 32) + 15) >> 4; };
         // second Linear of one MLP: A = bf16 hi/lo activations in TMEM columns `hid`, D = `dcol`
         auto w2_mma = [&](int mlp, uint32_t hid, uint32_t dcol, uint64_t* bar) {
             if (KF16 && mlp == 0) {
-                if (lane == 0) {
-                    constexpr uint32_t idesc16 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // A, B = F16
+                constexpr uint32_t idesc16 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // A, B = F16
 #pragma unroll
-                    for (int ks = 0; ks < 8; ks++) {
-                        const uint64_t bd = tc::umma_desc_sw128(sW_u32 + (ks >> 2) * 16384 + (ks & 3) * 32);
-                        tc::umma_bf16_ts(dcol, hid + ks * 8, bd, idesc16, ks > 0);
-                    }
-                    tc::umma_commit(bar);
+                for (int ks = 0; ks < 8; ks++) {
+                    const uint64_t bd = tc::umma_desc_sw128(sW_u32 + (ks >> 2) * 16384 + (ks & 3) * 32);
+                    tc::umma_bf16_ts_w(dcol, hid + ks * 8, bd, idesc16, ks > 0);
                 }
-                __syncwarp();
+                tc::umma_commit_w(bar);
                 return;
             }
-            if (lane == 0) {
-                uint32_t acc = 0;
+            uint32_t acc = 0;
 #pragma unroll
-                for (int combo = 0; combo < 3; combo++) {       // hi*hi, hi*lo, lo*hi
-                    const uint32_t abase = hid + (combo == 2 ? 64 : 0);
-                    const uint32_t bbase = sW_u32 + (mlp * 2 + (combo == 1 ? 1 : 0)) * W_TILE;
+            for (int combo = 0; combo < 3; combo++) {       // hi*hi, hi*lo, lo*hi
+                const uint32_t abase = hid + (combo == 2 ? 64 : 0);
+                const uint32_t bbase = sW_u32 + (mlp * 2 + (combo == 1 ? 1 : 0)) * W_TILE;
 #pragma unroll
-                    for (int ks = 0; ks < 8; ks++) {
-                        const uint64_t bd = tc::umma_desc_sw128(bbase + (ks >> 2) * 16384 + (ks & 3) * 32);
-                        tc::umma_bf16_ts(dcol, abase + ks * 8, bd, idesc, acc);
-                        acc = 1;
-                    }
+                for (int ks = 0; ks < 8; ks++) {
+                    const uint64_t bd = tc::umma_desc_sw128(bbase + (ks >> 2) * 16384 + (ks & 3) * 32);
+                    tc::umma_bf16_ts_w(dcol, abase + ks * 8, bd, idesc, acc);
+                    acc = 1;
                 }
-                tc::umma_commit(bar);
             }
-            __syncwarp();
+            tc::umma_commit_w(bar);
         };
+        uint32_t psk = 0, psv = 0, prk = 0, prv = 0;               // phases of the P / R transaction barriers
         load_ps(it, 0);
         load_ps(it, 1);
-        load_qr(it, 0);
+        load_r(it, 0);
+        load_r(it, 1);
+        load_q(it, 0);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         tc::mbar_arrive(&bars[B_FEAT0]);
         tc::mbar_wait_wd(&bars[B_FEAT0], 0);
+        tc::mbar_wait_wd(&bars[B_PSK], psk); psk ^= 1;
+        tc::mbar_wait_wd(&bars[B_RK], prk); prk ^= 1;
         tc::tc_fence_after();
-        feat_mma(0, 0, tmem + 0, &bars[B_PREK]);
-        feat_mma(0, 1, tmem + 128, &bars[B_PREV0]);
+        feat_mma(0, 0, slabs_of(it), tmem + 0, &bars[B_PREK]);
+        tc::mbar_wait_wd(&bars[B_PSV], psv); psv ^= 1;
+        tc::mbar_wait_wd(&bars[B_RV], prv); prv ^= 1;
+        tc::tc_fence_after();
+        feat_mma(0, 1, slabs_of(it), tmem + 128, &bars[B_PREV0]);
         int tcount = 0;
         while (it.valid) {
             const uint32_t ph = tcount & 1;
@@ -326,10 +370,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             const bool newu = nx.valid && nx.stage != it.stage;     // the staged P rows change with the next tile
             uint64_t* featbar = &bars[(tcount + 1) & 1 ? B_FEAT1 : B_FEAT0];
             TRACE(2, 0);
-            tc::mbar_wait_wd(&bars[B_HIDK], ph);          // key activations of tile t are in TMEM; logits of tile t-1 are done
+            // key activations of tile t are in TMEM: its first-Linear MMAs have completed (the P_k image and the R_k rows
+            // are free), and the logits of tile t-1 are done
+            tc::mbar_wait_wd(&bars[B_HIDK], ph);
             TRACE(2, 1);
             tc::tc_fence_after();
-            if (nx.valid) load_qr(nx, (tcount + 1) & 1);
+            if (nx.valid) { load_q(nx, (tcount + 1) & 1); load_r(nx, 0); }
             if (newu) load_ps(nx, 0);
             w2_mma(0, hidK, preK, &bars[B_OUTK]);
             TRACE(2, 2);
@@ -338,22 +384,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
                 tc::mbar_arrive(featbar);
                 tc::mbar_wait_wd(&bars[B_OUTK], ph);      // hid_k(t) has been consumed: its columns take pre_k(t+1)
                 tc::mbar_wait_wd(featbar, ((tcount + 1) >> 1) & 1);
+                tc::mbar_wait_wd(&bars[B_RK], prk); prk ^= 1;
+                if (newu) { tc::mbar_wait_wd(&bars[B_PSK], psk); psk ^= 1; }
                 tc::tc_fence_after();
                 TRACE(2, 3);
-                feat_mma(tcount + 1, 0, hidK, &bars[B_PREK]);
+                feat_mma(tcount + 1, 0, slabs_of(nx), hidK, &bars[B_PREK]);
             }
             TRACE(2, 4);
             tc::mbar_wait_wd(&bars[B_HIDV], ph);
             TRACE(2, 5);
             tc::tc_fence_after();
+            if (nx.valid) load_r(nx, 1);
             if (newu) load_ps(nx, 1);
             w2_mma(1, hidV, preV, &bars[B_OUTV]);
             TRACE(2, 6);
             if (nx.valid) {
                 tc::mbar_wait_wd(&bars[B_OUTV], ph);
+                tc::mbar_wait_wd(&bars[B_RV], prv); prv ^= 1;
+                if (newu) { tc::mbar_wait_wd(&bars[B_PSV], psv); psv ^= 1; }
                 tc::tc_fence_after();
                 TRACE(2, 7);
-                feat_mma(tcount + 1, 1, hidV, &bars[(tcount + 1) & 1 ? B_PREV1 : B_PREV0]);
+                feat_mma(tcount + 1, 1, slabs_of(nx), hidV, &bars[(tcount + 1) & 1 ? B_PREV1 : B_PREV0]);
             }
             TRACE(2, 8);
             it = nx; tcount++;
@@ -398,8 +449,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
         //   LN-k(t) | epilogue(t-1) | LN-v(t) | logits(t)      while the tensor pipe runs   W2k(t), angle-k(t+1) | W2v(t), angle-v(t+1)
         const int cq = warp >> 2;
         const bool fold[2] = {a.fold[0] > 0.5f, a.fold[1] > 0.5f};
-        uint32_t psk = 0, psv = 0;
-        int staged_k = -1, staged_v = -1;
         int tcount = 0;
         const int role = cq; (void)role;
         float al[4] = {0.f, 0.f, 0.f, 0.f};
@@ -410,8 +459,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
         float mrun[4] = {0.f, 0.f, 0.f, 0.f}, lrun[4] = {0.f, 0.f, 0.f, 0.f}, psc[4] = {0.f, 0.f, 0.f, 0.f}, oacc = 0.f;
         bool prev_first = true, prev_last = true;
         // pre-activation slice -> LayerNorm + ReLU -> bf16 hi/lo A operand of the second Linear
-        auto layer_norm = [&](int mlp, uint32_t pre, uint32_t hid, int trow, const float* sR) {
-            const int c0 = mlp * 128 + cq * 32;          // first of this thread's 32 channels inside the 256-wide (k|v) row
+        // (the tensor pipe has already summed the angle, P[k->j] and R[j->i] parts of the first Linear)
+        auto layer_norm = [&](int mlp, uint32_t pre, uint32_t hid) {
             float2 x2[16];
             {
                 uint32_t xu[32];
@@ -421,13 +470,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
                 for (int i = 0; i < 16; i++) x2[i] = make_float2(__uint_as_float(xu[2 * i]), __uint_as_float(xu[2 * i + 1]));
             }
             float2 s1 = make_float2(0.f, 0.f), s2 = s1, s1b = s1, s2b = s1;
-            const float* prow = sPs + ((size_t)mlp * psr + trow) * PS_HALF + cq * 32;
-            const float* rrow = sR + wq * 256 + c0;
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
-                const float4 p = ld4(prow + 2 * i), rr = ld4(rrow + 2 * i);
-                x2[i] = tc::add2(x2[i], tc::add2(make_float2(p.x, p.y), make_float2(rr.x, rr.y)));
-                x2[i + 1] = tc::add2(x2[i + 1], tc::add2(make_float2(p.z, p.w), make_float2(rr.z, rr.w)));
                 s1 = tc::add2(s1, x2[i]); s1b = tc::add2(s1b, x2[i + 1]);
                 s2 = tc::fma2(x2[i], x2[i], s2); s2b = tc::fma2(x2[i + 1], x2[i + 1], s2b);
             }
@@ -526,28 +570,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             const uint32_t preK = tmem + (ph ? 256 : 0), hidK = tmem + (ph ? 0 : 256);
             const uint32_t preV = tmem + (ph ? 384 : 128), hidV = tmem + (ph ? 128 : 384);
             const Seg sg = seg_of(it, wq);
-            const int srow = it.chunk * 32 + lane;                  // row inside the segment
-            const bool rowvalid = sg.valid && srow < it.n - 2;
-            const int trow = rowvalid ? lane + (srow >= sg.ti) : 0;   // staged row: unit row (srow + skip of k = i) - 32 * chunk
-            const float* sQ = sQR + (tcount & 1) * (SM_QR / 8);
-            const float* sR = sQ + 4 * 128;
+            const int srow = it.chunk * 32 + lane;                  // row of the unit (edge k -> j); the lane with k = i is masked
+            const bool rowvalid = sg.valid && srow < it.n - 1 && srow != sg.ti;
+            const float* sQ = sQ0 + (tcount & 1) * (SM_Q / 8);
             TRACE(role, 0);
             // ---- key MLP
-            if (staged_k != it.stage) { tc::mbar_wait(&bars[B_PSK], psk); psk ^= 1; staged_k = it.stage; }   // P rows (key half) landed
             tc::mbar_wait(&bars[B_PREK], ph);
             tc::tc_fence_after();
             TRACE(role, 1);
-            layer_norm(0, preK, hidK, trow, sR);
+            layer_norm(0, preK, hidK);
             TRACE(role, 2);
             // ---- value epilogue of the previous tile (its W2v MMA ran during that tile's logits and the LayerNorm above)
             if (tcount > 0) epilogue(ph ? 128 + tmem : 384 + tmem, ph ^ 1);
             TRACE(role, 4);
             // ---- value MLP
-            if (staged_v != it.stage) { tc::mbar_wait(&bars[B_PSV], psv); psv ^= 1; staged_v = it.stage; }
             tc::mbar_wait(&bars[ph ? B_PREV1 : B_PREV0], (tcount >> 1) & 1);
             tc::tc_fence_after();
             TRACE(role, 5);
-            layer_norm(1, preV, hidV, trow, sR);
+            layer_norm(1, preV, hidV);
             TRACE(role, 6);
             // ---- logits of this thread's 4 heads, segment softmax across the 32 lanes (rows) of the warp
             {
@@ -629,7 +669,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
 // Per-edge partials of the triplet MLPs' first Linear, for every bond edge e = (src -> dst):
 //   P[e] = h_bond[e] Wb (edge GEMM output T) + h_src Whk + h_dst Whj + b1 + smear(|x_dst - x_src|) Wrkj   (edge in the k->j role)
 //   R[e] = smear(|x_dst - x_src|) Wrji                                                                    (edge in the j->i role)
-// Both k|v halves (256 channels).  P rows of the edges into one atom are contiguous -> one bulk copy per unit.
+// Both k|v halves (256 channels), written as the bf16 hi/lo operand images trip_tc_kernel bulk-copies (layout at the top of
+// this file): P in the block of the DESTINATION atom's unit at row k (its position among the edges into dst), R in the block
+// of the SOURCE atom's unit at the segment index of dst, pre-swizzled for rows 11..14 of the angle slab.
 constexpr int PR_EDGES = 4;      // edges per warp: every weight row read from L1 is used for 4 edges
 __global__ void __launch_bounds__(256, 2) trip_pr_kernel(TripTcArgs a) {
     const PlanDev& d = a.d;
@@ -654,10 +696,27 @@ __global__ void __launch_bounds__(256, 2) trip_pr_kernel(TripTcArgs a) {
         tv[k] = ldg4(a.T + (size_t)ee[k] * a.ldt + a.t_v + lane * 4);
     }
     float xs[PR_EDGES][3], xt[PR_EDGES][3];
+    int gg_[PR_EDGES];
 #pragma unroll
     for (int k = 0; k < PR_EDGES; k++) {
+        gg_[k] = d.node_graph[tn[k]];
 #pragma unroll
         for (int c = 0; c < 3; c++) { xs[k][c] = a.x[(size_t)sn[k] * 3 + c]; xt[k][c] = a.x[(size_t)tn[k] * 3 + c]; }
+    }
+    // rows of the operand images: P row = (unit of dst, position of this edge among the edges into dst),
+    //                             R row = (unit of src, segment index of dst), both in units of 128-byte rows
+    long long prow[PR_EDGES], rrow[PR_EDGES];
+    int nrow[PR_EDGES], pswz[PR_EDGES], rswz[PR_EDGES];
+#pragma unroll
+    for (int k = 0; k < PR_EDGES; k++) {
+        const int g = gg_[k], n = d.g_n[g], c0 = d.ctx_off[g] + d.g_p[g];
+        const long long eo = d.eoff[g];
+        const int sl = sn[k] - c0, tl = tn[k] - c0;
+        const long long ubp = eo + (long long)tl * (n - 1), ubr = eo + (long long)sl * (n - 1);
+        const int kr = (int)(ee[k] - ubp), sidx = tl - (tl > sl);
+        nrow[k] = n - 1;
+        prow[k] = ubp * 4 + kr; pswz[k] = kr & 7;
+        rrow[k] = ubr * 4 + sidx; rswz[k] = (R_ROW0 + (sidx & 3)) & 7;
     }
 #pragma unroll
     for (int k = 0; k < PR_EDGES; k++) {
@@ -688,16 +747,26 @@ __global__ void __launch_bounds__(256, 2) trip_pr_kernel(TripTcArgs a) {
             acc[k][6] = fma2_raw(ss, u6, acc[k][6]); acc[k][7] = fma2_raw(ss, u7, acc[k][7]);
         }
     }
-    auto f4 = [](unsigned long long lo, unsigned long long hi) { const float2 x = up2(lo), y = up2(hi); return make_float4(x.x, x.y, y.x, y.y); };
+    // this lane's 4 channels of one MLP -> bf16 hi and lo (8 bytes each) at chunk ((lane & 15) >> 1) ^ swizzle of the row
+    const int half = lane >> 4, c8 = (lane & 15) >> 1, sub = (lane & 1) * 8;
+    const size_t mlp_bytes = (size_t)d.Eb * 512;
+    auto put = [&](uint8_t* img, long long row0, int nr, int swz, unsigned long long v01, unsigned long long v23) {
+        const float2 x01 = up2(v01), x23 = up2(v23);
+        uint32_t h0, l0, h1, l1;
+        tc::split_pair_trunc(x01.x, x01.y, h0, l0);
+        tc::split_pair_trunc(x23.x, x23.y, h1, l1);
+        uint8_t* dst = img + (size_t)(row0 + (long long)half * nr) * 128 + ((c8 ^ swz) << 4) + sub;
+        *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);                                    // hi image: blocks 0, 1
+        *reinterpret_cast<uint2*>(dst + (size_t)2 * nr * 128) = make_uint2(l0, l1);             // lo image: blocks 2, 3
+    };
 #pragma unroll
     for (int k = 0; k < PR_EDGES; k++) {
         const long long e = e0 + k;
         if (e >= d.Eb) break;
-        st4(a.R + (size_t)e * 256 + lane * 4, f4(acc[k][0], acc[k][1]));
-        st4(a.R + (size_t)e * 256 + 128 + lane * 4, f4(acc[k][2], acc[k][3]));
-        // P: key / value halves in separate arrays of padded rows (the staging layout of trip_tc_kernel)
-        st4(a.P + (size_t)e * PS_HALF + lane * 4, f4(acc[k][4], acc[k][5]));
-        st4(a.P + (size_t)d.Eb * PS_HALF + (size_t)e * PS_HALF + lane * 4, f4(acc[k][6], acc[k][7]));
+        put((uint8_t*)a.R, rrow[k], nrow[k], rswz[k], acc[k][0], acc[k][1]);
+        put((uint8_t*)a.R + mlp_bytes, rrow[k], nrow[k], rswz[k], acc[k][2], acc[k][3]);
+        put((uint8_t*)a.P, prow[k], nrow[k], pswz[k], acc[k][4], acc[k][5]);
+        put((uint8_t*)a.P + mlp_bytes, prow[k], nrow[k], pswz[k], acc[k][6], acc[k][7]);
     }
 }
 }  // namespace
@@ -709,7 +778,7 @@ int pg_launch_trip_pr(const TripTcArgs& a, cudaStream_t s) {
     return PG_OK;
 }
 
-size_t pg_trip_tc_smem(int maxn) { return (size_t)SM_FIXED + ((size_t)2 * ps_rows(maxn) * PS_HALF + 2 * (size_t)maxn * 4) * sizeof(float) + 1024; }
+size_t pg_trip_tc_smem(int maxn) { return (size_t)SM_FIXED + (2 * (size_t)maxn * 4) * sizeof(float) + 1024; }
 
 int pg_launch_trip_tc(const TripTcArgs& a, int num_sms, cudaStream_t s) {
     if (a.d.Nl <= 0) return PG_OK;

@@ -168,6 +168,32 @@ def bf16_tiles64(wt):
     return out.reshape(-1).view(np.float32)
 
 
+def angle_slab_image(wa13):
+    """Angle slice of the triplet MLPs' first Linear, [13][256] (k | v) -> the shared-memory image of the tcgen05 triplet
+    kernel's angle slab (csrc/pg_trip_tc.cu): [mlp][hi|lo][channel half][16 rows][64 bf16], MN-major with the 128-byte
+    swizzle (16-byte chunk c of row r stored at chunk c ^ (r % 8)).  Rows 0..10 are the 11 DISTINCT angular features
+    [theta, sin(theta * {1,2,3}), sin(theta / {2,3}), cos(theta * {1,2,3}), cos(theta / {2,3})]: the reference encoding
+    (common.py:67-87) lists sin(theta) and cos(theta) twice (frequencies 1 and 1/1), so their weight rows are added here
+    (fp64).  Rows 11..14 receive the tile's R[j->i] rows at run time, row 15 stays zero."""
+    w = np.asarray(wa13, dtype=np.float64)
+    assert w.shape == (13, 256)
+    rows = np.zeros((16, 256))
+    rows[0] = w[0]; rows[1] = w[1] + w[4]; rows[2] = w[2]; rows[3] = w[3]; rows[4] = w[5]; rows[5] = w[6]
+    rows[6] = w[7] + w[10]; rows[7] = w[8]; rows[8] = w[9]; rows[9] = w[11]; rows[10] = w[12]
+    r32 = rows.astype(np.float32)
+    hi = _bf16_bits(r32)
+    lo = _bf16_bits(r32 - (hi.astype(np.uint32) << 16).view(np.float32))
+    out = np.zeros((2, 2, 2, 16, 8, 8), dtype=np.uint16)                 # [mlp][hl][half][row][chunk][8]
+    r = np.arange(16)[:, None]
+    c = np.arange(8)[None, :]
+    for hl, bits in enumerate((hi, lo)):
+        t = bits.reshape(16, 2, 2, 8, 8)                                  # [row][mlp][half][chunk][8]
+        for mlp in range(2):
+            for half in range(2):
+                out[mlp, hl, half][r, c ^ (r % 8)] = t[:, mlp, half][r, c]
+    return out.reshape(-1).view(np.float32)
+
+
 def build_blob(sd):
     """-> (fp32 numpy blob, int64 offsets in floats) following the library's own slot table."""
     packed = pack_state_dict(sd)
@@ -193,9 +219,7 @@ def build_blob(sd):
     for name in [k for k in packed if k.endswith((".nk.tab_k", ".nk.tab_v", ".pk.tab_k", ".pk.tab_v"))]:
         packed[name + ".bf"] = bf16_split(np.asarray(packed[name]).reshape(96, 128))   # [type*24 + feat][128] -> [hi|lo][128][96]
     for name in [k for k in packed if k.endswith(".tr.wa")]:
-        wa = np.zeros((16, 256))
-        wa[:13] = packed[name]                                                  # [13][256] -> pad K to 16
-        packed[name + ".bf"] = bf16_split(wa)                                   # -> [hi|lo][256][16]
+        packed[name + ".bf"] = angle_slab_image(packed[name])
     table = _lib.slot_table()
     offsets = np.zeros(len(table), dtype=np.int64)
     chunks, cur = [], 0

@@ -95,16 +95,19 @@ def test_gradient_fixture_from_reference_matches(tmp_path):
     check_digest(dig, f["digest"])
 
 
-def check_digest(got, want, rel=1e-3):
+def check_digest(got, want, rel=1e-3, prj_slack=3.0):
     """Norms within `rel`; projections within `rel` x norm x sqrt-ish slack (a projection is a sum of signed terms); tensors
-    whose reference gradient is numerically zero (key output biases: softmax-invariant) must be numerically zero too."""
+    whose reference gradient is numerically zero (key output biases: softmax-invariant) must be numerically zero too.
+    `prj_slack`: the GPU run accumulates the scatter gradients with atomics in a run-dependent order; the projection of
+    a small, cancellation-dominated gradient (e.g. a key-MLP bias, |g| ~ 1e-3 of the largest) moves by a few 1e-3 |g|
+    between runs there, so that caller passes a wider slack on the projection (the norm bar stays at `rel`)."""
     scale = max(n for n, _ in want.values())
     for k, (nrm, prj) in want.items():
         if nrm < 1e-6 * scale:
             assert got[k][0] < 1e-5 * scale, k
             continue
         assert got[k][0] == pytest.approx(nrm, rel=rel), k
-        assert abs(got[k][1] - prj) <= 3 * rel * nrm * np.sqrt(2.0) + 1e-12, k
+        assert abs(got[k][1] - prj) <= prj_slack * rel * nrm * np.sqrt(2.0) + 1e-12, k
 
 
 # ---------------------------------------------------------------- gradient reducer, gloo world size 2
