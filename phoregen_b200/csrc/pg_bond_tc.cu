@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
     const long long ntiles = MULTI ? d.nbt : (d.Nl + 3) / 4;
 
     if (warp >= MMA_WARP) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         if (warp == MMA_WARP) {
             // ================= MMA issue =================
             constexpr uint32_t idesc_k = tc::umma_idesc_bf16(128, 128);

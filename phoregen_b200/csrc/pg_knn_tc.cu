@@ -54,6 +54,26 @@ struct KSeg {
     int v, R, ctx0, gp;
     long long e0;
 };
+// graph of the node that lane quarter wq handles in `tile` (first level of the dependent index loads; -1 past the end)
+__device__ __forceinline__ int kseg_graph(const PlanDev& d, long long tile, int wq) {
+    const long long v = tile * 4 + wq;
+    return v < d.N ? d.node_graph[v] : -1;
+}
+// second level, given the graph (the row warps fetch the graph one tile earlier, so neither level's latency is exposed)
+__device__ __forceinline__ KSeg kseg_of_graph(const PlanDev& d, long long tile, int wq, int g) {
+    KSeg s;
+    const long long v = tile * 4 + wq;
+    s.valid = false; s.dl = false; s.inr = v < d.N; s.v = 0; s.R = 0; s.ctx0 = 0; s.gp = 0; s.e0 = 0;
+    if (v < d.N) {
+        const int ng = d.g_n[g] + d.g_p[g];
+        s.v = (int)v; s.ctx0 = d.ctx_off[g]; s.gp = d.g_p[g];
+        s.R = min(PG_KNN, ng - 1);
+        s.e0 = d.koff[g] + (long long)(s.v - s.ctx0) * s.R;
+        s.dl = (s.v - s.ctx0) >= s.gp;
+        s.valid = s.R >= 1;
+    }
+    return s;
+}
 __device__ __forceinline__ KSeg kseg(const PlanDev& d, long long tile, int wq) {
     KSeg s;
     const long long v = tile * 4 + wq;
@@ -132,37 +152,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
     const long long ntiles = (d.N + 3) / 4;
 
     if (warp >= MMA_WARP) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         // ================= auxiliary warpgroup: edge features of the next tile (one row per thread) + MMA issue (warp 16) =======
         // feature row r = tid - 512: segment r / 32, neighbour row r % 32 -> bf16 hi/lo one-hot-typed operand row
         const int r = tid - MMA_WARP * 32, frow = r & 31;
         int prev_type = -1;
-        // neighbour index of this thread's row in `tile` (-1: padded row); fetched one tile ahead of its use
-        auto row_src = [&](long long tile) -> int {
-            if (tile >= ntiles) return -1;
-            const KSeg sg = kseg(d, tile, r >> 5);
-            return (sg.valid && frow < sg.R) ? a.knn_src[sg.e0 + frow] : -1;
-        };
-        auto features = [&](long long tile, int s) {
-            int type = -1;
-            uint32_t hi[12], lo[12];
+        // The inputs of a feature row hang off a four-level chain of dependent loads (node -> graph -> offsets -> neighbour
+        // index -> coordinates / direction vectors).  Fetched inside the per-tile feature step the chain was fully exposed
+        // (~4,000 cycles per tile, the critical path of the whole kernel: table MMA(t) -> features(t+1) -> table MMA(t+1));
+        // here every level runs one tile ahead of the next one, so a tile's feature step finds its inputs in registers.
+        struct FIn { float xd0, xd1, xd2, xs0, xs1, xs2, cs0, cs1, cs2, cd0, cd1, cd2; int type; };    // type -1: padded row
+        const long long fstep = gridDim.x;
+        auto graph_at = [&](long long t) -> int { return kseg_graph(d, t < ntiles ? t : (long long)blockIdx.x, r >> 5); };
+        auto seg_at = [&](long long t, int g) -> KSeg { return kseg_of_graph(d, t < ntiles ? t : (long long)blockIdx.x, r >> 5, g); };
+        auto src_at = [&](long long t, const KSeg& sg) -> int { return (t < ntiles && sg.valid && frow < sg.R) ? a.knn_src[sg.e0 + frow] : -1; };
+        auto load_in = [&](int s, const KSeg& sg) -> FIn {
+            FIn f;
+            f.xd0 = f.xd1 = f.xd2 = f.xs0 = f.xs1 = f.xs2 = f.cs0 = f.cs1 = f.cs2 = f.cd0 = f.cd1 = f.cd2 = 0.f;
+            f.type = -1;
             if (s >= 0) {
-                const KSeg sg = kseg(d, tile, r >> 5);
-                const float x0 = a.x[(size_t)sg.v * 3], x1 = a.x[(size_t)sg.v * 3 + 1], x2 = a.x[(size_t)sg.v * 3 + 2];
-                const float r0 = x0 - a.x[(size_t)s * 3], r1 = x1 - a.x[(size_t)s * 3 + 1], r2 = x2 - a.x[(size_t)s * 3 + 2];
+                f.xd0 = a.x[(size_t)sg.v * 3]; f.xd1 = a.x[(size_t)sg.v * 3 + 1]; f.xd2 = a.x[(size_t)sg.v * 3 + 2];
+                f.xs0 = a.x[(size_t)s * 3]; f.xs1 = a.x[(size_t)s * 3 + 1]; f.xs2 = a.x[(size_t)s * 3 + 2];
                 const float* c1 = a.comb + (size_t)s * 3;                             // vec_1 = comb[src]
                 const float* c2 = a.comb + (size_t)sg.v * 3;                          // vec_2 = comb[dst]
-                const float c10 = c1[0], c11 = c1[1], c12 = c1[2], c20 = c2[0], c21 = c2[1], c22 = c2[2];
-                const float dist = sqrtf(r0 * r0 + r1 * r1 + r2 * r2);
+                f.cs0 = c1[0]; f.cs1 = c1[1]; f.cs2 = c1[2]; f.cd0 = c2[0]; f.cd1 = c2[1]; f.cd2 = c2[2];
                 const bool sl = (s - sg.ctx0) >= sg.gp;
-                type = sl ? (sg.dl ? 0 : 1) : (sg.dl ? 2 : 3);                        // uni_denoiser.py:373-378
+                f.type = sl ? (sg.dl ? 0 : 1) : (sg.dl ? 2 : 3);                      // uni_denoiser.py:373-378
+            }
+            return f;
+        };
+        auto features = [&](const FIn& in) {
+            const int type = in.type;
+            uint32_t hi[12], lo[12];
+            if (type >= 0) {
+                const float r0 = in.xd0 - in.xs0, r1 = in.xd1 - in.xs1, r2 = in.xd2 - in.xs2;
+                const float dist = sqrtf(r0 * r0 + r1 * r1 + r2 * r2);
                 float f[24];
 #pragma unroll
                 for (int gg = 0; gg < 20; gg++) { const float dd = dist - c_smear_off[gg]; f[gg] = __expf(-0.5f * dd * dd); }
                 f[20] = 1.0f;
-                f[21] = c10 * c20 + c11 * c21 + c12 * c22;
-                f[22] = -(c10 * r0 + c11 * r1 + c12 * r2);                            // vec_3 = x[src] - x[dst]
-                f[23] = -(c20 * r0 + c21 * r1 + c22 * r2);
+                f[21] = in.cs0 * in.cd0 + in.cs1 * in.cd1 + in.cs2 * in.cd2;
+                f[22] = -(in.cs0 * r0 + in.cs1 * r1 + in.cs2 * r2);                   // vec_3 = x[src] - x[dst]
+                f[23] = -(in.cd0 * r0 + in.cd1 * r1 + in.cd2 * r2);
 #pragma unroll
                 for (int i = 0; i < 12; i++) tc::split_pair_trunc(f[2 * i], f[2 * i + 1], hi[i], lo[i]);
             }
@@ -205,66 +236,81 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
             }
             tc::umma_commit_w(&bars[B_PRE]);
         };
-        int s_cur = row_src(blockIdx.x);
-        int s_nxt = row_src(blockIdx.x + gridDim.x);
-        features(blockIdx.x, s_cur);
-        if (warp == MMA_WARP) {
-            tc::mbar_wait_wd(&bars[B_FEAT], 0);
-            tc::tc_fence_after();
-            table_mma();
+        // fill the index pipeline (the only place where the chain is walked in one go)
+        const long long f0 = blockIdx.x;
+        FIn in_cur;
+        int s1;
+        KSeg seg1, seg2;
+        int g3;
+        {
+            const KSeg seg0 = seg_at(f0, graph_at(f0));
+            in_cur = load_in(src_at(f0, seg0), seg0);
+            seg1 = seg_at(f0 + fstep, graph_at(f0 + fstep));
+            s1 = src_at(f0 + fstep, seg1);
+            seg2 = seg_at(f0 + 2 * fstep, graph_at(f0 + 2 * fstep));
+            g3 = graph_at(f0 + 3 * fstep);
         }
-        uint32_t ph = 0;
+        // Rotated loop: iteration n computes the features and issues the table product of the CTA's n-th tile, and issues the
+        // second Linear of tile n-1.  Every tile goes through the SAME feature / MMA code (one call site each): a peeled
+        // first tile is compiled separately and may round differently, which would make a molecule's result depend on its
+        // position in the batch (tests: bit-exact batch independence).
         int tcount = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1, tcount++) {
-            const long long nt = tile + gridDim.x;
-            const bool more = nt < ntiles;
+        for (long long ft = f0;; ft += fstep, tcount++) {
+            const bool have = ft < ntiles;
+            const uint32_t pp = (uint32_t)(tcount - 1) & 1;         // phase parity of tile n-1
             KTRACE(1, 0);
-            // features of the next tile as soon as the table MMA of this one has consumed the operand
-            tc::mbar_wait_wd(&bars[B_PRE], ph);
+            // the table MMA of tile n-1 has consumed the feature operand
+            if (tcount > 0) tc::mbar_wait_wd(&bars[B_PRE], pp);
             KTRACE(1, 1);
-            if (more) {
-                s_cur = s_nxt;
-                s_nxt = row_src(nt + gridDim.x);
-                features(nt, s_cur);
+            if (have) {
+                features(in_cur);                                   // inputs fetched while the previous tile was processed
+                in_cur = load_in(s1, seg1);                         // tile n+1
+                s1 = src_at(ft + 2 * fstep, seg2);                  // neighbour index of tile n+2
+                seg1 = seg2;
+                seg2 = seg_at(ft + 3 * fstep, g3);                  // offsets of tile n+3
+                g3 = graph_at(ft + 4 * fstep);                      // graph of tile n+4
             }
             KTRACE(1, 2);
             if (warp == MMA_WARP) {
-                tc::mbar_wait_wd(&bars[B_HID], ph);
-                KTRACE(1, 3);
-                tc::tc_fence_after();
-                if (KF16) {
-                    constexpr uint32_t idesc16 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // A, B = F16
-#pragma unroll
-                    for (int ks = 0; ks < 8; ks++) {
-                        const uint64_t bd = tc::umma_desc_sw128(sW_u32 + (ks >> 2) * 16384 + (ks & 3) * 32);
-                        tc::umma_bf16_ts_w(tmem + C_OUT + ph * 128, tmem + C_HID + ks * 8, bd, idesc16, ks > 0);
-                    }
-                    tc::umma_commit_w(&bars[B_OUT]);
-                } else {
-                    const uint32_t dcol = tmem + C_OUT + ph * 128;
-                    uint32_t acc = 0;
-#pragma unroll
-                    for (int combo = 0; combo < 3; combo++) {
-                        const uint32_t abase = tmem + C_HID + (combo == 2 ? 64 : 0);
-                        const uint32_t bbase = sW_u32 + (combo == 1 ? W_TILE : 0);
+                if (tcount > 0) {
+                    tc::mbar_wait_wd(&bars[B_HID], pp);
+                    KTRACE(1, 3);
+                    tc::tc_fence_after();
+                    if (KF16) {
+                        constexpr uint32_t idesc16 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // A, B = F16
 #pragma unroll
                         for (int ks = 0; ks < 8; ks++) {
-                            const uint64_t bd = tc::umma_desc_sw128(bbase + (ks >> 2) * 16384 + (ks & 3) * 32);
-                            tc::umma_bf16_ts_w(dcol, abase + ks * 8, bd, idesc_w, acc);
-                            acc = 1;
+                            const uint64_t bd = tc::umma_desc_sw128(sW_u32 + (ks >> 2) * 16384 + (ks & 3) * 32);
+                            tc::umma_bf16_ts_w(tmem + C_OUT + pp * 128, tmem + C_HID + ks * 8, bd, idesc16, ks > 0);
                         }
+                        tc::umma_commit_w(&bars[B_OUT]);
+                    } else {
+                        const uint32_t dcol = tmem + C_OUT + pp * 128;
+                        uint32_t acc = 0;
+#pragma unroll
+                        for (int combo = 0; combo < 3; combo++) {
+                            const uint32_t abase = tmem + C_HID + (combo == 2 ? 64 : 0);
+                            const uint32_t bbase = sW_u32 + (combo == 1 ? W_TILE : 0);
+#pragma unroll
+                            for (int ks = 0; ks < 8; ks++) {
+                                const uint64_t bd = tc::umma_desc_sw128(bbase + (ks >> 2) * 16384 + (ks & 3) * 32);
+                                tc::umma_bf16_ts_w(dcol, abase + ks * 8, bd, idesc_w, acc);
+                                acc = 1;
+                            }
+                        }
+                        tc::umma_commit_w(&bars[B_OUT]);
                     }
-                    tc::umma_commit_w(&bars[B_OUT]);
                 }
                 KTRACE(1, 4);
-                if (more) {
-                    tc::mbar_wait_wd(&bars[B_FEAT], ph ^ 1);   // features of the next tile (pre columns are free: HID(t) has fired)
+                if (have) {
+                    tc::mbar_wait_wd(&bars[B_FEAT], (uint32_t)tcount & 1);   // features of tile n (pre columns are free: HID(n-1) has fired)
                     tc::tc_fence_after();
                     KTRACE(1, 5);
                     table_mma();
                     KTRACE(1, 6);
                 }
             }
+            if (!have) break;
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
@@ -314,27 +360,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
                     s0 = tc::add2(s0, s1);
                     al[h] = prow ? (s0.x + s0.y) * kScale : -INFINITY;
                 }
-                float mx[4], sm[4];
                 KTRACE(0, 11);
-#pragma unroll
-                for (int h = 0; h < 4; h++) mx[h] = al[h];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                    for (int h = 0; h < 4; h++) mx[h] = fmaxf(mx[h], __shfl_xor_sync(PG_FULL, mx[h], o));
-#pragma unroll
-                for (int h = 0; h < 4; h++) { al[h] = prow ? tc::ex2_approx(al[h] - mx[h]) : 0.f; sm[h] = al[h]; }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                    for (int h = 0; h < 4; h++) sm[h] += __shfl_xor_sync(PG_FULL, sm[h], o);
+                // segment softmax across the 32 lanes on the REDUX unit (max; fixed-point sums of values in [0, 1]) instead
+                // of three 5-round shuffle butterflies: the dependent shuffle chains were a quarter of the tile time
                 float sw[4];
 #pragma unroll
-                for (int h = 0; h < 4; h++) { al[h] = prow ? al[h] * __frcp_rn(sm[h]) * ew : 0.f; sw[h] = al[h]; }
+                for (int h = 0; h < 4; h++) {
+                    const float mx = tc::warp_max_redux(al[h]);
+                    al[h] = prow ? tc::ex2_approx(al[h] - mx) : 0.f;
+                }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
+                for (int h = 0; h < 4; h++) {
+                    const float sm = tc::warp_sum01_redux(al[h]);
+                    al[h] = prow ? al[h] * __frcp_rn(sm) * ew : 0.f;      // e_w is a sigmoid: alpha' stays in [0, 1]
+                }
 #pragma unroll
-                    for (int h = 0; h < 4; h++) sw[h] += __shfl_xor_sync(PG_FULL, sw[h], o);
+                for (int h = 0; h < 4; h++) sw[h] = tc::warp_sum01_redux(al[h]);
                 KTRACE(0, 12);
                 if (prow) st4(a.alpha + (size_t)(psg.e0 + lane) * 16 + cq * 4, make_float4(al[0], al[1], al[2], al[3]));
                 if (psg.valid && lane == 0) st4(a.alpha_sum + (size_t)psg.v * 16 + cq * 4, make_float4(sw[0], sw[1], sw[2], sw[3]));
@@ -384,15 +425,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
         uint32_t ph = 0;
         bool any = false;
         KSeg sg = kseg(d, blockIdx.x, wq);
-        int idx[8];
-        {
-            const int nn = sg.valid ? sg.R : 0;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int row = (i * 4 + sr) < nn ? (i * 4 + sr) : 0;
-                idx[i] = nn > 0 ? a.knn_src[sg.e0 + row] : 0;
-            }
-        }
+        // index pipeline: graph of the segment two tiles ahead -> its offsets one tile ahead -> neighbour indices one tile
+        // ahead -> gathers at the start of the tile; every level is requested a phase before its first use
+        // (tiles past the end fall back to the CTA's first tile: always a valid address, never used for real work)
+        auto tile_or_first = [&](long long t) { return t < ntiles ? t : (long long)blockIdx.x; };
+        KSeg nsg = kseg(d, tile_or_first(blockIdx.x + (long long)gridDim.x), wq);
+        int g2 = kseg_graph(d, tile_or_first(blockIdx.x + 2 * (long long)gridDim.x), wq);
+        // neighbour index of this lane's row (padded rows re-read row 0, an isolated node reads node 0); the gather below
+        // needs the indices of rows 4 i + (lane >> 3) and takes them from their lanes by shuffle (2 registers instead of 16)
+        int myidx = sg.valid ? a.knn_src[sg.e0 + (lane < sg.R ? lane : 0)] : 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1, tcount++) {
             const bool rowvalid = sg.valid && lane < sg.R;
             KTRACE(0, 0);
@@ -403,7 +444,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
             const float* ps = a.nc.A + (PASS == 0 ? a.nc.src_k : a.nc.src_v) + c0 + ch;
             float4 u[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) u[i] = ldg4(ps + (size_t)idx[i] * a.nc.lda);
+            for (int i = 0; i < 8; i++) u[i] = ldg4(ps + (size_t)__shfl_sync(PG_FULL, myidx, i * 4 + sr) * a.nc.lda);
             const float4 d4 = ldg4(a.nc.A + (size_t)sg.v * a.nc.lda + (PASS == 0 ? a.nc.dst_k : a.nc.dst_v) + c0 + ch);
             // this tile's post-processing inputs (consumed one iteration later) and the next tile's neighbour indices
             float4 nf = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -418,18 +459,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
                              "l"(a.q + (size_t)sg.v * 128 + c0 + lane * 4) : "memory");
             asm volatile("cp.async.commit_group;" ::: "memory");
             KTRACE(0, 13);
-            const bool more = tile + gridDim.x < ntiles;
-            const KSeg nsg = kseg(d, more ? tile + gridDim.x : tile, wq);
+            // next tile's neighbour indices (its offsets were fetched during the previous tile), the offsets of the tile after
+            // it (graph fetched during the previous tile) and the graph of the tile after that
+            const int nmyidx = nsg.valid ? a.knn_src[nsg.e0 + (lane < nsg.R ? lane : 0)] : 0;
+            const long long t2 = tile_or_first(tile + 2 * (long long)gridDim.x), t3 = tile_or_first(tile + 3 * (long long)gridDim.x);
+            const KSeg nsg2 = kseg_of_graph(d, t2, wq, g2);
+            const int g3 = kseg_graph(d, t3, wq);
             KTRACE(0, 14);
-            int nidx[8];
-            {
-                const int nn = nsg.valid ? nsg.R : 0;
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int row = (i * 4 + sr) < nn ? (i * 4 + sr) : 0;
-                    nidx[i] = nn > 0 ? a.knn_src[nsg.e0 + row] : 0;
-                }
-            }
             float2 x2[16];
             KTRACE(0, 1);
 #pragma unroll
@@ -540,9 +576,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
                 rel2 = a.x[(size_t)sg.v * 3 + 2] - a.x[(size_t)s * 3 + 2];
             }
             any = true;
-            sg = nsg;
-#pragma unroll
-            for (int i = 0; i < 8; i++) idx[i] = nidx[i];
+            sg = nsg; nsg = nsg2; g2 = g3;
+            myidx = nmyidx;
         }
         if (any) { asm volatile("cp.async.wait_group 0;" ::: "memory"); __syncwarp(); post(ph ^ 1, ph ^ 1, true); }
     }
