@@ -125,7 +125,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
     constexpr uint32_t C_HIDK = 0, C_OUTK = 128, C_HIDV = 256, C_OUTV = 384;
-    const long long ntiles = MULTI ? d.nbt : (d.Nl + 3) / 4;
+    // a CTA walks a CONTIGUOUS range of tiles [tile_begin, ntiles): consecutive tiles are atoms of the same molecule, whose
+    // node partial rows are then re-read from this SM's L1 instead of L2
+    const long long ntiles_all = MULTI ? d.nbt : (d.Nl + 3) / 4;
+    const long long tile_begin = ntiles_all * blockIdx.x / gridDim.x, ntiles = ntiles_all * (blockIdx.x + 1) / gridDim.x;
 
     if (warp >= MMA_WARP) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
             constexpr uint32_t idesc_v = tc::umma_idesc_bf16(128, NV);
             const uint32_t sW_u32 = tc::smem_u32(sW);
             uint32_t ph = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
+            for (long long tile = tile_begin; tile < ntiles; tile++, ph ^= 1) {
 #pragma unroll
                 for (int mlp = 0; mlp < 2; mlp++) {
                     tc::mbar_wait_wd(&bars[mlp == 0 ? B_HIDK : B_HIDV], ph);
@@ -174,8 +177,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
             const int pt = tid - (MMA_WARP + 1) * 32;      // 0..95
             uint32_t ph = 0;
             int k = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1, k++) {
-                const long long nt = tile + gridDim.x;
+            for (long long tile = tile_begin; tile < ntiles; tile++, ph ^= 1, k++) {
+                const long long nt = tile + 1;
                 if (nt < ntiles) {
                     for (int s4 = 0; s4 < 4; s4++) {
                         const SegInfo sg = seg_info<MULTI>(d, nt, s4);
@@ -379,13 +382,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
         uint32_t ph = 0;
         int tiles_done = 0;
         bool any = false;
-        SegInfo sg = seg_info<MULTI>(d, blockIdx.x, wq);
+        SegInfo sg = seg_info<MULTI>(d, tile_begin, wq);
         request_edge_rows(0, sg);
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
+        for (long long tile = tile_begin; tile < ntiles; tile++, ph ^= 1) {
             const bool rowvalid = sg.valid && sg.r0 + lane < sg.n - 1;
             const int r = rowvalid ? sg.r0 + lane : 0;
-            const bool more = tile + gridDim.x < ntiles;
-            const SegInfo nsg = seg_info<MULTI>(d, more ? tile + gridDim.x : tile, wq);
+            const bool more = tile + 1 < ntiles;
+            const SegInfo nsg = seg_info<MULTI>(d, more ? tile + 1 : tile, wq);
             // ---- key MLP
             layer_norm(0, sg, tmem + C_HIDK, true, 1, sg);
             // ---- value epilogue of the previous tile (its W2v MMA ran during that tile's logits and the LayerNorm above)

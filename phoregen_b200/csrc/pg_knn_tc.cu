@@ -149,7 +149,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
     constexpr uint32_t C_PRE = 0, C_HID = 128, C_OUT = 256;     // out: two buffers of 128 columns
-    const long long ntiles = (d.N + 3) / 4;
+    // a CTA walks a CONTIGUOUS range of tiles: consecutive tiles are nodes of the same molecule, so the gathered partial
+    // rows, coordinates and neighbour lists of a molecule are re-read from this SM's L1 instead of L2
+    const long long ntiles_all = (d.N + 3) / 4;
+    const long long tile_begin = ntiles_all * blockIdx.x / gridDim.x, ntiles = ntiles_all * (blockIdx.x + 1) / gridDim.x;   // [tile_begin, ntiles)
 
     if (warp >= MMA_WARP) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
@@ -162,9 +165,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
         // (~4,000 cycles per tile, the critical path of the whole kernel: table MMA(t) -> features(t+1) -> table MMA(t+1));
         // here every level runs one tile ahead of the next one, so a tile's feature step finds its inputs in registers.
         struct FIn { float xd0, xd1, xd2, xs0, xs1, xs2, cs0, cs1, cs2, cd0, cd1, cd2; int type; };    // type -1: padded row
-        const long long fstep = gridDim.x;
-        auto graph_at = [&](long long t) -> int { return kseg_graph(d, t < ntiles ? t : (long long)blockIdx.x, r >> 5); };
-        auto seg_at = [&](long long t, int g) -> KSeg { return kseg_of_graph(d, t < ntiles ? t : (long long)blockIdx.x, r >> 5, g); };
+        const long long fstep = 1;
+        auto graph_at = [&](long long t) -> int { return kseg_graph(d, t < ntiles ? t : tile_begin, r >> 5); };
+        auto seg_at = [&](long long t, int g) -> KSeg { return kseg_of_graph(d, t < ntiles ? t : tile_begin, r >> 5, g); };
         auto src_at = [&](long long t, const KSeg& sg) -> int { return (t < ntiles && sg.valid && frow < sg.R) ? a.knn_src[sg.e0 + frow] : -1; };
         auto load_in = [&](int s, const KSeg& sg) -> FIn {
             FIn f;
@@ -237,7 +240,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
             tc::umma_commit_w(&bars[B_PRE]);
         };
         // fill the index pipeline (the only place where the chain is walked in one go)
-        const long long f0 = blockIdx.x;
+        const long long f0 = tile_begin;
         FIn in_cur;
         int s1;
         KSeg seg1, seg2;
@@ -320,7 +323,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
         const int sr = lane >> 3, ch = (lane & 7) * 4;
         float* xp = sXp + warp * (16 * XP_LD);
         float al[4] = {0.f, 0.f, 0.f, 0.f};
-        KSeg psg = kseg(d, blockIdx.x, wq);                 // segment of the tile whose post-processing is pending
+        KSeg psg = kseg(d, tile_begin, wq);                 // segment of the tile whose post-processing is pending
         bool prow = false;
         float rel0 = 0.f, rel1 = 0.f, rel2 = 0.f;
         float4 pf = make_float4(0.f, 0.f, 0.f, 0.f);       // per-row inputs of the pending tile's post-processing, fetched a tile ahead:
@@ -424,17 +427,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
 
         uint32_t ph = 0;
         bool any = false;
-        KSeg sg = kseg(d, blockIdx.x, wq);
+        KSeg sg = kseg(d, tile_begin, wq);
         // index pipeline: graph of the segment two tiles ahead -> its offsets one tile ahead -> neighbour indices one tile
         // ahead -> gathers at the start of the tile; every level is requested a phase before its first use
         // (tiles past the end fall back to the CTA's first tile: always a valid address, never used for real work)
-        auto tile_or_first = [&](long long t) { return t < ntiles ? t : (long long)blockIdx.x; };
-        KSeg nsg = kseg(d, tile_or_first(blockIdx.x + (long long)gridDim.x), wq);
-        int g2 = kseg_graph(d, tile_or_first(blockIdx.x + 2 * (long long)gridDim.x), wq);
+        auto tile_or_first = [&](long long t) { return t < ntiles ? t : tile_begin; };
+        KSeg nsg = kseg(d, tile_or_first(tile_begin + 1), wq);
+        int g2 = kseg_graph(d, tile_or_first(tile_begin + 2), wq);
         // neighbour index of this lane's row (padded rows re-read row 0, an isolated node reads node 0); the gather below
         // needs the indices of rows 4 i + (lane >> 3) and takes them from their lanes by shuffle (2 registers instead of 16)
         int myidx = sg.valid ? a.knn_src[sg.e0 + (lane < sg.R ? lane : 0)] : 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1, tcount++) {
+        for (long long tile = tile_begin; tile < ntiles; tile++, ph ^= 1, tcount++) {
             const bool rowvalid = sg.valid && lane < sg.R;
             KTRACE(0, 0);
             // ---- gather the src-node partial rows: 8 lanes cover the 128-byte slice of one row (coalesced), the dst-node
@@ -462,7 +465,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
             // next tile's neighbour indices (its offsets were fetched during the previous tile), the offsets of the tile after
             // it (graph fetched during the previous tile) and the graph of the tile after that
             const int nmyidx = nsg.valid ? a.knn_src[nsg.e0 + (lane < nsg.R ? lane : 0)] : 0;
-            const long long t2 = tile_or_first(tile + 2 * (long long)gridDim.x), t3 = tile_or_first(tile + 3 * (long long)gridDim.x);
+            const long long t2 = tile_or_first(tile + 2), t3 = tile_or_first(tile + 3);
             const KSeg nsg2 = kseg_of_graph(d, t2, wq, g2);
             const int g3 = kseg_graph(d, t3, wq);
             KTRACE(0, 14);
