@@ -538,8 +538,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
         };
         // alpha-weighted sum of the value rows over the segment (lanes), residual add into h_bond
         auto epilogue = [&](uint32_t outV, uint32_t parity) {
-            tc::mbar_wait(&bars[B_OUTV], parity);
+            tc::mbar_wait(&bars[B_OUTV], parity);      // (also orders W2v(t-1)'s writes before this thread's next hid_v rows)
             tc::tc_fence_after();
+            if (!prev_valid) return;                   // no segment in this lane quarter of the previous tile
             uint32_t vu[32];
             tc::tmem_ld32_nowait(outV + lane_base + cq * 32, vu);
             tc::tmem_ld_wait();
@@ -578,7 +579,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             tc::mbar_wait(&bars[B_PREK], ph);
             tc::tc_fence_after();
             TRACE(role, 1);
-            layer_norm(0, preK, hidK);
+            // A lane quarter without a segment (the 3 spare slots of a unit's last tile: 9 % of all slots at n = 30) only keeps
+            // the hand-off protocol going: it reads nothing, so it may arrive at once; its stale hid rows feed MMAs whose
+            // output rows nobody reads.  The skipped arithmetic is power the capped GPU spends on clock instead.
+            if (sg.valid) layer_norm(0, preK, hidK);
+            else { tc::tc_fence_before(); tc::mbar_arrive(&bars[B_HIDK]); }
             TRACE(role, 2);
             // ---- value epilogue of the previous tile (its W2v MMA ran during that tile's logits and the LayerNorm above)
             if (tcount > 0) epilogue(ph ? 128 + tmem : 384 + tmem, ph ^ 1);
@@ -587,13 +592,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             tc::mbar_wait(&bars[ph ? B_PREV1 : B_PREV0], (tcount >> 1) & 1);
             tc::tc_fence_after();
             TRACE(role, 5);
-            layer_norm(1, preV, hidV);
+            if (sg.valid) layer_norm(1, preV, hidV);
+            else { tc::tc_fence_before(); tc::mbar_arrive(&bars[B_HIDV]); }
             TRACE(role, 6);
             // ---- logits of this thread's 4 heads, segment softmax across the 32 lanes (rows) of the warp
             {
                 tc::mbar_wait(&bars[B_OUTK], ph);
                 tc::tc_fence_after();
                 TRACE(role, 7);
+                if (sg.valid) {
                 uint32_t vv[32];
                 tc::tmem_ld32_nowait(preK + lane_base + cq * 32, vv);
                 tc::tmem_ld_wait();
@@ -650,6 +657,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
                         for (int h = 0; h < 4; h++) sm[h] += __shfl_xor_sync(PG_FULL, sm[h], o);
 #pragma unroll
                     for (int h = 0; h < 4; h++) al[h] *= __frcp_rn(sm[h]);
+                }
                 }
             }
             TRACE(role, 8);
