@@ -680,108 +680,117 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
 // Both k|v halves (256 channels), written as the bf16 hi/lo operand images trip_tc_kernel bulk-copies (layout at the top of
 // this file): P in the block of the DESTINATION atom's unit at row k (its position among the edges into dst), R in the block
 // of the SOURCE atom's unit at the segment index of dst, pre-swizzled for rows 11..14 of the angle slab.
-constexpr int PR_EDGES = 4;      // edges per warp: every weight row read from L1 is used for 4 edges
-__global__ void __launch_bounds__(256, 2) trip_pr_kernel(TripTcArgs a) {
+// The smearing products depend on the distance only, which both directions of a bond edge share: a CTA takes one molecule
+// and walks its UNDIRECTED pairs (s < t), computing smear(d_st) Wrkj and smear(d_st) Wrji once (half the FFMA work of an
+// edge-wise kernel) and emitting the P and R rows of both directed edges s->t and t->s.
+constexpr int PR_PAIRS = 2;      // pairs per warp and iteration: every weight row read from L1 serves 2 pairs = 4 edges
+constexpr int PR_WARPS = 8;
+__global__ void __launch_bounds__(PR_WARPS * 32, 2) trip_pr_kernel(TripTcArgs a) {
     const PlanDev& d = a.d;
-    const int lane = threadIdx.x & 31;
-    const long long e0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * PR_EDGES;
-    if (e0 >= d.Eb) return;
-    float mine[PR_EDGES];
-    unsigned long long acc[PR_EDGES][8];
-    // the warp issues in order: every dependent load level (indices -> coordinates / partial rows) is requested for all
-    // edges of the warp before the first use, so the warp pays one memory round trip per level instead of one per edge
-    long long ee[PR_EDGES];
-    int sn[PR_EDGES], tn[PR_EDGES];
-#pragma unroll
-    for (int k = 0; k < PR_EDGES; k++) {
-        ee[k] = min(e0 + k, d.Eb - 1);
-        sn[k] = d.esrc_node[ee[k]]; tn[k] = d.edst_node[ee[k]];
-    }
-    float4 tk[PR_EDGES], tv[PR_EDGES];
-#pragma unroll
-    for (int k = 0; k < PR_EDGES; k++) {
-        tk[k] = ldg4(a.T + (size_t)ee[k] * a.ldt + a.t_k + lane * 4);
-        tv[k] = ldg4(a.T + (size_t)ee[k] * a.ldt + a.t_v + lane * 4);
-    }
-    float xs[PR_EDGES][3], xt[PR_EDGES][3];
-    int gg_[PR_EDGES];
-#pragma unroll
-    for (int k = 0; k < PR_EDGES; k++) {
-        gg_[k] = d.node_graph[tn[k]];
-#pragma unroll
-        for (int c = 0; c < 3; c++) { xs[k][c] = a.x[(size_t)sn[k] * 3 + c]; xt[k][c] = a.x[(size_t)tn[k] * 3 + c]; }
-    }
-    // rows of the operand images: P row = (unit of dst, position of this edge among the edges into dst),
-    //                             R row = (unit of src, segment index of dst), both in units of 128-byte rows
-    long long prow[PR_EDGES], rrow[PR_EDGES];
-    int nrow[PR_EDGES], pswz[PR_EDGES], rswz[PR_EDGES];
-#pragma unroll
-    for (int k = 0; k < PR_EDGES; k++) {
-        const int g = gg_[k], n = d.g_n[g], c0 = d.ctx_off[g] + d.g_p[g];
-        const long long eo = d.eoff[g];
-        const int sl = sn[k] - c0, tl = tn[k] - c0;
-        const long long ubp = eo + (long long)tl * (n - 1), ubr = eo + (long long)sl * (n - 1);
-        const int kr = (int)(ee[k] - ubp), sidx = tl - (tl > sl);
-        nrow[k] = n - 1;
-        prow[k] = ubp * 4 + kr; pswz[k] = kr & 7;
-        rrow[k] = ubr * 4 + sidx; rswz[k] = (R_ROW0 + (sidx & 3)) & 7;
-    }
-#pragma unroll
-    for (int k = 0; k < PR_EDGES; k++) {
-        const float4 hs0 = ldg4(a.H + (size_t)sn[k] * a.ldh + a.hk_k + lane * 4), ht0 = ldg4(a.H + (size_t)tn[k] * a.ldh + a.hj_k + lane * 4);
-        const float4 hs1 = ldg4(a.H + (size_t)sn[k] * a.ldh + a.hk_v + lane * 4), ht1 = ldg4(a.H + (size_t)tn[k] * a.ldh + a.hj_v + lane * 4);
-        const float d0 = xt[k][0] - xs[k][0], d1 = xt[k][1] - xs[k][1], d2 = xt[k][2] - xs[k][2];
-        const float dist = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
-        mine[k] = lane < 20 ? smear_val(dist, lane) : 0.f;
-        const float4 p0 = f4add(f4add(tk[k], hs0), ht0);
-        const float4 p1 = f4add(f4add(tv[k], hs1), ht1);
-        acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0ull;
-        acc[k][4] = pk2(p0.x, p0.y); acc[k][5] = pk2(p0.z, p0.w); acc[k][6] = pk2(p1.x, p1.y); acc[k][7] = pk2(p1.z, p1.w);
-    }
-    // accumulators stay packed (two fp32 per 64-bit register pair) through the 20-term loop (FFMA2)
-#pragma unroll 2
-    for (int gg = 0; gg < 20; gg++) {
-        const float4 w0 = ldg4(a.wrji + gg * 256 + lane * 4), w1 = ldg4(a.wrji + gg * 256 + 128 + lane * 4);
-        const float4 w2 = ldg4(a.wrkj + gg * 256 + lane * 4), w3 = ldg4(a.wrkj + gg * 256 + 128 + lane * 4);
-        const unsigned long long u0 = pk2(w0.x, w0.y), u1 = pk2(w0.z, w0.w), u2 = pk2(w1.x, w1.y), u3 = pk2(w1.z, w1.w);
-        const unsigned long long u4 = pk2(w2.x, w2.y), u5 = pk2(w2.z, w2.w), u6 = pk2(w3.x, w3.y), u7 = pk2(w3.z, w3.w);
-#pragma unroll
-        for (int k = 0; k < PR_EDGES; k++) {
-            const float sg = __shfl_sync(PG_FULL, mine[k], gg);
-            const unsigned long long ss = pk2(sg, sg);
-            acc[k][0] = fma2_raw(ss, u0, acc[k][0]); acc[k][1] = fma2_raw(ss, u1, acc[k][1]);
-            acc[k][2] = fma2_raw(ss, u2, acc[k][2]); acc[k][3] = fma2_raw(ss, u3, acc[k][3]);
-            acc[k][4] = fma2_raw(ss, u4, acc[k][4]); acc[k][5] = fma2_raw(ss, u5, acc[k][5]);
-            acc[k][6] = fma2_raw(ss, u6, acc[k][6]); acc[k][7] = fma2_raw(ss, u7, acc[k][7]);
-        }
-    }
-    // this lane's 4 channels of one MLP -> bf16 hi and lo (8 bytes each) at chunk ((lane & 15) >> 1) ^ swizzle of the row
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = blockIdx.x;
+    const int n = d.g_n[g];
+    if (n < 2) return;
+    const int c0 = d.ctx_off[g] + d.g_p[g];                // context node of the molecule's first ligand atom
+    const long long eo = d.eoff[g];
+    const int npairs = n * (n - 1) / 2;
     const int half = lane >> 4, c8 = (lane & 15) >> 1, sub = (lane & 1) * 8;
     const size_t mlp_bytes = (size_t)d.Eb * 512;
-    auto put = [&](uint8_t* img, long long row0, int nr, int swz, unsigned long long v01, unsigned long long v23) {
-        const float2 x01 = up2(v01), x23 = up2(v23);
+    // this lane's 4 channels of one MLP -> bf16 hi and lo (8 bytes each) at chunk ((lane & 15) >> 1) ^ swizzle of the row
+    auto put = [&](uint8_t* img, long long row0, int nr, int swz, float4 v) {
         uint32_t h0, l0, h1, l1;
-        tc::split_pair_trunc(x01.x, x01.y, h0, l0);
-        tc::split_pair_trunc(x23.x, x23.y, h1, l1);
+        tc::split_pair_trunc(v.x, v.y, h0, l0);
+        tc::split_pair_trunc(v.z, v.w, h1, l1);
         uint8_t* dst = img + (size_t)(row0 + (long long)half * nr) * 128 + ((c8 ^ swz) << 4) + sub;
         *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);                                    // hi image: blocks 0, 1
         *reinterpret_cast<uint2*>(dst + (size_t)2 * nr * 128) = make_uint2(l0, l1);             // lo image: blocks 2, 3
     };
+    auto f4 = [](unsigned long long lo, unsigned long long hi) { const float2 x = up2(lo), y = up2(hi); return make_float4(x.x, x.y, y.x, y.y); };
+    for (int p0 = (blockIdx.y * PR_WARPS + warp) * PR_PAIRS; p0 < npairs; p0 += gridDim.y * PR_WARPS * PR_PAIRS) {
+        int sl[PR_PAIRS], tl[PR_PAIRS];
+        float mine[PR_PAIRS];
+        unsigned long long acc[PR_PAIRS][8];
+        float4 pst[PR_PAIRS][2], pts[PR_PAIRS][2];         // partial P rows (k, v) of s->t and t->s before the smearing term
 #pragma unroll
-    for (int k = 0; k < PR_EDGES; k++) {
-        const long long e = e0 + k;
-        if (e >= d.Eb) break;
-        put((uint8_t*)a.R, rrow[k], nrow[k], rswz[k], acc[k][0], acc[k][1]);
-        put((uint8_t*)a.R + mlp_bytes, rrow[k], nrow[k], rswz[k], acc[k][2], acc[k][3]);
-        put((uint8_t*)a.P, prow[k], nrow[k], pswz[k], acc[k][4], acc[k][5]);
-        put((uint8_t*)a.P + mlp_bytes, prow[k], nrow[k], pswz[k], acc[k][6], acc[k][7]);
+        for (int k = 0; k < PR_PAIRS; k++) {
+            const int p = min(p0 + k, npairs - 1);
+            // pair index p = t (t - 1) / 2 + s with s < t
+            int t = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+            while (t * (t - 1) / 2 > p) t--;
+            while ((t + 1) * t / 2 <= p) t++;
+            tl[k] = t; sl[k] = p - t * (t - 1) / 2;
+        }
+        // every dependent load level is requested for both pairs before its first use
+        float xs[PR_PAIRS][3], xt[PR_PAIRS][3];
+#pragma unroll
+        for (int k = 0; k < PR_PAIRS; k++) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) { xs[k][c] = a.x[(size_t)(c0 + sl[k]) * 3 + c]; xt[k][c] = a.x[(size_t)(c0 + tl[k]) * 3 + c]; }
+        }
+#pragma unroll
+        for (int k = 0; k < PR_PAIRS; k++) {
+            const long long est = eo + (long long)tl[k] * (n - 1) + sl[k];            // s -> t: row s of unit t (s < t)
+            const long long ets = eo + (long long)sl[k] * (n - 1) + (tl[k] - 1);      // t -> s: row t - 1 of unit s
+            const float* hs = a.H + (size_t)(c0 + sl[k]) * a.ldh + lane * 4;
+            const float* ht = a.H + (size_t)(c0 + tl[k]) * a.ldh + lane * 4;
+            const float4 t0 = ldg4(a.T + (size_t)est * a.ldt + a.t_k + lane * 4), t1 = ldg4(a.T + (size_t)est * a.ldt + a.t_v + lane * 4);
+            const float4 u0 = ldg4(a.T + (size_t)ets * a.ldt + a.t_k + lane * 4), u1 = ldg4(a.T + (size_t)ets * a.ldt + a.t_v + lane * 4);
+            // (edge GEMM slice + h_src Whk) + h_dst Whj, as in the edge-wise formulation
+            pst[k][0] = f4add(f4add(t0, ldg4(hs + a.hk_k)), ldg4(ht + a.hj_k));
+            pst[k][1] = f4add(f4add(t1, ldg4(hs + a.hk_v)), ldg4(ht + a.hj_v));
+            pts[k][0] = f4add(f4add(u0, ldg4(ht + a.hk_k)), ldg4(hs + a.hj_k));
+            pts[k][1] = f4add(f4add(u1, ldg4(ht + a.hk_v)), ldg4(hs + a.hj_v));
+            const float d0 = xt[k][0] - xs[k][0], d1 = xt[k][1] - xs[k][1], d2 = xt[k][2] - xs[k][2];
+            const float dist = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+            mine[k] = lane < 20 ? smear_val(dist, lane) : 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[k][i] = 0ull;
+        }
+        // accumulators stay packed (two fp32 per 64-bit register pair) through the 20-term loop (FFMA2)
+#pragma unroll 2
+        for (int gg = 0; gg < 20; gg++) {
+            const float4 w0 = ldg4(a.wrji + gg * 256 + lane * 4), w1 = ldg4(a.wrji + gg * 256 + 128 + lane * 4);
+            const float4 w2 = ldg4(a.wrkj + gg * 256 + lane * 4), w3 = ldg4(a.wrkj + gg * 256 + 128 + lane * 4);
+            const unsigned long long u0 = pk2(w0.x, w0.y), u1 = pk2(w0.z, w0.w), u2 = pk2(w1.x, w1.y), u3 = pk2(w1.z, w1.w);
+            const unsigned long long u4 = pk2(w2.x, w2.y), u5 = pk2(w2.z, w2.w), u6 = pk2(w3.x, w3.y), u7 = pk2(w3.z, w3.w);
+#pragma unroll
+            for (int k = 0; k < PR_PAIRS; k++) {
+                const float sg = __shfl_sync(PG_FULL, mine[k], gg);
+                const unsigned long long ss = pk2(sg, sg);
+                acc[k][0] = fma2_raw(ss, u0, acc[k][0]); acc[k][1] = fma2_raw(ss, u1, acc[k][1]);
+                acc[k][2] = fma2_raw(ss, u2, acc[k][2]); acc[k][3] = fma2_raw(ss, u3, acc[k][3]);
+                acc[k][4] = fma2_raw(ss, u4, acc[k][4]); acc[k][5] = fma2_raw(ss, u5, acc[k][5]);
+                acc[k][6] = fma2_raw(ss, u6, acc[k][6]); acc[k][7] = fma2_raw(ss, u7, acc[k][7]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PR_PAIRS; k++) {
+            if (p0 + k >= npairs) break;
+            const int nr = n - 1;
+            const float4 rk = f4(acc[k][0], acc[k][1]), rv = f4(acc[k][2], acc[k][3]);       // smear Wrji (key | value)
+            const float4 sk = f4(acc[k][4], acc[k][5]), sv = f4(acc[k][6], acc[k][7]);       // smear Wrkj
+            const long long ut = (eo + (long long)tl[k] * nr) * 4, us = (eo + (long long)sl[k] * nr) * 4;   // units of t / of s, in 128-byte rows
+            // P rows: s -> t is row s of unit t, t -> s is row t - 1 of unit s
+            put((uint8_t*)a.P, ut + sl[k], nr, sl[k] & 7, f4add(pst[k][0], sk));
+            put((uint8_t*)a.P + mlp_bytes, ut + sl[k], nr, sl[k] & 7, f4add(pst[k][1], sv));
+            put((uint8_t*)a.P, us + tl[k] - 1, nr, (tl[k] - 1) & 7, f4add(pts[k][0], sk));
+            put((uint8_t*)a.P + mlp_bytes, us + tl[k] - 1, nr, (tl[k] - 1) & 7, f4add(pts[k][1], sv));
+            // R rows live in the unit of the SOURCE atom at the segment index of the destination
+            const int sidx_st = tl[k] - 1, sidx_ts = sl[k];                                   // s -> t in unit s; t -> s in unit t
+            put((uint8_t*)a.R, us + sidx_st, nr, (R_ROW0 + (sidx_st & 3)) & 7, rk);
+            put((uint8_t*)a.R + mlp_bytes, us + sidx_st, nr, (R_ROW0 + (sidx_st & 3)) & 7, rv);
+            put((uint8_t*)a.R, ut + sidx_ts, nr, (R_ROW0 + (sidx_ts & 3)) & 7, rk);
+            put((uint8_t*)a.R + mlp_bytes, ut + sidx_ts, nr, (R_ROW0 + (sidx_ts & 3)) & 7, rv);
+        }
     }
 }
 }  // namespace
 
 int pg_launch_trip_pr(const TripTcArgs& a, cudaStream_t s) {
     if (a.d.Eb <= 0) return PG_OK;
-    trip_pr_kernel<<<(unsigned)((a.d.Eb + 8 * PR_EDGES - 1) / (8 * PR_EDGES)), 256, 0, s>>>(a);
+    // gridDim.x = molecules; gridDim.y splits a molecule's pairs so that the grid has at least ~8 waves of CTAs (tail effect)
+    const int split = std::max(1, std::min(8, (8 * 2 * 148 + a.d.G - 1) / a.d.G));
+    trip_pr_kernel<<<dim3((unsigned)a.d.G, (unsigned)split), PR_WARPS * 32, 0, s>>>(a);
     PG_LAUNCH_CHECK();
     return PG_OK;
 }
