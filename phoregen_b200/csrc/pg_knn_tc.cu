@@ -38,7 +38,7 @@ constexpr int FEAT_PART = 128 * KF * 2;     // 24 KB: [k-step 6][row/8][kc 2][ro
 constexpr int SM_FEAT = 2 * FEAT_PART;
 constexpr int XP_LD = 36;
 constexpr int SM_XP = 16 * 16 * XP_LD * 4;  // per row warp: transpose tile of 16 rows x 32 channels (two rounds per tile)
-constexpr int SM_STAT = 128 * 4 * 2 * 4;    // [128 rows][4 quarters][2] partial LayerNorm sums
+constexpr int SM_STAT = 128 * 4 * 2 * 4;    // [4 quarters][128 rows] partial second moments of the LayerNorm (half used)
 constexpr int SM_RED = 4 * 4 * 4 * 4;
 constexpr int SM_Q = 16 * 2 * 32 * 4;       // per row warp: two 128-byte slots for the query slice of the pending / current tile
 constexpr int SM_TOTAL = SM_W + SM_TAB + SM_FEAT + SM_XP + SM_STAT + SM_RED + SM_Q + 3 * 128 * 4 + 128 + 1024;
@@ -499,23 +499,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
 #pragma unroll
                 for (int i = 0; i < 16; i++) x2[i] = tc::add2(x2[i], make_float2(__uint_as_float(xu[2 * i]), __uint_as_float(xu[2 * i + 1])));
             }
-            float2 s1 = make_float2(0.f, 0.f), s2 = s1, s1b = s1, s2b = s1;
+            // the pre-activation is mean-free (every first-Linear block and table row has its channel mean removed at pack
+            // time, weights._center_first_linears): the LayerNorm only needs the second moment
+            float2 s2 = make_float2(0.f, 0.f), s2b = s2;
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
-                s1 = tc::add2(s1, x2[i]); s1b = tc::add2(s1b, x2[i + 1]);
                 s2 = tc::fma2(x2[i], x2[i], s2); s2b = tc::fma2(x2[i + 1], x2[i + 1], s2b);
             }
-            s1 = tc::add2(s1, s1b); s2 = tc::add2(s2, s2b);
-            // quarter-major layout [quarter][row]: consecutive lanes touch consecutive 8-byte words (no bank conflicts)
-            float* st = sStat + (wq * 32 + lane) * 2;
-            *reinterpret_cast<float2*>(st + cq * 256) = make_float2(s1.x + s1.y, s2.x + s2.y);
+            s2 = tc::add2(s2, s2b);
+            // quarter-major layout [quarter][row]: consecutive lanes touch consecutive words (no bank conflicts)
+            float* st = sStat + wq * 32 + lane;
+            st[cq * 128] = s2.x + s2.y;
             asm volatile("bar.sync %0, 128;" ::"r"(3 + wq) : "memory");
             KTRACE(0, 4);
-            const float2 q0 = *reinterpret_cast<const float2*>(st), q1 = *reinterpret_cast<const float2*>(st + 256);
-            const float2 q2 = *reinterpret_cast<const float2*>(st + 512), q3 = *reinterpret_cast<const float2*>(st + 768);
-            const float mu = ((q0.x + q1.x) + (q2.x + q3.x)) * (1.0f / 128.0f);
-            const float rstd = rsqrtf(fmaxf(fmaf(-mu, mu, ((q0.y + q1.y) + (q2.y + q3.y)) * (1.0f / 128.0f)), 0.f) + 1e-5f);
-            const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mu * rstd, -mu * rstd);
+            const float rstd = rsqrtf(((st[0] + st[128]) + (st[256] + st[384])) * (1.0f / 128.0f) + 1e-5f);
+            const float2 rs2 = make_float2(rstd, rstd);
             const float* gam = sLn + cq * 32;
             const float* bet = gam + 128;
             if (KF16) {
@@ -524,13 +522,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
                     const float4 b4 = ld4(bet + 2 * i);
-                    float2 y0 = tc::fma2(x2[i], rs2, nm2), y1 = tc::fma2(x2[i + 1], rs2, nm2);
+                    float2 y0, y1;
                     if (fold) {
-                        y0 = tc::add2(y0, make_float2(b4.x, b4.y)); y1 = tc::add2(y1, make_float2(b4.z, b4.w));
+                        y0 = tc::fma2(x2[i], rs2, make_float2(b4.x, b4.y)); y1 = tc::fma2(x2[i + 1], rs2, make_float2(b4.z, b4.w));
                     } else {
                         const float4 g4 = ld4(gam + 2 * i);
-                        y0 = tc::fma2(y0, make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
-                        y1 = tc::fma2(y1, make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
+                        y0 = tc::fma2(tc::mul2(x2[i], rs2), make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
+                        y1 = tc::fma2(tc::mul2(x2[i + 1], rs2), make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
                     }
                     asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(hh[i]) : "f"(y0.y), "f"(y0.x));
                     asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(hh[i + 1]) : "f"(y1.y), "f"(y1.x));
@@ -545,15 +543,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
                     const float4 b4 = ld4(bet + 2 * i);
-                    tc::split_pair_relu(tc::add2(tc::fma2(x2[i], rs2, nm2), make_float2(b4.x, b4.y)), hi[i], lo[i]);
-                    tc::split_pair_relu(tc::add2(tc::fma2(x2[i + 1], rs2, nm2), make_float2(b4.z, b4.w)), hi[i + 1], lo[i + 1]);
+                    tc::split_pair_relu(tc::fma2(x2[i], rs2, make_float2(b4.x, b4.y)), hi[i], lo[i]);
+                    tc::split_pair_relu(tc::fma2(x2[i + 1], rs2, make_float2(b4.z, b4.w)), hi[i + 1], lo[i + 1]);
                 }
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
                     const float4 g4 = ld4(gam + 2 * i), b4 = ld4(bet + 2 * i);
-                    float2 y0 = tc::fma2(tc::fma2(x2[i], rs2, nm2), make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
-                    float2 y1 = tc::fma2(tc::fma2(x2[i + 1], rs2, nm2), make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
+                    float2 y0 = tc::fma2(tc::mul2(x2[i], rs2), make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
+                    float2 y1 = tc::fma2(tc::mul2(x2[i + 1], rs2), make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
                     tc::split_pair_relu(y0, hi[i], lo[i]);
                     tc::split_pair_relu(y1, hi[i + 1], lo[i + 1]);
                 }

@@ -60,7 +60,7 @@ constexpr int SM_ONE = 2 * 4096;           // constant one-hot A operand: two K1
 constexpr int SM_FEAT1 = 2 * 4096;         // (hi,lo) x [128 x 16] bf16, no swizzle
 constexpr int SM_FEAT = 2 * SM_FEAT1;      // double-buffered: the feature warps run up to two tiles ahead
 constexpr int SM_Q = 2 * 4 * 128 * 4;      // double-buffered query rows of a tile's 4 segments
-constexpr int SM_STAT = 128 * 16 * 4;      // LayerNorm partial sums [mlp][quarter][row][2]
+constexpr int SM_STAT = 128 * 8 * 4;       // LayerNorm partial second moments [mlp][quarter][row]
 constexpr int SM_FIXED = SM_W + SM_WA + SM_P + SM_ONE + SM_FEAT + SM_Q + SM_STAT + 6 * 128 * 4 /*ln + b2*/ + 256 /*barriers*/;
 constexpr float kInvSqrtD = 0.35355339059327373f;
 constexpr int ROW_WARPS = 16;               // 4 warps per TMEM lane quarter, each owning a 32-channel slice of the row
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
     uint8_t* sOne = sP + SM_P;
     uint8_t* sFeat = sOne + SM_ONE;
     float* sQ0 = (float*)(sFeat + SM_FEAT);         // [2][4 x 128] query rows
-    float* sStat = sQ0 + SM_Q / 4;                  // [2 mlp][4 quarters][128 rows][2]  partial LayerNorm sums (quarter-major: conflict-free)
+    float* sStat = sQ0 + SM_Q / 4;                  // [2 mlp][4 quarters][128 rows] partial second moments of the LayerNorm (quarter-major: conflict-free)
     float* sLn = sStat + SM_STAT / 4;               // gk, bk, gv, bv
     float* sB2 = sLn + 4 * 128;                     // b2k, b2v
     uint64_t* bars = (uint64_t*)(sB2 + 2 * 128);
@@ -469,24 +469,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
 #pragma unroll
                 for (int i = 0; i < 16; i++) x2[i] = make_float2(__uint_as_float(xu[2 * i]), __uint_as_float(xu[2 * i + 1]));
             }
-            float2 s1 = make_float2(0.f, 0.f), s2 = s1, s1b = s1, s2b = s1;
+            // The pre-activation arrives MEAN-FREE: every operand of the first Linear (Wa, P, R) has its channel mean removed
+            // (weights._center_first_linears), so the LayerNorm only needs the second moment: var = sum x^2 / 128.
+            float2 s2 = make_float2(0.f, 0.f), s2b = s2;
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
-                s1 = tc::add2(s1, x2[i]); s1b = tc::add2(s1b, x2[i + 1]);
                 s2 = tc::fma2(x2[i], x2[i], s2); s2b = tc::fma2(x2[i + 1], x2[i + 1], s2b);
             }
-            s1 = tc::add2(s1, s1b); s2 = tc::add2(s2, s2b);
+            s2 = tc::add2(s2, s2b);
             // combine with the other three channel quarters of the same row (warps w +- 4k, same lane).  The barrier also
             // orders this lane quarter's reads of the previous tile's accumulators before the hid columns overwrite them.
-            // quarter-major layout [mlp][quarter][row]: consecutive lanes touch consecutive 8-byte words (no bank conflicts)
-            float* st = sStat + ((size_t)(mlp * 4) * 128 + wq * 32 + lane) * 2;
-            *reinterpret_cast<float2*>(st + cq * 256) = make_float2(s1.x + s1.y, s2.x + s2.y);
+            // quarter-major layout [mlp][quarter][row]: consecutive lanes touch consecutive words (no bank conflicts)
+            float* st = sStat + (size_t)(mlp * 4) * 128 + wq * 32 + lane;
+            st[cq * 128] = s2.x + s2.y;
             asm volatile("bar.sync %0, 128;" ::"r"(3 + wq) : "memory");
-            const float2 q0 = *reinterpret_cast<const float2*>(st), q1 = *reinterpret_cast<const float2*>(st + 256);
-            const float2 q2 = *reinterpret_cast<const float2*>(st + 512), q3 = *reinterpret_cast<const float2*>(st + 768);
-            const float mu = ((q0.x + q1.x) + (q2.x + q3.x)) * (1.0f / 128.0f);
-            const float rstd = rsqrtf(fmaxf(fmaf(-mu, mu, ((q0.y + q1.y) + (q2.y + q3.y)) * (1.0f / 128.0f)), 0.f) + 1e-5f);
-            const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mu * rstd, -mu * rstd);
+            const float rstd = rsqrtf(((st[0] + st[128]) + (st[256] + st[384])) * (1.0f / 128.0f) + 1e-5f);
+            const float2 rs2 = make_float2(rstd, rstd);
             const float* gam = sLn + mlp * 256 + cq * 32;
             const float* bet = gam + 128;
             uint32_t hi[16], lo[16];
@@ -495,13 +493,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
                     const float4 b4 = ld4(bet + 2 * i);
-                    float2 y0 = tc::fma2(x2[i], rs2, nm2), y1 = tc::fma2(x2[i + 1], rs2, nm2);
+                    float2 y0, y1;
                     if (fold[0]) {
-                        y0 = tc::add2(y0, make_float2(b4.x, b4.y)); y1 = tc::add2(y1, make_float2(b4.z, b4.w));
+                        y0 = tc::fma2(x2[i], rs2, make_float2(b4.x, b4.y)); y1 = tc::fma2(x2[i + 1], rs2, make_float2(b4.z, b4.w));
                     } else {
                         const float4 g4 = ld4(gam + 2 * i);
-                        y0 = tc::fma2(y0, make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
-                        y1 = tc::fma2(y1, make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
+                        y0 = tc::fma2(tc::mul2(x2[i], rs2), make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
+                        y1 = tc::fma2(tc::mul2(x2[i + 1], rs2), make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
                     }
                     asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi[i]) : "f"(y0.y), "f"(y0.x));
                     asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi[i + 1]) : "f"(y1.y), "f"(y1.x));
@@ -517,15 +515,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
                     const float4 b4 = ld4(bet + 2 * i);
-                    tc::split_pair_relu(tc::add2(tc::fma2(x2[i], rs2, nm2), make_float2(b4.x, b4.y)), hi[i], lo[i]);
-                    tc::split_pair_relu(tc::add2(tc::fma2(x2[i + 1], rs2, nm2), make_float2(b4.z, b4.w)), hi[i + 1], lo[i + 1]);
+                    tc::split_pair_relu(tc::fma2(x2[i], rs2, make_float2(b4.x, b4.y)), hi[i], lo[i]);
+                    tc::split_pair_relu(tc::fma2(x2[i + 1], rs2, make_float2(b4.z, b4.w)), hi[i + 1], lo[i + 1]);
                 }
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
                     const float4 g4 = ld4(gam + 2 * i), b4 = ld4(bet + 2 * i);
-                    float2 y0 = tc::fma2(tc::fma2(x2[i], rs2, nm2), make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
-                    float2 y1 = tc::fma2(tc::fma2(x2[i + 1], rs2, nm2), make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
+                    float2 y0 = tc::fma2(tc::mul2(x2[i], rs2), make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
+                    float2 y1 = tc::fma2(tc::mul2(x2[i + 1], rs2), make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
                     tc::split_pair_relu(y0, hi[i], lo[i]);
                     tc::split_pair_relu(y1, hi[i + 1], lo[i + 1]);
                 }

@@ -123,7 +123,26 @@ def pack_state_dict(sd):
                 out[S + "wrkj"] = np.concatenate([k["W1"][:, 128:148].T, v["W1"][:, 128:148].T], 1)
                 out[S + "wrji"] = np.concatenate([k["W1"][:, 148:168].T, v["W1"][:, 148:168].T], 1)
                 out[S + "wa"] = np.concatenate([k["W1"][:, 168:181].T, v["W1"][:, 168:181].T], 1)
+        _center_first_linears(out, L)
     return out
+
+
+def _center_first_linears(out, L):
+    """Every first Linear of the attention MLPs is followed by a LayerNorm over its 128 hidden channels (common.py:99-119
+    with norm=True), which subtracts the channel mean of the pre-activation.  That subtraction is linear, so it is applied
+    to the weights instead: each 128-column block of the split first Linears (node / edge GEMM blocks and their biases,
+    the kNN edge-type tables, the triplet smearing and angle slices) has its mean over the 128 output channels removed
+    (fp64).  Every partial product the kernels add up is then mean-free, their sum is the pre-activation minus its mean, and
+    the tensor-core attention kernels only need the second moment (sum x^2) for the LayerNorm.  Kernels that still
+    subtract the mean (fp32 twins, the GEMM prologue of the query MLPs) see a mean of ~0: same result."""
+    def blocks(a):
+        a = np.array(a, dtype=np.float64)
+        shp = a.shape
+        v = a.reshape(shp[:-1] + (shp[-1] // 128, 128))
+        return (v - v.mean(axis=-1, keepdims=True)).reshape(shp)
+    for name in ("n1.wt", "n1.b", "e1.wt", "e1.b", "n2.wt", "n2.b", "e2.wt", "e2.b", "nk.tab_k", "nk.tab_v", "pk.tab_k", "pk.tab_v",
+                 "tr.wrkj", "tr.wrji", "tr.wa"):
+        out[L + name] = blocks(out[L + name])
 
 
 def _bf16_bits(x32):
