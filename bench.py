@@ -298,6 +298,7 @@ def hbm_kernels(plan, smp, dev, peaks, reps=20):
 
     Nl, Eb, N, Ek, G = plan.Nl, plan.Eb, plan.N, plan.Ek, plan.G
     ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+    ts = torch.full_like(smp.time_step, 500)          # a fixed mid-trajectory step (the sampler's own may be past the last one)
     log_e, log_n = smp.log_edge.clone(), smp.log_node.clone()
     oh_e, oh_n = torch.empty_like(smp.h_edge), torch.empty_like(smp.h_node)
     cl_e, cl_n = torch.empty_like(smp.edge_cls), torch.empty_like(smp.node_cls)
@@ -307,12 +308,12 @@ def hbm_kernels(plan, smp, dev, peaks, reps=20):
     opts = [dict(type="atom_prox", min_d=1.2, max_d=1.9), dict(type="center_prox")]
     cases = {
         # bytes: pred + log_vt read, log_vt + onehot written (K f32 each), class int32 written, row->graph int32 read
-        "categorical_step_kernel<6> (edges)": (lambda: plan.categorical_step(pm, "edge", smp.pred[2], log_e, smp.time_step, seed=1, step_counter=ctr,
+        "categorical_step_kernel<6> (edges)": (lambda: plan.categorical_step(pm, "edge", smp.pred[2], log_e, ts, seed=1, step_counter=ctr,
                                                                              onehot=oh_e, cls=cl_e), Eb * (4 * 6 * 4 + 8)),
-        "categorical_step_kernel<12> (atoms)": (lambda: plan.categorical_step(pm, "node", smp.pred[0], log_n, smp.time_step, seed=1, step_counter=ctr,
+        "categorical_step_kernel<12> (atoms)": (lambda: plan.categorical_step(pm, "node", smp.pred[0], log_n, ts, seed=1, step_counter=ctr,
                                                                               onehot=oh_n, cls=cl_n), Nl * (4 * 12 * 4 + 8)),
         # x_t, x_recon read, x_prev written (3 f32 each), row->graph read
-        "position_step_kernel": (lambda: plan.position_step(pm, smp.pos, smp.pred[1], smp.time_step, seed=1, step_counter=ctr, out=xo), Nl * (3 * 12 + 4)),
+        "position_step_kernel": (lambda: plan.position_step(pm, smp.pos, smp.pred[1], ts, seed=1, step_counter=ctr, out=xo), Nl * (3 * 12 + 4)),
         # coordinates read once, one int64 pair per kNN edge written by the exporting entry point (pg_knn_graph)
         "knn_kernel<0> (k=32 joint graph, exporting entry point)": (lambda: plan.knn_graph(xctx, 0), N * 12 + Ek * 16),
         # positions + sampled edge classes (through the edge permutation) read, gradient written; two launches (one per drift entry)
