@@ -51,7 +51,14 @@ const char* pg_last_error(void);
 /* ---------------------------------------------------------------- packed weights
  * The Python host packs the reference state_dict (641 keys, SURVEY.md §8(b) "Checkpoint") into one
  * fp32 device blob; slot i starts at d_blob + h_offsets[i] (in floats).  Slot names/sizes are
- * self-described so the packer and the library cannot drift apart. */
+ * self-described so the packer and the library cannot drift apart.
+ * Contract of the slot contents (phoregen_b200/weights.py is the reference packer):
+ *   - first Linears of the attention MLPs are split along their concatenated input (DESIGN.md "Factorisation") and every
+ *     128-column block of them ("L*.n1/e1/n2/e2.wt|b", "L*.nk|pk.tab_k|v", "L*.tr.wrkj|wrji|wa") has its mean over the
+ *     128 output channels removed: the LayerNorm that follows subtracts it anyway, and the tensor-core attention kernels
+ *     rely on mean-free pre-activations (they only accumulate the second moment);
+ *   - "<S>.w2k.bf" / "<S>.w2v.bf" are bf16 hi|lo images [2][out][128] (LayerNorm gain folded in where "<S>.fold" says so),
+ *     "*.wt.bf" the pre-swizzled 64-column GEMM images, "L*.tr.wa.bf" the angle-slab image of csrc/pg_trip_tc.cu. */
 int pg_weight_slot_count(void);
 const char* pg_weight_slot_name(int slot);      /* e.g. "L3.trip.w2k" or "G.ew.w1t" */
 int64_t pg_weight_slot_numel(int slot);

@@ -129,3 +129,29 @@ def test_schedules_shapes_and_invariants():
     np.testing.assert_allclose(prior.sum(), 1.0)
     g = schedules.gaussian_tables(schedules.beta_schedule("advance", 1000, scale_start=0.9999, scale_end=0.0001, width=3))
     assert g["std"][0] == 0.0 and np.all(np.diff(g["alphas_bar"]) <= 0)
+
+
+def test_mma_issue_stays_on_the_uniform_datapath():
+    """The tcgen05 kernels issue their MMAs warp-collectively (pg_tc.cuh umma_*_w): descriptor arithmetic on the uniform
+    datapath, one elected lane issues.  Issued from `if (lane == 0)` inside a role branch on `threadIdx.x >> 5` instead,
+    ptxas feeds every UTCHMMA through an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop (~110 cycles per MMA; the
+    triplet kernel was 25 % slower).  The SASS of the built library must not contain that pattern."""
+    import shutil
+    import subprocess
+    from phoregen_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump) and not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    cur, counts = None, {}
+    for line in sass.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+            continue
+        if cur and any(k in cur for k in ("trip_tc_kernel", "bond_tc_kernel", "knn_tc_kernel", "gemm_tc_kernel")):
+            c = counts.setdefault(cur, [0, 0])
+            c[0] += "UTCHMMA" in line
+            c[1] += "R2UR.BROADCAST" in line
+    assert counts, "no tensor-core kernels found in the library"
+    assert all(c[0] > 0 for c in counts.values())                      # tcgen05.mma present in every one of them
+    assert sum(c[1] for c in counts.values()) == 0, {k: v for k, v in counts.items() if v[1]}
