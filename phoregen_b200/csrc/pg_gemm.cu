@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(256, 1) gemm_k128_kernel(GemmArgs a) {
 
 int pg_launch_gemm(const GemmArgs& a, int pro, cudaStream_t stream) {
     if (a.M <= 0) return PG_OK;
+    if (a.csplit > 0) { pg_set_error("fp32 GEMM: split outputs are a feature of the tcgen05 kernel"); return PG_EINVAL; }
     const size_t smem = (size_t)(TM * AS_LD + TK * TN) * sizeof(float);
     static bool configured = false;
     if (!configured) {

@@ -13,6 +13,7 @@ struct GemmArgs {
     const float* Wbf;                    // bf16 hi|lo split of the same weight, [2][ntiles*128][128] K-major (tcgen05 kernel)
     const float* bias;                   // [ntiles*128] or null
     float* C; long long ldc;
+    float* C2; long long ldc2; int csplit;   // optional second output (tcgen05 kernel): columns >= csplit go to C2[m * ldc2 + c - csplit]
     int ntiles;
     const float* resid; long long ldr;   // optional residual added in the epilogue (may alias C)
     int relu;

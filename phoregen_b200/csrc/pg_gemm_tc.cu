@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(GemmArgs a) {
                         float4 o = f4add(ld4(stg + r * 32 + ((cj ^ (r & 7)) << 2)), bb);
                         if (a.resid) o = f4add(o, ld4(a.resid + m * a.ldr + c0));
                         if (a.relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
-                        st4(a.C + m * a.ldc + c0, o);
+                        if (a.csplit > 0 && c0 >= a.csplit) st4(a.C2 + m * a.ldc2 + (c0 - a.csplit), o);
+                        else st4(a.C + m * a.ldc + c0, o);
                     }
                 }
                 __syncwarp();

@@ -47,6 +47,8 @@ std::vector<PgSlotDesc> build_slots() {
         add(L + "n2.wt", 128 * 1280); add(L + "n2.wt.bf", 128 * 1280); add(L + "n2.b", 1280);
         add(L + "e2.wt", 128 * 256); add(L + "e2.wt.bf", 128 * 256); add(L + "e2.b", 256);
         add(L + "lin.wt", 128 * 128); add(L + "lin.wt.bf", 128 * 128); add(L + "lin.b", 128);
+        // e2 of this layer and e1 of the next read the same h_bond: one GEMM with 896 output columns (tcgen05 path)
+        if (l + 1 < PG_NUM_LAYERS) { add(L + "e2e1.wt", 128 * 896); add(L + "e2e1.wt.bf", 128 * 896); }
         for (int s = 0; s < 5; s++) {
             std::string S = L + kSub[s] + ".";
             add(S + "lnq_g", 128); add(S + "lnq_b", 128); add(S + "w2q_t", 128 * 128); add(S + "w2q_t.bf", 128 * 128); add(S + "b2q", 128);
@@ -358,8 +360,9 @@ bool use_simt_gemm() {
 int gemm(PgPlan* p, cudaStream_t s, int pro, long long M, const float* A, long long lda, const W& w, const std::string& wname,
          long long ldw, const float* bias, float* C, long long ldc, int ntiles, const float* A2 = nullptr, long long lda2 = 0,
          const int* gidx = nullptr, const float* lng = nullptr, const float* lnb = nullptr, const float* resid = nullptr,
-         long long ldr = 0) {
+         long long ldr = 0, float* C2 = nullptr, long long ldc2 = 0, int csplit = 0) {
     GemmArgs a;
+    a.C2 = C2; a.ldc2 = ldc2; a.csplit = csplit;
     a.M = M; a.A = A; a.lda = lda; a.A2 = A2; a.lda2 = lda2; a.gidx = gidx; a.ln_g = lng; a.ln_b = lnb;
     a.Wt = w(wname); a.Wbf = w(wname + ".bf"); a.ldw = ldw; a.bias = bias; a.C = C; a.ldc = ldc; a.ntiles = ntiles;
     a.resid = resid; a.ldr = ldr; a.relu = 0;
@@ -407,7 +410,11 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
         PG_TRY(pg_launch_knn(p, p->x, phore_norm, 1, nullptr, p->comb, nullptr, s));
         // first Linear of every MLP, node and bond parts
         PG_TRY(gemm(p, s, PRO_PLAIN, N, p->h, 128, w, L + "n1.wt", N1_COLS, w(L + "n1.b"), p->nbuf, N1_COLS, N1_COLS / 128));
-        PG_TRY(gemm(p, s, PRO_PLAIN, Eb, p->hb, 128, w, L + "e1.wt", E1_COLS, w(L + "e1.b"), p->ebuf, E1_COLS, E1_COLS / 128));
+        // (from the second layer on the previous layer's merged e2 | e1 GEMM has already produced this layer's edge partials)
+        static const bool no_merge = getenv("PG_NO_MERGE_E") != nullptr;      // A/B switch: separate e2 / e1 GEMMs as with PG_GEMM=simt
+        const bool merged_e = !use_simt_gemm() && !no_merge;
+        if (l == 0 || !merged_e)
+            PG_TRY(gemm(p, s, PRO_PLAIN, Eb, p->hb, 128, w, L + "e1.wt", E1_COLS, w(L + "e1.b"), p->ebuf, E1_COLS, E1_COLS / 128));
         // queries: LN -> ReLU -> second Linear
         PG_TRY(gemm(p, s, PRO_LNRELU, N, p->nbuf + N1_NK_Q, N1_COLS, w, L + "nk.w2q_t", 128, w(L + "nk.b2q"), p->qn1, 128, 1,
                     nullptr, 0, nullptr, w(L + "nk.lnq_g"), w(L + "nk.lnq_b")));
@@ -460,7 +467,17 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
                     nullptr, nullptr, p->h, 128));
         // position update with the new h / h_bond and the old coordinates
         PG_TRY(gemm(p, s, PRO_PLAIN, N, p->h, 128, w, L + "n2.wt", N2_COLS, w(L + "n2.b"), p->nbuf, N2_COLS, N2_COLS / 128));
-        PG_TRY(gemm(p, s, PRO_PLAIN, Eb, p->hb, 128, w, L + "e2.wt", 256, w(L + "e2.b"), p->ebuf, 256, 2));
+        // bond partials of the position layer.  h_bond does not change between here and the next layer's first Linears, so
+        // with the tcgen05 GEMM one launch computes [e2 of this layer | e1 of the next] (896 columns, both biases are zero):
+        // the e2 part goes to the triplet work space (the P images are dead until the next trip_pr), the e1 part to ebuf.
+        float* e2buf = p->ebuf;
+        if (merged_e && l + 1 < PG_NUM_LAYERS) {
+            e2buf = p->pbuf2;
+            PG_TRY(gemm(p, s, PRO_PLAIN, Eb, p->hb, 128, w, L + "e2e1.wt", 896, nullptr, e2buf, 256, 7, nullptr, 0, nullptr, nullptr, nullptr,
+                        nullptr, 0, p->ebuf, E1_COLS, 256));
+        } else {
+            PG_TRY(gemm(p, s, PRO_PLAIN, Eb, p->hb, 128, w, L + "e2.wt", 256, w(L + "e2.b"), p->ebuf, 256, 2));
+        }
         PG_TRY(gemm(p, s, PRO_LNRELU, N, p->nbuf + N2_PK_Q, N2_COLS, w, L + "pk.w2q_t", 128, w(L + "pk.b2q"), p->qn1, 128, 1,
                     nullptr, 0, nullptr, w(L + "pk.lnq_g"), w(L + "pk.lnq_b")));
         PG_TRY(gemm(p, s, PRO_LNRELU, N, p->nbuf + N2_PB_Q, N2_COLS, w, L + "pb.w2q_t", 128, w(L + "pb.b2q"), p->qn2, 128, 1,
@@ -476,7 +493,7 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
             BondAttnArgs a;
             a.d = d; a.x = p->x;
             a.nc = NodeCols{p->nbuf, N2_COLS, N2_PB_DK, N2_PB_SK, N2_PB_DV, N2_PB_SV};
-            a.B = p->ebuf; a.ldb = 256; a.b_k = 0; a.b_v = 128;
+            a.B = e2buf; a.ldb = 256; a.b_k = 0; a.b_v = 128;
             a.q = p->qn2; a.w = attn_w(w, L + "pb.", false); a.out = p->dx2; a.maxr = maxr_bond;
             PG_TRY(launch_bond(p, a, w, L + "pb.", 1, s));
         }
@@ -627,6 +644,6 @@ extern "C" int pg_gemm_k128(int impl, int prologue, int64_t M, const float* d_a,
     GemmArgs a;
     a.M = M; a.A = d_a; a.lda = lda; a.A2 = d_a2; a.lda2 = lda2; a.gidx = d_gather; a.ln_g = d_ln_g; a.ln_b = d_ln_b;
     a.Wt = d_wt; a.Wbf = d_w_bf16_tiles; a.ldw = 128LL * ntiles128; a.bias = d_bias; a.C = d_c; a.ldc = ldc; a.ntiles = ntiles128;
-    a.resid = d_resid; a.ldr = ldr; a.relu = 0;
+    a.resid = d_resid; a.ldr = ldr; a.relu = 0; a.C2 = nullptr; a.ldc2 = 0; a.csplit = 0;
     return impl == 1 ? pg_launch_gemm(a, prologue, (cudaStream_t)stream) : pg_launch_gemm_tc(a, prologue, (cudaStream_t)stream);
 }

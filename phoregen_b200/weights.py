@@ -124,6 +124,9 @@ def pack_state_dict(sd):
                 out[S + "wrji"] = np.concatenate([k["W1"][:, 148:168].T, v["W1"][:, 148:168].T], 1)
                 out[S + "wa"] = np.concatenate([k["W1"][:, 168:181].T, v["W1"][:, 168:181].T], 1)
         _center_first_linears(out, L)
+    # h_bond does not change between the e2 GEMM of a layer and the e1 GEMM of the next: one 896-column weight for both
+    for l in range(n_layers - 1):
+        out[f"L{l}.e2e1.wt"] = np.concatenate([out[f"L{l}.e2.wt"], out[f"L{l + 1}.e1.wt"]], 1)
     return out
 
 
