@@ -111,7 +111,7 @@ int pg_launch_gemm(const GemmArgs& a, int pro, cudaStream_t stream) {
     switch (pro) {
         case PRO_PLAIN: gemm_k128_kernel<PRO_PLAIN><<<grid, 256, smem, stream>>>(a); break;
         case PRO_SUM2: gemm_k128_kernel<PRO_SUM2><<<grid, 256, smem, stream>>>(a); break;
-        case PRO_LNRELU: gemm_k128_kernel<PRO_LNRELU><<<grid, 256, smem, stream>>>(a); break;
+        case PRO_LNRELU: case PRO_LNRELU_MF: gemm_k128_kernel<PRO_LNRELU><<<grid, 256, smem, stream>>>(a); break;
         default: pg_set_error("bad gemm prologue"); return PG_EINVAL;
     }
     PG_LAUNCH_CHECK();

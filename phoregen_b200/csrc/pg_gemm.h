@@ -1,7 +1,9 @@
 #pragma once
 #include "pg_common.cuh"
 
-enum { PRO_PLAIN = 0, PRO_SUM2 = 1, PRO_LNRELU = 2 };
+// PRO_LNRELU_MF: LayerNorm + ReLU prologue for inputs that are already mean-free (first-Linear blocks centred at pack time,
+// weights._center_first_linears): only the second moment is reduced.  The fp32 kernel runs it as PRO_LNRELU.
+enum { PRO_PLAIN = 0, PRO_SUM2 = 1, PRO_LNRELU = 2, PRO_LNRELU_MF = 3 };
 
 struct GemmArgs {
     long long M;

@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(GemmArgs a) {
         // ================= A producer: fused prologue, bf16 hi/lo split, swizzled K-major layout =================
         const int pw = warp - PROD_WARP0;
         float4 g4 = make_float4(1, 1, 1, 1), b4 = make_float4(0, 0, 0, 0);
-        if (PRO == PRO_LNRELU) { g4 = ldg4(a.ln_g + lane * 4); b4 = ldg4(a.ln_b + lane * 4); }
+        constexpr bool LN = PRO == PRO_LNRELU || PRO == PRO_LNRELU_MF;
+    if (LN) { g4 = ldg4(a.ln_g + lane * 4); b4 = ldg4(a.ln_b + lane * 4); }
         long long it = 0;
         for (long long mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x, it++) {
             const int buf = it & 1;
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(GemmArgs a) {
                 float4 v[BATCH], w[BATCH];
                 // gather indices of the whole batch first: one round trip instead of one per row (the warp issues in order)
                 long long gi[BATCH];
-                if (PRO == PRO_LNRELU) {
+                if (LN) {
 #pragma unroll
                     for (int i = 0; i < BATCH; i++) {
                         const long long m = min(m0 + pw + (long long)(rb + i) * PROD_WARPS, a.M - 1);
@@ -134,26 +135,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(GemmArgs a) {
                     v[i] = ld4(a.A + mc * a.lda + lane * 4);
                     w[i] = make_float4(0, 0, 0, 0);
                     if (PRO == PRO_SUM2) w[i] = ld4(a.A2 + mc * a.lda2 + lane * 4);
-                    if (PRO == PRO_LNRELU && a.A2) w[i] = ld4(a.A2 + gi[i] * a.lda2 + lane * 4);
+                    if (LN && a.A2) w[i] = ld4(a.A2 + gi[i] * a.lda2 + lane * 4);
                     if (m >= a.M) { v[i] = make_float4(0, 0, 0, 0); w[i] = v[i]; }
                 }
                 if (PRO != PRO_PLAIN) {
 #pragma unroll
                     for (int i = 0; i < BATCH; i++) v[i] = f4add(v[i], w[i]);
                 }
-                if (PRO == PRO_LNRELU) {
+                if (LN) {
                     // LayerNorm + ReLU of the whole batch: the BATCH rows walk through the shuffle butterflies together (ILP)
                     float s1[BATCH], s2[BATCH];
+                    if (PRO != PRO_LNRELU_MF) {        // mean-free inputs skip the first butterfly and the subtraction
 #pragma unroll
-                    for (int i = 0; i < BATCH; i++) s1[i] = (v[i].x + v[i].y) + (v[i].z + v[i].w);
+                        for (int i = 0; i < BATCH; i++) s1[i] = (v[i].x + v[i].y) + (v[i].z + v[i].w);
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1)
+                        for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-                        for (int i = 0; i < BATCH; i++) s1[i] += __shfl_xor_sync(PG_FULL, s1[i], o);
+                            for (int i = 0; i < BATCH; i++) s1[i] += __shfl_xor_sync(PG_FULL, s1[i], o);
+                    }
 #pragma unroll
                     for (int i = 0; i < BATCH; i++) {
-                        const float mu = s1[i] * (1.0f / 128.0f);
-                        v[i] = make_float4(v[i].x - mu, v[i].y - mu, v[i].z - mu, v[i].w - mu);
+                        if (PRO != PRO_LNRELU_MF) {
+                            const float mu = s1[i] * (1.0f / 128.0f);
+                            v[i] = make_float4(v[i].x - mu, v[i].y - mu, v[i].z - mu, v[i].w - mu);
+                        }
                         s2[i] = fmaf(v[i].x, v[i].x, fmaf(v[i].y, v[i].y, fmaf(v[i].z, v[i].z, v[i].w * v[i].w)));
                     }
 #pragma unroll
@@ -249,6 +254,7 @@ int pg_launch_gemm_tc(const GemmArgs& a, int pro, cudaStream_t stream) {
         PG_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<PRO_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
         PG_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<PRO_SUM2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
         PG_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<PRO_LNRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        PG_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<PRO_LNRELU_MF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
         int dev = 0;
         PG_CUDA_CHECK(cudaGetDevice(&dev));
         PG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -261,6 +267,7 @@ int pg_launch_gemm_tc(const GemmArgs& a, int pro, cudaStream_t stream) {
         case PRO_PLAIN: gemm_tc_kernel<PRO_PLAIN><<<grid, NTHREADS, SMEM_TOTAL, stream>>>(b); break;
         case PRO_SUM2: gemm_tc_kernel<PRO_SUM2><<<grid, NTHREADS, SMEM_TOTAL, stream>>>(b); break;
         case PRO_LNRELU: gemm_tc_kernel<PRO_LNRELU><<<grid, NTHREADS, SMEM_TOTAL, stream>>>(b); break;
+        case PRO_LNRELU_MF: gemm_tc_kernel<PRO_LNRELU_MF><<<grid, NTHREADS, SMEM_TOTAL, stream>>>(b); break;
         default: pg_set_error("bad gemm prologue"); return PG_EINVAL;
     }
     PG_LAUNCH_CHECK();

@@ -416,11 +416,11 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
         if (l == 0 || !merged_e)
             PG_TRY(gemm(p, s, PRO_PLAIN, Eb, p->hb, 128, w, L + "e1.wt", E1_COLS, w(L + "e1.b"), p->ebuf, E1_COLS, E1_COLS / 128));
         // queries: LN -> ReLU -> second Linear
-        PG_TRY(gemm(p, s, PRO_LNRELU, N, p->nbuf + N1_NK_Q, N1_COLS, w, L + "nk.w2q_t", 128, w(L + "nk.b2q"), p->qn1, 128, 1,
+        PG_TRY(gemm(p, s, PRO_LNRELU_MF, N, p->nbuf + N1_NK_Q, N1_COLS, w, L + "nk.w2q_t", 128, w(L + "nk.b2q"), p->qn1, 128, 1,
                     nullptr, 0, nullptr, w(L + "nk.lnq_g"), w(L + "nk.lnq_b")));
-        PG_TRY(gemm(p, s, PRO_LNRELU, N, p->nbuf + N1_NB_Q, N1_COLS, w, L + "nb.w2q_t", 128, w(L + "nb.b2q"), p->qn2, 128, 1,
+        PG_TRY(gemm(p, s, PRO_LNRELU_MF, N, p->nbuf + N1_NB_Q, N1_COLS, w, L + "nb.w2q_t", 128, w(L + "nb.b2q"), p->qn2, 128, 1,
                     nullptr, 0, nullptr, w(L + "nb.lnq_g"), w(L + "nb.lnq_b")));
-        PG_TRY(gemm(p, s, PRO_LNRELU, Eb, p->ebuf + E1_TR_Q, E1_COLS, w, L + "tr.w2q_t", 128, w(L + "tr.b2q"), p->qt, 128, 1,
+        PG_TRY(gemm(p, s, PRO_LNRELU_MF, Eb, p->ebuf + E1_TR_Q, E1_COLS, w, L + "tr.w2q_t", 128, w(L + "tr.b2q"), p->qt, 128, 1,
                     p->nbuf + N1_TR_Q, N1_COLS, d.edst_node, w(L + "tr.lnq_g"), w(L + "tr.lnq_b")));
         {   // node update over the kNN graph
             KnnAttnArgs a;
@@ -478,9 +478,9 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
         } else {
             PG_TRY(gemm(p, s, PRO_PLAIN, Eb, p->hb, 128, w, L + "e2.wt", 256, w(L + "e2.b"), p->ebuf, 256, 2));
         }
-        PG_TRY(gemm(p, s, PRO_LNRELU, N, p->nbuf + N2_PK_Q, N2_COLS, w, L + "pk.w2q_t", 128, w(L + "pk.b2q"), p->qn1, 128, 1,
+        PG_TRY(gemm(p, s, PRO_LNRELU_MF, N, p->nbuf + N2_PK_Q, N2_COLS, w, L + "pk.w2q_t", 128, w(L + "pk.b2q"), p->qn1, 128, 1,
                     nullptr, 0, nullptr, w(L + "pk.lnq_g"), w(L + "pk.lnq_b")));
-        PG_TRY(gemm(p, s, PRO_LNRELU, N, p->nbuf + N2_PB_Q, N2_COLS, w, L + "pb.w2q_t", 128, w(L + "pb.b2q"), p->qn2, 128, 1,
+        PG_TRY(gemm(p, s, PRO_LNRELU_MF, N, p->nbuf + N2_PB_Q, N2_COLS, w, L + "pb.w2q_t", 128, w(L + "pb.b2q"), p->qn2, 128, 1,
                     nullptr, 0, nullptr, w(L + "pb.lnq_g"), w(L + "pb.lnq_b")));
         {
             KnnAttnArgs a;
