@@ -26,6 +26,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
 }
+// Parity wait for LONG waits (a producer that is a whole tile ahead): between polls the warp sleeps, so that it neither
+// takes issue slots nor shared-memory cycles (every try_wait is a shared-memory access) from the warps on the critical path.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "WAIT_LOOP:\n\t"
+        "nanosleep.u32 256;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
 // Parity wait with a watchdog, used by the auxiliary warps (MMA issuer, loaders, feature warps).  In every hand-off cycle
 // of these kernels one of them is among the waiters, so a protocol error ("mbarrier parity waits")
 // surfaces as a launch failure of this kernel instead of a GPU that never comes back.  The wall clock is read every 4096

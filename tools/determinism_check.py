@@ -11,7 +11,8 @@ G = int(sys.argv[1]) if len(sys.argv) > 1 else 320
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 model = PhoreDiff(MODEL_CONFIG, "zinc_300"); model.load_state_dict(random_state_dict(model, 0), strict=True); model = model.to(dev).eval()
-b = synthetic_batch(2039, G, n_atoms=(26, 33))
+lo, hi = (int(x) for x in os.environ.get("DC_ATOMS", "26,33").split(","))      # DC_ATOMS=36,48 exercises the chunked (n > 33) kernels
+b = synthetic_batch(2039, G, n_atoms=(lo, hi))
 ref = None; bad = 0
 for r in range(reps):
     use_graph = bool(int(os.environ.get("DC_GRAPH", "0"))) and (r % 2 == 1)
