@@ -111,20 +111,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(GemmArgs a) {
                     st4(stg + lane * 32 + ((q ^ (lane & 7)) << 2), make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
                                                                              __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3])));
                 __syncwarp();
+                // The output buffer, its row pitch and the fused-epilogue flavour are per-block facts: decide them once, then a
+                // row costs LDS + 4 FADD + STG + one pointer step.  (With the decisions inside the row loop the epilogue warps
+                // executed 53 instructions per 512-byte store and were the limiter of the wide edge GEMMs: ncu, source view.)
+                const bool second = a.csplit > 0 && c0 >= a.csplit;
+                const long long ldo = second ? a.ldc2 : a.ldc;
+                float* prow = (second ? a.C2 + (c0 - a.csplit) : a.C + c0) + (mw + rsub) * ldo;
+                const int rows_left = (int)min((long long)32, a.M - mw) - rsub;        // rows rr * 4 + rsub < 32 of this warp that exist
+                const float* srow = stg + rsub * 32;
+                if (!a.resid && !a.relu) {
+                    float4 o[8];
 #pragma unroll
-                for (int rr = 0; rr < 8; rr++) {
-                    const int r = rr * 4 + rsub;
-                    const long long m = mw + r;
-                    if (m < a.M) {
-                        float4 o = f4add(ld4(stg + r * 32 + ((cj ^ (r & 7)) << 2)), bb);
-                        if (a.resid) o = f4add(o, ld4(a.resid + m * a.ldr + c0));
-                        if (a.relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
-#if defined(PG_GEMM_EXP) && (PG_GEMM_EXP & 2)      // timing experiment (wrong results): no output stores
-                        if (o.x == 1.2345e38f)
-#endif
-                        {
-                        if (a.csplit > 0 && c0 >= a.csplit) st4(a.C2 + m * a.ldc2 + (c0 - a.csplit), o);
-                        else st4(a.C + m * a.ldc + c0, o);
+                    for (int rr = 0; rr < 8; rr++) o[rr] = ld4(srow + rr * 128 + ((cj ^ ((rr * 4 + rsub) & 7)) << 2));     // all eight reads in flight
+#pragma unroll
+                    for (int rr = 0; rr < 8; rr++)
+                        if (rr * 4 < rows_left) st4(prow + (long long)(rr * 4) * ldo, f4add(o[rr], bb));
+                } else {
+#pragma unroll
+                    for (int rr = 0; rr < 8; rr++) {
+                        const int r = rr * 4 + rsub;
+                        if (rr * 4 < rows_left) {
+                            float4 o = f4add(ld4(srow + rr * 128 + ((cj ^ (r & 7)) << 2)), bb);
+                            if (a.resid) o = f4add(o, ld4(a.resid + (mw + r) * a.ldr + c0));
+                            if (a.relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+                            st4(prow + (long long)(rr * 4) * ldo, o);
                         }
                     }
                 }
