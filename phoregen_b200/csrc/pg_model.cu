@@ -293,10 +293,13 @@ bool use_tc_trip(const PlanDev& d) {
 // Precision of the key MLPs' second Linear (its output only feeds softmax logits).  Default bf16x3 everywhere.  Opt-in
 // single-pass fp16 (measured, configs[1]): PG_KEY=trip16 (triplet kernel only) 71.8 -> 67.1 ms/step, model outputs at
 // 0.50 x tolerance but the internal h_bond at 1.07 x; PG_KEY=fp16 (all three attention kernels) 65.4 ms/step, outputs at
-// 0.72 x, internal h / h_bond at 1.36 x / 1.20 x.  Not the default because of the internal-state bar.
-int key_mode() {      // 0 bf16x3 everywhere, 2 fp16 everywhere, 3 fp16 in the triplet kernel only
+// 0.72 x, internal h / h_bond at 1.36 x / 1.20 x.  PG_KEY=trip16x2 (triplet kernel: fp16 hi/lo ACTIVATIONS against the single
+// fp16 weight image, 16 MMAs instead of 24): 65.2 -> 61.8 ms/step in same-box A/B, outputs at <= 0.42 x, internal h_bond
+// at 1.11 x -- the fp16 rounding of the weights alone costs as much as that of the activations.  None is the default
+// because of the internal-state bar.
+int key_mode() {      // 0 bf16x3 everywhere, 2 fp16 everywhere, 3 fp16 in the triplet kernel only, 4 fp16 hi/lo activations x fp16 weights in the triplet kernel
     static int v = -1;
-    if (v < 0) { const char* e = getenv("PG_KEY"); v = !e ? 0 : !strcmp(e, "fp16") ? 2 : !strcmp(e, "trip16") ? 3 : 0; }
+    if (v < 0) { const char* e = getenv("PG_KEY"); v = !e ? 0 : !strcmp(e, "fp16") ? 2 : !strcmp(e, "trip16") ? 3 : !strcmp(e, "trip16x2") ? 4 : 0; }
     return v;
 }
 
@@ -452,7 +455,7 @@ int run_denoiser(const PgModel* m, PgPlan* p, const float* phore_norm, cudaStrea
                 t.w2k_bf = (const uint16_t*)w(L + "tr.w2k.bf"); t.w2v_bf = (const uint16_t*)w(L + "tr.w2v.bf");
                 t.w2k_h = (const uint16_t*)w(L + "tr.w2k.h");
                 t.wa_bf = (const uint16_t*)w(L + "tr.wa.bf");
-                { static int fl = -1; if (fl < 0) { const char* e = getenv("PG_TRIP_FLAGS"); fl = e ? atoi(e) : 0; } t.flags = fl | (key_mode() >= 2 ? 0 : 2); }       // bit 1 set = bf16x3 key MLP
+                { static int fl = -1; if (fl < 0) { const char* e = getenv("PG_TRIP_FLAGS"); fl = e ? atoi(e) : 0; } t.flags = fl | (key_mode() >= 2 ? 0 : 2) | (key_mode() == 4 ? 4 : 0); }       // bit 1 set = bf16x3 key MLP
                 t.lnk_g = a.w.lnk_g; t.lnk_b = a.w.lnk_b; t.lnv_g = a.w.lnv_g; t.lnv_b = a.w.lnv_b; t.b2k = a.w.b2k; t.b2v = a.w.b2v;
                 t.lnk_bf = a.w.lnk_bf; t.lnv_bf = a.w.lnv_bf; t.fold = a.w.fold;
                 t.hb = p->hb; t.maxn = d.max_n;

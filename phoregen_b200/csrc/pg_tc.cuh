@@ -274,6 +274,16 @@ __device__ __forceinline__ void split_pair_relu(float2 y, uint32_t& hi, uint32_t
     const float2 d = *reinterpret_cast<float2*>(&r);
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d.y), "f"(d.x));
 }
+// The same with an fp16 pair: hi = f16_rz(max(y, 0)), lo = f16_rn(max(y - hi, 0)); |y - hi - lo| <= 2^-22 |y| in the normal range.
+__device__ __forceinline__ void split_pair_relu_f16(float2 y, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(y.y), "f"(y.x));
+    float2 hf;
+    asm("{ .reg .b16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h; }" : "=f"(hf.x), "=f"(hf.y) : "r"(hi));
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&y)), "l"(*reinterpret_cast<unsigned long long*>(&hf)));
+    const float2 d = *reinterpret_cast<float2*>(&r);
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d.y), "f"(d.x));
+}
 // Warp-wide reductions on the REDUX unit (one instruction instead of a 5-round shuffle butterfly).
 __device__ __forceinline__ float warp_max_redux(float x) {        // sm_100a: redux.sync on f32
     float r;

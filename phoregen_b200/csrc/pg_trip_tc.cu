@@ -174,8 +174,12 @@ __device__ __forceinline__ void write_features(const float* xs, const TileIter& 
 //   bar (worst 0.50 x tolerance against 0.41), but the denoiser's internal h_bond reaches 1.07 x tolerance (one element
 //   in 66 k; the per-row rounding of the activations does not cancel in the softmax, a hi/lo weight pair does not help),
 //   so it is not the default.  A single-pass VALUE path misses the bar by 1.5x (measured) and is not offered.
-template <bool MULTI, bool KF16>
+//   KMODE 2 (PG_KEY=trip16x2) = the activations as an fp16 hi/lo pair (truncated hi, rounded remainder: ~2^-22) against the
+//   single fp16 weight image: 16 MMAs.  The activation rounding was what cost KMODE 1 the internal-state bar; the weight
+//   rounding is common to all rows of a segment's softmax.
+template <bool MULTI, int KMODE>
 __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
+    constexpr bool KF16 = KMODE != 0, KX2 = KMODE == 2;
     extern __shared__ uint8_t smem_raw[];
     // offset arithmetic on the __shared__ array (not a uintptr_t round trip) so the compiler keeps emitting LDS/STS
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -325,6 +329,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
                     const uint64_t bd = tc::umma_desc_sw128(sW_u32 + (ks >> 2) * 16384 + (ks & 3) * 32);
                     tc::umma_bf16_ts_w(dcol, hid + ks * 8, bd, idesc16, ks > 0);
                 }
+                if (KX2) {
+#pragma unroll
+                    for (int ks = 0; ks < 8; ks++) {
+                        const uint64_t bd = tc::umma_desc_sw128(sW_u32 + (ks >> 2) * 16384 + (ks & 3) * 32);
+                        tc::umma_bf16_ts_w(dcol, hid + 64 + ks * 8, bd, idesc16, 1);
+                    }
+                }
                 tc::umma_commit_w(bar);
                 return;
             }
@@ -383,8 +394,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
                 tc::mbar_arrive(featbar);
                 tc::mbar_wait_wd(&bars[B_OUTK], ph);      // hid_k(t) has been consumed: its columns take pre_k(t+1)
+                TRACE(2, 9);
                 tc::mbar_wait_wd(featbar, ((tcount + 1) >> 1) & 1);
+                TRACE(2, 10);
                 tc::mbar_wait_wd(&bars[B_RK], prk); prk ^= 1;
+                TRACE(2, 11);
                 if (newu) { tc::mbar_wait_wd(&bars[B_PSK], psk); psk ^= 1; }
                 tc::tc_fence_after();
                 TRACE(2, 3);
@@ -400,7 +414,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             TRACE(2, 6);
             if (nx.valid) {
                 tc::mbar_wait_wd(&bars[B_OUTV], ph);
+                TRACE(2, 12);
                 tc::mbar_wait_wd(&bars[B_RV], prv); prv ^= 1;
+                TRACE(2, 13);
                 if (newu) { tc::mbar_wait_wd(&bars[B_PSV], psv); psv ^= 1; }
                 tc::tc_fence_after();
                 TRACE(2, 7);
@@ -501,10 +517,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
                         y0 = tc::fma2(tc::mul2(x2[i], rs2), make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
                         y1 = tc::fma2(tc::mul2(x2[i + 1], rs2), make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
                     }
-                    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi[i]) : "f"(y0.y), "f"(y0.x));
-                    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi[i + 1]) : "f"(y1.y), "f"(y1.x));
+                    if (KX2) {
+                        tc::split_pair_relu_f16(y0, hi[i], lo[i]);
+                        tc::split_pair_relu_f16(y1, hi[i + 1], lo[i + 1]);
+                    } else {
+                        asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi[i]) : "f"(y0.y), "f"(y0.x));
+                        asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi[i + 1]) : "f"(y1.y), "f"(y1.x));
+                    }
                 }
                 tc::tmem_st16(hid + lane_base + cq * 16, hi);
+                if (KX2) tc::tmem_st16(hid + lane_base + 64 + cq * 16, lo);
                 tc::tmem_st_wait();
                 tc::tc_fence_before();
                 tc::mbar_arrive(&bars[B_HIDK]);
@@ -801,10 +823,12 @@ int pg_launch_trip_tc(const TripTcArgs& a, int num_sms, cudaStream_t s) {
     if (smem > 227 * 1024) { pg_set_error("trip_tc: shared memory budget exceeded"); return PG_ELIMIT; }
     static size_t cur = 0;
     if (smem > cur) {
-        PG_CUDA_CHECK(cudaFuncSetAttribute(trip_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PG_CUDA_CHECK(cudaFuncSetAttribute(trip_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PG_CUDA_CHECK(cudaFuncSetAttribute(trip_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PG_CUDA_CHECK(cudaFuncSetAttribute(trip_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PG_CUDA_CHECK(cudaFuncSetAttribute(trip_tc_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PG_CUDA_CHECK(cudaFuncSetAttribute(trip_tc_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PG_CUDA_CHECK(cudaFuncSetAttribute(trip_tc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PG_CUDA_CHECK(cudaFuncSetAttribute(trip_tc_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PG_CUDA_CHECK(cudaFuncSetAttribute(trip_tc_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PG_CUDA_CHECK(cudaFuncSetAttribute(trip_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cur = smem;
     }
     const unsigned grid = (unsigned)std::min<long long>(a.d.Nl, num_sms);
@@ -813,11 +837,14 @@ int pg_launch_trip_tc(const TripTcArgs& a, int num_sms, cudaStream_t s) {
     // launches both; each walks the unit list and skips the other's molecules.
     const bool have_single = a.d.min_n <= PG_TRIP_TC_SINGLE_CHUNK_ATOMS, have_multi = a.maxn > PG_TRIP_TC_SINGLE_CHUNK_ATOMS;
     if (a.flags & 2) {
-        if (have_single) trip_tc_kernel<false, false><<<grid, NTHREADS, smem, s>>>(a);
-        if (have_multi) trip_tc_kernel<true, false><<<grid, NTHREADS, smem, s>>>(a);
+        if (have_single) trip_tc_kernel<false, 0><<<grid, NTHREADS, smem, s>>>(a);
+        if (have_multi) trip_tc_kernel<true, 0><<<grid, NTHREADS, smem, s>>>(a);
+    } else if (a.flags & 4) {
+        if (have_single) trip_tc_kernel<false, 2><<<grid, NTHREADS, smem, s>>>(a);
+        if (have_multi) trip_tc_kernel<true, 2><<<grid, NTHREADS, smem, s>>>(a);
     } else {
-        if (have_single) trip_tc_kernel<false, true><<<grid, NTHREADS, smem, s>>>(a);
-        if (have_multi) trip_tc_kernel<true, true><<<grid, NTHREADS, smem, s>>>(a);
+        if (have_single) trip_tc_kernel<false, 1><<<grid, NTHREADS, smem, s>>>(a);
+        if (have_multi) trip_tc_kernel<true, 1><<<grid, NTHREADS, smem, s>>>(a);
     }
     PG_LAUNCH_CHECK();
     return PG_OK;

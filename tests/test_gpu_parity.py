@@ -493,11 +493,13 @@ torch.save([o.cpu() for o in out[:3]], sys.argv[2])
 
 def test_tensor_core_kernels_match_fp32_kernels(tmp_path):
     """The same forward pass with every tcgen05 kernel switched off (PG_GEMM=simt, PG_TRIP / PG_BOND / PG_KNN_ATTN=fp32: the
-    fp32 FFMA kernels that also serve out-of-range shapes) must agree with the default path and with the reference golden."""
+    fp32 FFMA kernels that also serve out-of-range shapes) must agree with the default path and with the reference golden;
+    the opt-in PG_KEY=trip16x2 key path must keep the model outputs inside the bar."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = {}
-    for name, env in (("tc", {}), ("fp32", {"PG_GEMM": "simt", "PG_TRIP": "fp32", "PG_BOND": "fp32", "PG_KNN_ATTN": "fp32"})):
+    for name, env in (("tc", {}), ("fp32", {"PG_GEMM": "simt", "PG_TRIP": "fp32", "PG_BOND": "fp32", "PG_KNN_ATTN": "fp32"}),
+                      ("key16x2", {"PG_KEY": "trip16x2"})):
         path = str(tmp_path / f"{name}.pt")
         subprocess.run([sys.executable, "-c", _AB_SCRIPT, root, path], check=True, env={**os.environ, **env}, timeout=600)
         outs[name] = torch.load(path)
@@ -505,6 +507,9 @@ def test_tensor_core_kernels_match_fp32_kernels(tmp_path):
     for k, what in enumerate(("pred_node", "pred_pos", "pred_edge")):
         assert_close(outs["tc"][k], outs["fp32"][k], f"tcgen05 vs fp32 kernels: {what}")
         assert_close(outs["fp32"][k], f[what], f"fp32 kernels vs reference golden: {what}")
+        # opt-in key path of the triplet kernel (fp16 hi/lo activations x fp16 weights, 16 MMAs instead of 24): the model
+        # outputs stay inside the bar (the denoiser's internal h_bond does not, which is why it is not the default)
+        assert_close(outs["key16x2"][k], f[what], f"PG_KEY=trip16x2 vs reference golden: {what}")
 
 
 # ---------------------------------------------------------------- liveness of the persistent, mbarrier-pipelined kernels

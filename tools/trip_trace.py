@@ -21,5 +21,5 @@ names = {0: "K", 1: "V", 2: "M"}
 for tile in range(8, 20):
     for role in (2, 0, 1):
         row = t[role, tile]
-        print(f"tile {tile} {names[role]}: " + " ".join(f"{(int(v) - int(base)) if v else -1:>7d}" for v in row[:12]))
+        print(f"tile {tile} {names[role]}: " + " ".join(f"{(int(v) - int(base)) if v else -1:>7d}" for v in row[:14]))
     print()
