@@ -64,7 +64,8 @@ constexpr int SM_STAT = 128 * 8 * 4;       // LayerNorm partial second moments [
 constexpr int SM_FIXED = SM_W + SM_WA + SM_P + SM_ONE + SM_FEAT + SM_Q + SM_STAT + 6 * 128 * 4 /*ln + b2*/ + 256 /*barriers*/;
 constexpr float kInvSqrtD = 0.35355339059327373f;
 constexpr int ROW_WARPS = 16;               // 4 warps per TMEM lane quarter, each owning a 32-channel slice of the row
-constexpr int MMA_WARP = ROW_WARPS;         // MMA issue + q/R/P loaders; the 3 warps after it compute angular features
+constexpr int MMA_WARP = ROW_WARPS;         // MMA issue; then the loader warp (q / R / P rows) and 2 warps that compute angular features
+constexpr int LOAD_WARP = MMA_WARP + 1;
 constexpr int NTHREADS = (ROW_WARPS + 4) * 32;
 constexpr int ROW_THREADS = ROW_WARPS * 32;
 constexpr int R_ROW0 = 11;                  // angle slab: K columns 0..10 features, 11..14 segment indicator, 15 zero
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
 
     if (warp == MMA_WARP) tc::tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
-        tc::mbar_init(&bars[B_FEAT0], 96 + 32); tc::mbar_init(&bars[B_FEAT1], 96 + 32);
+        tc::mbar_init(&bars[B_FEAT0], 64 + 32); tc::mbar_init(&bars[B_FEAT1], 64 + 32);     // 64 feature threads + the loader warp (query rows)
         tc::mbar_init(&bars[B_PREK], 1); tc::mbar_init(&bars[B_PREV0], 1); tc::mbar_init(&bars[B_PREV1], 1);
         tc::mbar_init(&bars[B_HIDK], ROW_THREADS); tc::mbar_init(&bars[B_HIDV], ROW_THREADS);
         tc::mbar_init(&bars[B_OUTK], 1); tc::mbar_init(&bars[B_OUTV], 1);
@@ -261,47 +262,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
         constexpr uint32_t idesc_bmn = idesc | (1u << 16);          // B operand MN-major (staged P rows, angle slab)
         const uint32_t sW_u32 = tc::smem_u32(sW), sWa_u32 = tc::smem_u32(sWa), sFeat_u32 = tc::smem_u32(sFeat);
         const uint32_t sP_u32 = tc::smem_u32(sP), sOne_u32 = tc::smem_u32(sOne);
-        const size_t mlp_stride = (size_t)a.d.Eb * 128;           // floats per MLP in the P and R images (512 B per edge)
-        auto load_q = [&](const TileIter& t, int buf) {
-            const uint32_t q = tc::smem_u32(sQ0 + buf * (SM_Q / 8));
-#pragma unroll
-            for (int s4 = 0; s4 < 4; s4++) {
-                const Seg sg = seg_of(t, s4);
-                const float* qs = a.q + (size_t)sg.eji * 128 + lane * 4;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(q + (s4 * 128 + lane * 4) * 4), "l"(qs) : "memory");
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        // P rows of the edges k -> j of a unit (or of one 32-row chunk of it): four contiguous pieces per MLP, (hi|lo) x
-        // (channel half), each nr x 128 B.  The key and value images travel separately (one mbarrier transaction each): an
-        // image is dead as soon as the first-Linear MMAs of the unit's last tile have completed, which the issuer knows
-        // when the row warps hand back that tile's activations (HIDK / HIDV).
-        auto load_ps = [&](const TileIter& t, int mlp) {
-            uint64_t* bar = &bars[mlp == 0 ? B_PSK : B_PSV];
-            const int r0 = t.chunk * 32, nr = min(32, t.n - 1 - r0);
-            if (lane == 0) {
-                tc::mbar_arrive_expect_tx(bar, (uint32_t)nr * 512u);
-                const uint8_t* src = (const uint8_t*)(a.P + (size_t)mlp * mlp_stride) + (size_t)(t.eoff + (long long)t.jl * (t.n - 1)) * 512;
-#pragma unroll
-                for (int b = 0; b < 4; b++)
-                    tc::bulk_copy_g2s(sP + (mlp * 4 + b) * 4096, src + ((size_t)b * (t.n - 1) + r0) * 128, (uint32_t)nr * 128u, bar);
-            }
-            __syncwarp();
-        };
-        // R rows of the tile's 4 segments (j -> i), contiguous in the source-major R image -> rows 11..14 of the angle slab
-        auto load_r = [&](const TileIter& t, int mlp) {
-            uint64_t* bar = &bars[mlp == 0 ? B_RK : B_RV];
-            const int s0 = t.grp * 4, nr = min(4, t.n - 1 - s0);
-            if (lane == 0) {
-                tc::mbar_arrive_expect_tx(bar, (uint32_t)nr * 512u);
-                const uint8_t* src = (const uint8_t*)(a.R + (size_t)mlp * mlp_stride) + (size_t)(t.eoff + (long long)t.jl * (t.n - 1)) * 512;
-#pragma unroll
-                for (int b = 0; b < 4; b++)
-                    tc::bulk_copy_g2s(sWa + (mlp * 4 + b) * 2048 + 1024 + (R_ROW0 - 8) * 128, src + ((size_t)b * (t.n - 1) + s0) * 128,
-                                      (uint32_t)nr * 128u, bar);
-            }
-            __syncwarp();
-        };
         // first Linear of one MLP for tile `tl` (feature operand buffer tl & 1) -> pre-activation columns `dcol`:
         // [angle | indicator] x [Wa ; R] in bf16x3, then one-hot x staged P rows (hi and lo images), `nslab` K16 slabs
         // (warp-collective issue: all lanes run the descriptor arithmetic on the uniform datapath, one elected lane issues)
@@ -354,13 +314,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             tc::umma_commit_w(bar);
         };
         uint32_t psk = 0, psv = 0, prk = 0, prv = 0;               // phases of the P / R transaction barriers
-        load_ps(it, 0);
-        load_ps(it, 1);
-        load_r(it, 0);
-        load_r(it, 1);
-        load_q(it, 0);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        tc::mbar_arrive(&bars[B_FEAT0]);
         tc::mbar_wait_wd(&bars[B_FEAT0], 0);
         tc::mbar_wait_wd(&bars[B_PSK], psk); psk ^= 1;
         tc::mbar_wait_wd(&bars[B_RK], prk); prk ^= 1;
@@ -386,13 +339,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             tc::mbar_wait_wd(&bars[B_HIDK], ph);
             TRACE(2, 1);
             tc::tc_fence_after();
-            if (nx.valid) { load_q(nx, (tcount + 1) & 1); load_r(nx, 0); }
-            if (newu) load_ps(nx, 0);
             w2_mma(0, hidK, preK, &bars[B_OUTK]);
             TRACE(2, 2);
             if (nx.valid) {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                tc::mbar_arrive(featbar);
                 tc::mbar_wait_wd(&bars[B_OUTK], ph);      // hid_k(t) has been consumed: its columns take pre_k(t+1)
                 TRACE(2, 9);
                 tc::mbar_wait_wd(featbar, ((tcount + 1) >> 1) & 1);
@@ -408,8 +357,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             tc::mbar_wait_wd(&bars[B_HIDV], ph);
             TRACE(2, 5);
             tc::tc_fence_after();
-            if (nx.valid) load_r(nx, 1);
-            if (newu) load_ps(nx, 1);
             w2_mma(1, hidV, preV, &bars[B_OUTV]);
             TRACE(2, 6);
             if (nx.valid) {
@@ -425,19 +372,92 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             TRACE(2, 8);
             it = nx; tcount++;
         }
+      } else if (warp == LOAD_WARP) {
+        // ================= loader: query rows via cp.async, P / R rows via bulk copies =================
+        // A warp of its own: on the MMA warp these requests (several hundred cycles of dependent address arithmetic per tile)
+        // either delayed the MMA issue (requests first: tensor pipe idle meanwhile) or were delayed by it (MMAs first: the
+        // issue blocks ~1500 cycles on the full MMA queue, 37.9 -> 40.4 ms/step).  The buffers of tile t+1 are free when the
+        // row warps hand back tile t's activations (HIDK / HIDV: the first-Linear MMAs of tile t have completed); the next
+        // completion of either barrier needs the rows requested here, so the parity waits cannot be overtaken.
+        const size_t mlp_stride = (size_t)a.d.Eb * 128;           // floats per MLP in the P and R images (512 B per edge)
+        auto load_q = [&](const TileIter& t, int buf) {
+            const uint32_t q = tc::smem_u32(sQ0 + buf * (SM_Q / 8));
+#pragma unroll
+            for (int s4 = 0; s4 < 4; s4++) {
+                const Seg sg = seg_of(t, s4);
+                const float* qs = a.q + (size_t)sg.eji * 128 + lane * 4;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(q + (s4 * 128 + lane * 4) * 4), "l"(qs) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        // P rows of the edges k -> j of a unit (or of one 32-row chunk of it): four contiguous pieces per MLP, (hi|lo) x
+        // (channel half), each nr x 128 B.  The key and value images travel separately (one mbarrier transaction each): an
+        // image is dead as soon as the first-Linear MMAs of the unit's last tile have completed, which the issuer knows
+        // when the row warps hand back that tile's activations (HIDK / HIDV).
+        auto load_ps = [&](const TileIter& t, int mlp) {
+            uint64_t* bar = &bars[mlp == 0 ? B_PSK : B_PSV];
+            const int r0 = t.chunk * 32, nr = min(32, t.n - 1 - r0);
+            if (lane == 0) {
+                tc::mbar_arrive_expect_tx(bar, (uint32_t)nr * 512u);
+                const uint8_t* src = (const uint8_t*)(a.P + (size_t)mlp * mlp_stride) + (size_t)(t.eoff + (long long)t.jl * (t.n - 1)) * 512;
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                    tc::bulk_copy_g2s(sP + (mlp * 4 + b) * 4096, src + ((size_t)b * (t.n - 1) + r0) * 128, (uint32_t)nr * 128u, bar);
+            }
+            __syncwarp();
+        };
+        // R rows of the tile's 4 segments (j -> i), contiguous in the source-major R image -> rows 11..14 of the angle slab
+        auto load_r = [&](const TileIter& t, int mlp) {
+            uint64_t* bar = &bars[mlp == 0 ? B_RK : B_RV];
+            const int s0 = t.grp * 4, nr = min(4, t.n - 1 - s0);
+            if (lane == 0) {
+                tc::mbar_arrive_expect_tx(bar, (uint32_t)nr * 512u);
+                const uint8_t* src = (const uint8_t*)(a.R + (size_t)mlp * mlp_stride) + (size_t)(t.eoff + (long long)t.jl * (t.n - 1)) * 512;
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                    tc::bulk_copy_g2s(sWa + (mlp * 4 + b) * 2048 + 1024 + (R_ROW0 - 8) * 128, src + ((size_t)b * (t.n - 1) + s0) * 128,
+                                      (uint32_t)nr * 128u, bar);
+            }
+            __syncwarp();
+        };
+        load_ps(it, 0);
+        load_ps(it, 1);
+        load_r(it, 0);
+        load_r(it, 1);
+        load_q(it, 0);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        tc::mbar_arrive(&bars[B_FEAT0]);
+        int tcount = 0;
+        while (it.valid) {
+            const uint32_t ph = tcount & 1;
+            TileIter nx = it;
+            iter_next<MULTI>(d, nx);
+            const bool newu = nx.valid && nx.stage != it.stage;     // the staged P rows change with the next tile
+            tc::mbar_wait_wd(&bars[B_HIDK], ph);                    // the P_k image, the R_k rows and query buffer (t+1)&1 are free
+            if (nx.valid) { load_q(nx, (tcount + 1) & 1); load_r(nx, 0); }
+            if (newu) load_ps(nx, 0);
+            if (nx.valid) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                tc::mbar_arrive(&bars[(tcount + 1) & 1 ? B_FEAT1 : B_FEAT0]);
+            }
+            tc::mbar_wait_wd(&bars[B_HIDV], ph);
+            if (nx.valid) load_r(nx, 1);
+            if (newu) load_ps(nx, 1);
+            it = nx; tcount++;
+        }
       } else {
         // ================= feature warps: angular features, up to two tiles ahead (double-buffered operand) =================
-        // 96 threads cover the 128 rows of a tile in two passes; they also stage the next unit's coordinates.
-        const int ft = tid - (MMA_WARP + 1) * 32;       // 0..95
+        // 64 threads cover the 128 rows of a tile in two passes; they also stage the next unit's coordinates.
+        const int ft = tid - (LOAD_WARP + 1) * 32;       // 0..63
         auto stage_x = [&](const TileIter& t, int b) {
-            for (int i = ft; i < t.n; i += 96) {
+            for (int i = ft; i < t.n; i += 64) {
                 const float* src = a.x + (size_t)(t.ctx0 + i) * 3;
                 st4(sX + ((size_t)b * a.maxn + i) * 4, make_float4(src[0], src[1], src[2], 0.f));
             }
-            asm volatile("bar.sync 2, 96;" ::: "memory");
+            asm volatile("bar.sync 2, 64;" ::: "memory");
         };
         auto features = [&](const TileIter& t, int b, int tl) {
-            for (int r = ft; r < 128; r += 96) write_features(sX + (size_t)b * a.maxn * 4, t, r >> 5, r & 31, sFeat + (tl & 1) * SM_FEAT1);
+            for (int r = ft; r < 128; r += 64) write_features(sX + (size_t)b * a.maxn * 4, t, r >> 5, r & 31, sFeat + (tl & 1) * SM_FEAT1);
             tc::fence_proxy_async_smem();
             tc::mbar_arrive(&bars[tl & 1 ? B_FEAT1 : B_FEAT0]);
         };
@@ -570,10 +590,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
                 const float2 pr = tc::mul2(make_float2(al[i >> 3], al[i >> 3]), make_float2(__uint_as_float(vu[i]), __uint_as_float(vu[i + 1])));
                 v[i] = pr.x; v[i + 1] = pr.y;
             }
+#if defined(PG_TRIP_EXP) && (PG_TRIP_EXP & 1)
+            float o = 0.f;                                   // knock-out experiment: no cross-lane reduction (wrong results)
+#pragma unroll
+            for (int i = 0; i < 32; i++) o += v[i];
+#else
             const float o = transpose_reduce32(v, lane);
+#endif
             const int c = cq * 32 + lane;
             if (!MULTI) {
+#if defined(PG_TRIP_EXP) && (PG_TRIP_EXP & 4)
+                if (prev_valid && o == 123.456f) a.hb[(size_t)prev_eji * 128 + c] += o + sB2[128 + c];   // knock-out: no h_bond update
+#else
                 if (prev_valid) a.hb[(size_t)prev_eji * 128 + c] += o + sB2[128 + c];     // sum(alpha) = 1; residual (uni_denoiser.py:285)
+#endif
             } else {
                 // channel c belongs to head cq*4 + (lane >> 3): rescale the running output by that head's factor, add the
                 // chunk, and divide by the running sum once the segment's last chunk is in
@@ -652,6 +682,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
                         lrun[h] = first ? ls : fmaf(lrun[h], sc, ls);
                         mrun[h] = mnew; psc[h] = sc;
                     }
+#if defined(PG_TRIP_EXP) && (PG_TRIP_EXP & 2)
+                } else if (true) {                            // knock-out experiment: no reductions (wrong results)
+#pragma unroll
+                    for (int h = 0; h < 4; h++) al[h] = rowvalid ? tc::ex2_approx(al[h] * 1e-3f) * 0.03f : 0.f;
+#endif
                 } else if (!(a.flags & 1)) {
                     // segment softmax across the 32 lanes: max and sum on the REDUX unit
 #pragma unroll
