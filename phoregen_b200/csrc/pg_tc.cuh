@@ -138,6 +138,17 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
     v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 16 TMEM lanes x 32 columns in the MMA-fragment shape: register j of thread t holds
+//   lane (taddr.lane + 8 ((j >> 1) & 1) + t / 4), column (taddr.col + 8 (j >> 2) + 2 (t % 4) + (j & 1))
+// (checked on the device by tools/micro/tmem_transpose_probe.cu).  No trailing wait.
+__device__ __forceinline__ void tmem_ld_16x256b_x4_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 
 // thread t of the warp writes 32 consecutive 32-bit columns [col, col+32) of TMEM lane (lane base + t)
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -160,6 +171,49 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Column sums of a 32 x 32 block held one row per lane (p[c] = this lane's row, column c): the block goes through 32 TMEM
+// columns of the warp's own lanes (taddr: lane base + first column; the columns are scratch) and comes back in the
+// 16x256b fragment shape, where a thread holds 4 rows x 8 columns: 24 additions in registers, then 7 shuffles instead of
+// the 31 of transpose_reduce32.  Returns the sum of column tmem_reduce_col(lane) -- note the permutation.
+__device__ __forceinline__ int tmem_reduce_col(int lane) { return (lane & 24) | ((lane & 3) << 1) | ((lane >> 2) & 1); }
+__device__ __forceinline__ float tmem_transpose_reduce32(uint32_t taddr, const float (&p)[32], int lane) {
+    uint32_t u[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) u[i] = __float_as_uint(p[i]);
+    tmem_st32(taddr, u);
+    tmem_st_wait();
+    uint32_t v0[16], v1[16];
+    tmem_ld_16x256b_x4_nowait(taddr, v0);
+    tmem_ld_16x256b_x4_nowait(taddr + (16u << 16), v1);
+    tmem_ld_wait();
+    float s[8];                                    // s[2 b + e]: rows = lane / 4 (mod 8), column 8 b + 2 (lane % 4) + e
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+#pragma unroll
+        for (int e = 0; e < 2; e++)
+            s[2 * b + e] = (__uint_as_float(v0[4 * b + e]) + __uint_as_float(v0[4 * b + 2 + e])) +
+                           (__uint_as_float(v1[4 * b + e]) + __uint_as_float(v1[4 * b + 2 + e]));
+    {
+        const bool up = lane & 16;                 // keeps blocks b = 2, 3
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float send = up ? s[i] : s[i + 4], keep = up ? s[i + 4] : s[i];
+            s[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool up = lane & 8;                  // keeps the odd block of its pair
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const float send = up ? s[i] : s[i + 2], keep = up ? s[i + 2] : s[i];
+            s[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    const bool up = lane & 4;                      // keeps e = 1
+    const float send = up ? s[0] : s[1], keep = up ? s[1] : s[0];
+    return keep + __shfl_xor_sync(0xffffffffu, send, 4);
+}
 
 // ---------------------------------------------------------------- UMMA descriptors
 // K-major operand tile in shared memory, 128-byte swizzle: rows of 64 bf16 (128 B), 8-row groups 1024 B apart.

@@ -594,10 +594,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             float o = 0.f;                                   // knock-out experiment: no cross-lane reduction (wrong results)
 #pragma unroll
             for (int i = 0; i < 32; i++) o += v[i];
-#else
+            const int cl = lane;
+#elif defined(PG_TRIP_SHFL_EPILOGUE)
             const float o = transpose_reduce32(v, lane);
+            const int cl = lane;
+#else
+            // the weighted rows go back through the accumulator columns they came from (this lane quarter's own 32 columns:
+            // free until the next value LayerNorm's barrier) and return in the MMA-fragment shape: 7 shuffles instead of 31
+            // (default single-chunk instantiation only: the chunked one carries the on-line softmax state and would spill)
+            constexpr bool SHFL = MULTI || KF16;
+            const float o = SHFL ? transpose_reduce32(v, lane) : tc::tmem_transpose_reduce32(outV + lane_base + cq * 32, v, lane);
+            const int cl = SHFL ? lane : tc::tmem_reduce_col(lane);        // cl >> 3 == lane >> 3: the lane's head does not change
 #endif
-            const int c = cq * 32 + lane;
+            const int c = cq * 32 + cl;
             if (!MULTI) {
 #if defined(PG_TRIP_EXP) && (PG_TRIP_EXP & 4)
                 if (prev_valid && o == 123.456f) a.hb[(size_t)prev_eji * 128 + c] += o + sB2[128 + c];   // knock-out: no h_bond update
