@@ -367,11 +367,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
                 // segment softmax across the 32 lanes on the REDUX unit (max; fixed-point sums of values in [0, 1]) instead
                 // of three 5-round shuffle butterflies: the dependent shuffle chains were a quarter of the tile time
                 float sw[4];
+#if defined(PG_KNN_EXP) && (PG_KNN_EXP & 1)
+#pragma unroll
+                for (int h = 0; h < 4; h++) { al[h] = prow ? tc::ex2_approx(al[h] * 1e-3f) * 0.03f * ew : 0.f; sw[h] = al[h]; }     // knock-out: no reductions (wrong results)
+                if (false)
+#endif
 #pragma unroll
                 for (int h = 0; h < 4; h++) {
                     const float mx = tc::warp_max_redux(al[h]);
                     al[h] = prow ? tc::ex2_approx(al[h] - mx) : 0.f;
                 }
+#if !(defined(PG_KNN_EXP) && (PG_KNN_EXP & 1))
 #pragma unroll
                 for (int h = 0; h < 4; h++) {
                     const float sm = tc::warp_sum01_redux(al[h]);
@@ -379,6 +385,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
                 }
 #pragma unroll
                 for (int h = 0; h < 4; h++) sw[h] = tc::warp_sum01_redux(al[h]);
+#endif
                 KTRACE(0, 12);
                 if (prow) st4(a.alpha + (size_t)(psg.e0 + lane) * 16 + cq * 4, make_float4(al[0], al[1], al[2], al[3]));
                 if (psg.valid && lane == 0) st4(a.alpha_sum + (size_t)psg.v * 16 + cq * 4, make_float4(sw[0], sw[1], sw[2], sw[3]));
@@ -447,8 +454,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
             const float* ps = a.nc.A + (PASS == 0 ? a.nc.src_k : a.nc.src_v) + c0 + ch;
             float4 u[8];
 #pragma unroll
+#if defined(PG_KNN_EXP) && (PG_KNN_EXP & 2)
+            for (int i = 0; i < 8; i++) u[i] = make_float4(0.1f * i, 0.2f, 0.3f * lane, 0.4f);      // knock-out: no gather (wrong results)
+            const float4 d4 = make_float4(0.f, 1.f, 0.f, -1.f); (void)ps;
+#else
             for (int i = 0; i < 8; i++) u[i] = ldg4(ps + (size_t)__shfl_sync(PG_FULL, myidx, i * 4 + sr) * a.nc.lda);
             const float4 d4 = ldg4(a.nc.A + (size_t)sg.v * a.nc.lda + (PASS == 0 ? a.nc.dst_k : a.nc.dst_v) + c0 + ch);
+#endif
             // this tile's post-processing inputs (consumed one iteration later) and the next tile's neighbour indices
             float4 nf = make_float4(0.f, 0.f, 0.f, 0.f);
             float nfs = 0.f;
