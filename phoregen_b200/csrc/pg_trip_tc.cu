@@ -8,8 +8,9 @@
 // indicator] x [Wa ; R rows of the tile] + one-hot(l) x P rows, so the row warps never touch P or R.
 //
 // Roles: 16 row warps, thread = (row, 32-channel quarter), warp w -> lane quarter w & 3, channel quarter w >> 2 (four row
-//        warps per scheduler); warp 16 issues every MMA and the cp.async / bulk copies; warps 17-19 compute the angular
-//        features of the tiles ahead.  setmaxnreg moves registers from the auxiliary warpgroup to the row warps (104 / 64).
+//        warps per scheduler); warp 16 issues every MMA and does nothing else; warp 17 requests the next tile's query rows
+//        (cp.async), R rows and P images (bulk copies); warps 18-19 compute the angular features of the tiles ahead.
+//        setmaxnreg moves registers from the auxiliary warpgroup to the row warps (104 / 64).
 //
 //   1. angular encoding (11 distinct values per triplet; sin/cos of the angle itself occur twice in the reference's encoding
 //      and their weight rows are summed at pack time) + a 1.0 in column 11 + segment slot -> bf16 hi/lo A tile in smem
@@ -24,8 +25,9 @@
 //   3. second Linear of the key and value MLPs: A from TMEM, B = W2 (bf16 hi/lo, resident in smem, 128B swizzle),
 //      24 tcgen05.mma (M128 N128 K16) each, fp32 accumulators in TMEM.
 //   4. logits = q . k per head (thread-local dot; the key bias is softmax-invariant and dropped), segment softmax across
-//      the 32 lanes on the REDUX unit, alpha-weighted sum of v over the lanes with a butterfly transpose-reduce, residual
-//      add into h_bond.
+//      the 32 lanes on the REDUX unit, alpha-weighted sum of v over the lanes (through TMEM: the weighted rows return in
+//      the 16x256b fragment shape, 7 shuffles; butterfly transpose-reduce in the chunked instantiation), residual add
+//      into h_bond.
 //
 // Software pipeline across tiles: the row warps run  LN-k(t) | epilogue(t-1) | LN-v(t) | logits(t)  while the tensor pipe
 // runs  W2k(t), angle-k(t+1) | W2v(t), angle-v(t+1).  The four 128-column TMEM blocks alternate roles per tile (pre/out of
