@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bond_tc_kernel(BondTcArgs a) {
                 for (int h = 0; h < 4; h++) ssum[h] = tc::warp_sum01_redux(al[h]);   // every lane takes part in the reduction
                 if (!MULTI) {
 #pragma unroll
-                    for (int h = 0; h < 4; h++) al[h] = rowvalid ? al[h] * __frcp_rn(ssum[h]) : 0.f;
+                    for (int h = 0; h < 4; h++) al[h] = rowvalid ? al[h] * tc::rcp_approx(ssum[h]) : 0.f;
                 } else {
                     // (max, sum) of every chunk of the segment -> global max M and sum L; alpha = p 2^(m - M) / L
                     float* ex = sEx + (cq * 4 + wq) * 8;

@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
 #pragma unroll
                 for (int h = 0; h < 4; h++) {
                     const float sm = tc::warp_sum01_redux(al[h]);
-                    al[h] = prow ? al[h] * __frcp_rn(sm) * ew : 0.f;      // e_w is a sigmoid: alpha' stays in [0, 1]
+                    al[h] = prow ? al[h] * tc::rcp_approx(sm) * ew : 0.f;      // e_w is a sigmoid: alpha' stays in [0, 1]
                 }
 #pragma unroll
                 for (int h = 0; h < 4; h++) sw[h] = tc::warp_sum01_redux(al[h]);

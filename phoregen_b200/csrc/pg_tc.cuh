@@ -352,6 +352,13 @@ __device__ __forceinline__ float warp_sum01_redux(float x) {
     asm volatile("redux.sync.add.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(q));
     return (float)r * (1.0f / 8388608.0f);
 }
+// 1 / x for the softmax denominators (x >= 1: the row with the maximum contributes 2^0): one MUFU instead of the
+// ~8 instructions of the correctly rounded __frcp_rn; 1 ulp.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));

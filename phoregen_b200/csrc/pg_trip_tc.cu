@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
                         al[h] = rowvalid ? tc::ex2_approx(al[h] - mx) : 0.f;
                     }
 #pragma unroll
-                    for (int h = 0; h < 4; h++) al[h] *= __frcp_rn(tc::warp_sum01_redux(al[h]));
+                    for (int h = 0; h < 4; h++) al[h] *= tc::rcp_approx(tc::warp_sum01_redux(al[h]));
                 } else {
                     float mx[4], sm[4];
 #pragma unroll
@@ -722,7 +722,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
 #pragma unroll
                         for (int h = 0; h < 4; h++) sm[h] += __shfl_xor_sync(PG_FULL, sm[h], o);
 #pragma unroll
-                    for (int h = 0; h < 4; h++) al[h] *= __frcp_rn(sm[h]);
+                    for (int h = 0; h < 4; h++) al[h] *= tc::rcp_approx(sm[h]);
                 }
                 }
             }

@@ -51,7 +51,7 @@ def src(fl):
             return src_cache[p][ln - 1].strip()[:110]
     return ""
 print("| samples | % | warp instr | SASS | line | source |\n|---:|---:|---:|---:|---|---|")
-for fl, (s, e, c) in sorted(agg.items(), key=lambda x: -x[1][0])[:top]:
+for fl, (s, e, c) in sorted(agg.items(), key=lambda x: -x[1][int(os.environ.get("SORT", 0))])[:top]:
     print(f"| {s} | {100.0 * s / max(tot_s, 1):.1f} | {e} | {c} | {fl[0] + ':' + str(fl[1]) if fl else '?'} | `{src(fl)}` |")
 # optional: SASS context of one source line (env LINE=file:line)
 if os.environ.get("LINE"):
