@@ -44,7 +44,7 @@ src_cache = {}
 def src(fl):
     if fl is None: return ""
     f, ln = fl
-    for d in ("phoregen_b200/csrc", "include"):
+    for d in (os.environ.get("SRCDIR", "phoregen_b200/csrc"), "include"):
         p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), d, f)
         if os.path.exists(p):
             if p not in src_cache: src_cache[p] = open(p).read().split("\n")
