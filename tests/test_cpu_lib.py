@@ -155,3 +155,25 @@ def test_mma_issue_stays_on_the_uniform_datapath():
     assert counts, "no tensor-core kernels found in the library"
     assert all(c[0] > 0 for c in counts.values())                      # tcgen05.mma present in every one of them
     assert sum(c[1] for c in counts.values()) == 0, {k: v for k, v in counts.items() if v[1]}
+
+
+def test_triplet_kernel_keeps_its_register_budget():
+    """trip_tc_kernel runs 640 threads per SM at 96 registers (row warps 104 after setmaxnreg); every instantiation must fit
+    without spilling (a spilled value turns an asynchronous TMEM / global load into a blocking one in the row warps' loop).
+    ptxas' stack frame of these kernels is 16 bytes with no spill; a spill shows up as a larger frame."""
+    import re
+    import shutil
+    import subprocess
+    from phoregen_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump) and not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-res-usage", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout.splitlines()
+    seen = 0
+    for i, line in enumerate(out):
+        if "Function" in line and "trip_tc_kernel" in line:
+            m = re.search(r"REG:(\d+) STACK:(\d+)", out[i + 1])
+            assert m, out[i + 1]
+            assert int(m.group(1)) <= 96 and int(m.group(2)) <= 16, (line.strip(), out[i + 1].strip())
+            seen += 1
+    assert seen == 6          # {single-chunk, chunked} x {bf16x3, fp16, fp16 hi/lo} key paths
