@@ -79,6 +79,42 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
         : "memory");
 #endif
 }
+// The same for the LONG waits of warps that run ahead of the critical path (loader, feature warps): the warp sleeps
+// between polls, so it takes neither issue slots nor shared-memory cycles (every try_wait is a shared-memory access)
+// from the row warps that share its scheduler.
+__device__ __forceinline__ void mbar_wait_wd_sleep(uint64_t* bar, uint32_t parity) {
+#ifdef PG_NO_WATCHDOG
+    mbar_wait_sleep(bar, parity);
+#else
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .u32 polls, m;\n\t"
+        ".reg .u64 t0, t1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "mov.u32 polls, 0;\n\t"
+        "mov.u64 t0, 0;\n\t"
+        "WAIT_LOOP:\n\t"
+        "nanosleep.u32 64;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "add.u32 polls, polls, 1;\n\t"
+        "and.b32 m, polls, 0xfff;\n\t"
+        "setp.ne.u32 q, m, 0;\n\t"
+        "@q bra WAIT_LOOP;\n\t"
+        "mov.u64 t1, %%globaltimer;\n\t"
+        "setp.eq.u64 q, t0, 0;\n\t"
+        "@q mov.u64 t0, t1;\n\t"
+        "sub.u64 t1, t1, t0;\n\t"
+        "setp.lt.u64 q, t1, 10000000000;\n\t"
+        "@q bra WAIT_LOOP;\n\t"
+        "trap;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+#endif
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

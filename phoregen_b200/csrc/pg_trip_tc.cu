@@ -435,14 +435,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             TileIter nx = it;
             iter_next<MULTI>(d, nx);
             const bool newu = nx.valid && nx.stage != it.stage;     // the staged P rows change with the next tile
-            tc::mbar_wait_wd(&bars[B_HIDK], ph);                    // the P_k image, the R_k rows and query buffer (t+1)&1 are free
+            tc::mbar_wait_wd_sleep(&bars[B_HIDK], ph);              // the P_k image, the R_k rows and query buffer (t+1)&1 are free
             if (nx.valid) { load_q(nx, (tcount + 1) & 1); load_r(nx, 0); }
             if (newu) load_ps(nx, 0);
             if (nx.valid) {
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
                 tc::mbar_arrive(&bars[(tcount + 1) & 1 ? B_FEAT1 : B_FEAT0]);
             }
-            tc::mbar_wait_wd(&bars[B_HIDV], ph);
+            tc::mbar_wait_wd_sleep(&bars[B_HIDV], ph);
             if (nx.valid) load_r(nx, 1);
             if (newu) load_ps(nx, 1);
             it = nx; tcount++;
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trip_tc_kernel(TripTcArgs a) {
             TileIter nx = it;
             iter_next<MULTI>(d, nx);
             // operand buffer (s+1)&1 was last read by the value-side angle MMA of tile s-1
-            if (s >= 1) tc::mbar_wait_wd(&bars[(s - 1) & 1 ? B_PREV1 : B_PREV0], ((s - 1) >> 1) & 1);
+            if (s >= 1) tc::mbar_wait_wd_sleep(&bars[(s - 1) & 1 ? B_PREV1 : B_PREV0], ((s - 1) >> 1) & 1);
             if (nx.valid) {
                 if (nx.u != it.u) { xb ^= 1; stage_x(nx, xb); }
                 features(nx, xb, s + 1);
