@@ -24,8 +24,13 @@
 __device__ long long g_knn_trace[2 * 64 * 16];
 extern "C" int pg_debug_knn_trace(long long* h_out) { return cudaMemcpyFromSymbol(h_out, g_knn_trace, sizeof(g_knn_trace)) == cudaSuccess ? 0 : -2; }
 #define KTRACE(role, slot) do { if (PASS == 0 && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 16) && tcount < 64) g_knn_trace[((role) * 64 + tcount) * 16 + (slot)] = clock64(); } while (0)
+// per row warp: 0 loop top, 1 PRE wait done, 2 HID arrival, 3 post-processing done
+__device__ long long g_knn_wtrace[16 * 64 * 4];
+extern "C" int pg_debug_knn_wtrace(long long* h_out) { return cudaMemcpyFromSymbol(h_out, g_knn_wtrace, sizeof(g_knn_wtrace)) == cudaSuccess ? 0 : -2; }
+#define KWTRACE(slot) do { if (PASS == 0 && blockIdx.x == 0 && lane == 0 && tcount < 64) g_knn_wtrace[(warp * 64 + tcount) * 4 + (slot)] = clock64(); } while (0)
 #else
 #define KTRACE(role, slot) do {} while (0)
+#define KWTRACE(slot) do {} while (0)
 #endif
 
 namespace {
@@ -447,6 +452,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
         for (long long tile = tile_begin; tile < ntiles; tile++, ph ^= 1, tcount++) {
             const bool rowvalid = sg.valid && lane < sg.R;
             KTRACE(0, 0);
+            KWTRACE(0);
             // ---- gather the src-node partial rows: 8 lanes cover the 128-byte slice of one row (coalesced), the dst-node
             //      partial is added in that layout, and the rows are transposed to row-per-lane through the warp's shared
             //      tile (two rounds of 16 rows).  Neighbour indices were fetched one tile ahead.
@@ -504,6 +510,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
             tc::mbar_wait(&bars[B_PRE], ph);
             tc::tc_fence_after();
             KTRACE(0, 3);
+            KWTRACE(1);
             {
                 uint32_t xu[32];
                 tc::tmem_ld32_nowait(tmem + C_PRE + lane_base + cq * 32, xu);
@@ -578,9 +585,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(KnnTcArgs a) {
             tc::tc_fence_before();
             tc::mbar_arrive(&bars[B_HID]);
             KTRACE(0, 5);
+            KWTRACE(2);
             // ---- post-processing of the previous tile while the tensor pipe works on this one
             if (any) { asm volatile("cp.async.wait_group 1;" ::: "memory"); __syncwarp(); post(ph ^ 1, ph ^ 1, false); }
             KTRACE(0, 6);
+            KWTRACE(3);
             psg = sg; prow = rowvalid; pf = nf; pfs = nfs;
             if (PASS == 1 && POS) {
                 const int s = rowvalid ? a.knn_src[sg.e0 + lane] : sg.v;

@@ -22,3 +22,16 @@ for tile in range(8, 16):
         row = t[role, tile]
         print(f"tile {tile} {name}: " + " ".join(f"{(int(v) - int(base)) if v else -1:>7d}" for v in row[:15]))
     print()
+
+# per row warp (warp = 4 * channel quarter + lane quarter): loop top | PRE wait done | HID arrival | post-processing done
+wb = np.zeros(16 * 64 * 4, dtype=np.int64)
+fn2 = getattr(_lib.lib, "pg_debug_knn_wtrace", None)
+if fn2 is not None:
+    fn2.restype = ctypes.c_int; fn2.argtypes = [ctypes.c_void_p]
+    assert fn2(wb.ctypes.data) == 0
+    w = wb.reshape(16, 64, 4)
+    for tile in range(10, 14):
+        print(f"tile {tile}: per-warp stamps relative to warp 0's loop top")
+        b0 = int(w[0, tile, 0])
+        for wi in range(16):
+            print(f"  warp {wi:2d} (wq {wi & 3}, cq {wi >> 2}): " + " ".join(f"{int(v) - b0:>7d}" for v in w[wi, tile]))
